@@ -1,0 +1,126 @@
+"""`BatchedSim`: R lock-stepped road-network replicas on one GPU (thin ctypes shim over libtsc).
+
+PyTorch is used only as the owner of device buffers and streams; all simulation work happens in
+the hand-written kernel `tsc_step_kernel` (csrc/tsc_sim.cu).  Replaces, for R replicas at once,
+what reference envs/env.py does against one SUMO process: `reset` (:544-561), `step` (:566-631),
+`update_fingerprint` (:633-635) and the detector reads (:325-407).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .net.tables import EnvParams, NetTables
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+class BatchedSim:
+    def __init__(self, net: NetTables, params: EnvParams, n_replicas: int, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedSim needs a CUDA device (no CPU fallback exists)")
+        self.net, self.params, self.R = net, params, int(n_replicas)
+        self.device = torch.device("cuda", device)
+        self._cnet, self._ccfg = net.as_c(), params.as_c()
+        h = C.c_void_p()
+        _lib.check(_lib.lib().tsc_create(C.byref(self._cnet), C.byref(self._ccfg), C.c_int32(self.R),
+                                         C.c_int32(device), C.byref(h)))
+        self._h = h
+        N = net.n_nodes
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros(self.R, net.n_obs, dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(self.R, N, dtype=torch.float32, device=self.device)
+            self.greward = torch.zeros(self.R, dtype=torch.float32, device=self.device)
+            self.done = torch.zeros(self.R, dtype=torch.uint8, device=self.device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().tsc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- control -------------------------------------------------------------------------
+    def reset(self, seeds) -> None:
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        assert seeds.shape == (self.R,)
+        _lib.check(_lib.lib().tsc_reset(self._h, _np(seeds, C.c_uint64), self._stream()))
+
+    def set_train_mode(self, train: bool) -> None:
+        _lib.check(_lib.lib().tsc_set_train_mode(self._h, C.c_int32(int(train))))
+
+    def observe(self, fp: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _lib.check(_lib.lib().tsc_observe(self._h, _ptr(fp), _ptr(self.obs), self._stream()))
+        return self.obs
+
+    def step(self, action: torch.Tensor, fp: Optional[torch.Tensor] = None):
+        """action int32 [R, n_nodes] on the device; fp float32 [R, n_nodes, max_na] or None.
+        Returns views of the persistent output tensors (obs, reward, global_reward, done)."""
+        assert action.dtype == torch.int32 and action.is_cuda and action.is_contiguous()
+        assert action.numel() == self.R * self.net.n_nodes
+        if fp is not None:
+            assert fp.dtype == torch.float32 and fp.is_contiguous()
+            assert fp.numel() == self.R * self.net.n_nodes * self.net.max_na
+        _lib.check(_lib.lib().tsc_step(self._h, _ptr(action), _ptr(fp), _ptr(self.obs), _ptr(self.reward),
+                                       _ptr(self.greward), _ptr(self.done), self._stream()))
+        return self.obs, self.reward, self.greward, self.done
+
+    def step_host(self, action: np.ndarray, fp: Optional[np.ndarray] = None):
+        """Host-buffer entry point (`tsc_step_host`): numpy in, numpy out, copies included."""
+        n = self.net
+        action = np.ascontiguousarray(action, np.int32).reshape(self.R, n.n_nodes)
+        fp = None if fp is None else np.ascontiguousarray(fp, np.float32)
+        if not hasattr(self, "_h_out"):
+            self._h_out = (np.zeros((self.R, n.n_obs), np.float32), np.zeros((self.R, n.n_nodes), np.float32),
+                           np.zeros(self.R, np.float32), np.zeros(self.R, np.uint8))
+        obs, reward, greward, done = self._h_out
+        _lib.check(_lib.lib().tsc_step_host(self._h, _np(action, C.c_int32), _np(fp, C.c_float),
+                                            _np(obs, C.c_float), _np(reward, C.c_float),
+                                            _np(greward, C.c_float), _np(done, C.c_uint8), self._stream()))
+        return obs, reward, greward, done
+
+    # ---- parity taps ---------------------------------------------------------------------
+    def counts(self):
+        n = self.net
+        veh = torch.zeros(self.R, n.n_det, dtype=torch.int32, device=self.device)
+        halt, wait = torch.zeros_like(veh), torch.zeros_like(veh)
+        phase = torch.zeros(self.R, n.n_nodes, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().tsc_get_counts(self._h, _ptr(veh), _ptr(halt), _ptr(wait), _ptr(phase),
+                                             self._stream()))
+        return veh, halt, wait, phase
+
+    def dump_state(self, replica: int = 0):
+        n = self.net
+        cnt = np.zeros(n.n_lanes, np.int32)
+        veh = np.zeros((n.n_slots, 4), np.uint32)
+        nv = C.c_int32(0)
+        _lib.check(_lib.lib().tsc_dump_state(self._h, C.c_int32(replica), _np(cnt, C.c_int32),
+                                             _np(veh, C.c_uint32), C.byref(nv)))
+        return cnt, veh[:nv.value].copy()
+
+    def mean_live(self) -> float:
+        v = C.c_double(0)
+        _lib.check(_lib.lib().tsc_mean_live(self._h, C.byref(v)))
+        return v.value
+
+    def info(self):
+        sb, tpb, sm = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        _lib.check(_lib.lib().tsc_info(self._h, C.byref(sb), C.byref(tpb), C.byref(sm)))
+        return dict(state_bytes_per_replica=sb.value, threads_per_block=tpb.value, smem_bytes=sm.value)

@@ -296,8 +296,11 @@ def build_obs_program(net: NetTables, agent: str, coop_gamma: float, use_wait: b
                     kinds.append(2); idxs.append(j * net.max_na + a); scales.append(1.0)
                     n_f += 1
         obs_off.append(len(kinds))
-        n_s_ls.append(len(kinds) - k0)
-        n_w_ls.append(n_w)
+        # declared dims follow envs/env.py:303-323 literally: the wait block is counted whenever
+        # 'wait' is a state name, even for the greedy agent whose state omits it (:171-172)
+        n_w_decl = len(own) if use_wait else 0
+        n_s_ls.append(len(kinds) - k0 + (n_w_decl - n_w))
+        n_w_ls.append(n_w_decl)
         n_f_ls.append(n_f)
     net.obs_kind = np.array(kinds, dtype=np.int32)
     net.obs_idx = np.array(idxs, dtype=np.int32)

@@ -24,3 +24,42 @@ class LargeGridController:
 
     def greedy(self, ob, node_name):
         return int(self.forward([ob])[0])
+
+
+from .env import PhaseMap, PhaseSet, TrafficSimulator        # noqa: E402
+from ..net import large_grid as _grid                         # noqa: E402
+
+
+class LargeGridPhase(PhaseMap):                               # envs/large_grid_env.py:38-42
+    def __init__(self):
+        self.phases = {PHASE_NUM: PhaseSet(list(_grid.PHASES))}
+
+
+class LargeGridEnv(TrafficSimulator):
+    """Drop-in for reference envs/large_grid_env.py:63-223: same constructor
+    `LargeGridEnv(config['ENV_CONFIG'], port=0, output_path='', is_record=False, record_stat=False)`;
+    `n_replicas`/`device` are extensions (default 1 replica = the reference's behaviour)."""
+
+    def __init__(self, config, port=0, output_path='', is_record=False, record_stat=False,
+                 n_replicas=1, device=0):
+        self.peak_flow1 = config.getint('peak_flow1')
+        self.peak_flow2 = config.getint('peak_flow2')
+        self.init_density = config.getfloat('init_density')
+        if self.init_density > 0:
+            raise NotImplementedError('init_density > 0 (large_grid/data/build_file.py:223-266) is not supported; '
+                                      'every shipped config uses 0')
+        super().__init__(config, output_path, is_record, record_stat, port=port,
+                         n_replicas=n_replicas, device=device)
+
+    def _get_node_phase_id(self, node_name):
+        return PHASE_NUM
+
+    def _init_map(self):                                       # envs/large_grid_env.py:209-215
+        self.neighbor_map = _grid.large_neighbor_map()
+        self.phase_map = LargeGridPhase()
+        self.state_names = STATE_NAMES
+
+    def _build_tables(self):
+        return _grid.build_large_grid(self.peak_flow1, self.peak_flow2, agent=self.agent,
+                                      coop_gamma=self.coop_gamma, use_wait='wait' in self.state_names,
+                                      episode_length_sec=self.episode_length_sec)

@@ -1,0 +1,240 @@
+"""`BatchedA2C`: all A per-intersection actor-critics, R replicas at once, on one GPU.
+
+Device-side counterpart of reference agents/models.py (IA2C/MA2C) + agents/policies.py
+(LstmACPolicy / FPLstmACPolicy) + agents/utils.py (OnPolicyBuffer).  Semantics kept:
+  * two separate LSTM networks per agent, state zeroed inside the cell on a pre-decision done
+    (agents/utils.py:104-105); 'v'-only forward does not advance the state (agents/policies.py:127-135);
+  * BPTT over n_step from `states_bw`, refreshed from `states_fw` after each update (:153);
+  * loss of agents/policies.py:41-52, per-agent clip_by_global_norm, TF1 RMSProp (:54-61);
+  * n-step returns of OnPolicyBuffer (agents/utils.py:202-214), reward /= reward_norm then clip
+    (agents/models.py:222-229).
+Replicas share the weights: the gradient is the mean over replicas (and over ranks: one
+`all_reduce(SUM)` of the flat gradient per update, then identical updates everywhere).
+
+Hand-written kernels (csrc/tsc_learn.cu) do the fc front end, the LSTM sequence forward/backward
+with the cell fused, heads + sampling, loss gradients, returns and clip+RMSProp.  The three plain
+batched GEMMs (X.Wx, dZ.Wx^T, [X|H]^T.dZ) go through cuBLAS (`torch.baddbmm/bmm`) this round.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .layout import PolicyLayout
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedA2C:
+    def __init__(self, layout: PolicyLayout, n_replicas: int, n_step: int, gamma: float = 0.99,
+                 v_coef: float = 0.5, max_grad_norm: float = 40.0, alpha: float = 0.99, eps: float = 1e-5,
+                 reward_norm: float = 1.0, reward_clip: float = 0.0, seed: int = 0, device: int = 0,
+                 chunk: int = 1024, replica0: int = 0, total_replicas: Optional[int] = None,
+                 process_group=None, allow_tf32: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedA2C needs a CUDA device (no CPU fallback exists)")
+        self.lay, self.R, self.T = layout, int(n_replicas), int(n_step)
+        self.gamma, self.v_coef, self.max_grad_norm = gamma, v_coef, max_grad_norm
+        self.alpha, self.eps = alpha, eps
+        self.reward_norm, self.reward_clip = reward_norm, reward_clip
+        self.seed, self.replica0 = int(seed), int(replica0)
+        self.total_replicas = int(total_replicas or n_replicas)
+        self.pg = process_group
+        self.allow_tf32 = allow_tf32
+        self.dev = torch.device("cuda", device)
+        self.chunk = min(int(chunk), self.R)
+        lib = _lib.lib()
+        self._cd = layout.as_c()
+        h = C.c_void_p()
+        _lib.check(lib.tscl_create(C.byref(self._cd), C.c_int32(device), C.byref(h)))
+        self._h = h
+        L, R, T, U, A = layout, self.R, self.T, layout.U, layout.A
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.P = torch.from_numpy(layout.init_params(seed)).to(self.dev)
+        self.G = torch.zeros_like(self.P)
+        self.MS = torch.ones_like(self.P)                      # TF1 RMSProp slot "rms" starts at 1
+        self.agent_of = torch.from_numpy(layout.agent_of).to(self.dev)
+        self.norms = torch.zeros(A, **f32)
+        self.stats = torch.zeros(4, **f32)
+        self.pv, self.gv = layout.views(self.P), layout.views(self.G)
+        # recurrent state: [U][R][h] each
+        self.c_fw = torch.zeros(U, R, L.h, **f32); self.h_fw = torch.zeros(U, R, L.h, **f32)
+        self.c_bw = torch.zeros_like(self.c_fw); self.h_bw = torch.zeros_like(self.h_fw)
+        self.c_tmp = torch.zeros_like(self.c_fw); self.h_tmp = torch.zeros_like(self.h_fw)
+        # per-step work buffers
+        self.X1 = torch.empty(U, R, L.dx, **f32)
+        self.Z1 = torch.empty(U, R, 4 * L.h, **f32)
+        self.H1 = torch.empty(U, R, L.h, **f32)
+        self.pi = torch.zeros(R, A, L.max_na, **f32)
+        self.val = torch.zeros(R, A, **f32)
+        self.act = torch.zeros(R, A, dtype=torch.int32, device=self.dev)
+        self.boot = torch.zeros(R, A, **f32)
+        # rollout storage; obs slot t is what forward consumed at step t, slot T is the next obs
+        self.obs_hist = torch.zeros(T + 1, R, L.n_obs, **f32)
+        self.act_hist = torch.zeros(T, R, A, dtype=torch.int32, device=self.dev)
+        self.rew_hist = torch.zeros(T, R, A, **f32)
+        self.val_hist = torch.zeros(T, R, A, **f32)
+        self.Rs = torch.zeros(T, R, A, **f32); self.Adv = torch.zeros(T, R, A, **f32)
+        self.done_pre = [0.0] * T
+        self.done_post = [0.0] * T
+        self.last_done = False      # OnPolicyBuffer.reset(done) carries the last done (agents/utils.py:187-193)
+        self.t = 0
+        self.n_forward = 0
+        self._one = torch.zeros(1, **f32)
+        self._upd_bufs = None
+        self.kernel_launches = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().tscl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _st(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _mm(self):
+        # cuBLAS fp32 (or TF32 when allowed) for the plain batched GEMMs
+        torch.backends.cuda.matmul.allow_tf32 = bool(self.allow_tf32)
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self):
+        """model.reset(): zero the LSTM states (agents/models.py:218-220, policies.py:120-123)."""
+        for t in (self.c_fw, self.h_fw, self.c_bw, self.h_bw):
+            t.zero_()
+
+    def forward(self, obs: torch.Tensor, done: bool, out_type: str = "pv", sample: bool = True):
+        """One decision for all replicas/agents.  obs [R, n_obs] device tensor.  Returns
+        (pi [R, A, max_na], val [R, A], act [R, A] or None); 'v' does not advance the state."""
+        L, R, lib = self.lay, self.R, _lib.lib()
+        self._mm()
+        commit = "p" in out_type
+        dflag = self._one.fill_(1.0 if done else 0.0)
+        _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs), C.c_int64(R), C.c_int64(R), C.c_int64(0),
+                                     _p(self.X1), self._st()))
+        torch.baddbmm(self.pv["bl"].unsqueeze(1), self.X1, self.pv["wx"], out=self.Z1)
+        c1, h1 = (self.c_fw, self.h_fw) if commit else (self.c_tmp, self.h_tmp)
+        _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(self.Z1), None, _p(self.H1), _p(self.c_fw),
+                                         _p(self.h_fw), _p(c1), _p(h1), _p(dflag), C.c_int32(1), C.c_int64(R),
+                                         C.c_int64(R), C.c_int64(0), self._st()))
+        want_act = sample and commit
+        _lib.check(lib.tscl_heads(self._h, _p(self.P), _p(self.H1), C.c_int64(R), _p(self.pi), _p(self.val),
+                                  _p(self.act) if want_act else None, C.c_uint64(self.seed),
+                                  C.c_int64(self.n_forward), C.c_int64(self.replica0), self._st()))
+        self.kernel_launches += 3
+        if commit:
+            self.n_forward += 1
+        return self.pi, self.val, (self.act if want_act else None)
+
+    # ------------------------------------------------------------------------------------------
+    def obs_slot(self, t: Optional[int] = None) -> torch.Tensor:
+        return self.obs_hist[self.t if t is None else t]
+
+    def add_transition(self, reward: torch.Tensor, done_pre: bool, done_post: bool):
+        """Record step t: obs must already be in obs_slot(t) (the env writes there), actions and
+        values are the ones of the last forward().  agents/models.py:222-229."""
+        t = self.t
+        r = reward
+        if self.reward_norm:
+            r = r / self.reward_norm
+        if self.reward_clip:
+            r = torch.clamp(r, -self.reward_clip, self.reward_clip)
+        self.rew_hist[t].copy_(r)
+        self.act_hist[t].copy_(self.act)
+        self.val_hist[t].copy_(self.val)
+        self.done_pre[t] = 1.0 if done_pre else 0.0
+        self.done_post[t] = 1.0 if done_post else 0.0
+        self.t += 1
+
+    def _bufs(self, rc):
+        L, T, U = self.lay, self.T, self.lay.U
+        if self._upd_bufs is None or self._upd_bufs["rc"] < rc:
+            M = T * rc
+            f32 = dict(dtype=torch.float32, device=self.dev)
+            self._upd_bufs = dict(rc=rc, X=torch.empty(U, M, L.dx, **f32), ZG=torch.empty(U, M, 4 * L.h, **f32),
+                                  C=torch.empty(U, M, L.h, **f32), H=torch.empty(U, M, L.h, **f32),
+                                  Hp=torch.empty(U, M, L.h, **f32), dH=torch.empty(U, M, L.h, **f32),
+                                  dX=torch.empty(U, M, L.dx, **f32), dlog=torch.empty(U, M, L.max_na, **f32))
+        return self._upd_bufs
+
+    def backward(self, boot: Optional[torch.Tensor], lr: float, beta: float):
+        """One A2C update from the stored n_step rollout (agents/models.py:174-183).  `boot` is the
+        bootstrap value [R, A] (None / zeros when the episode ended, utils.py:186-190)."""
+        assert self.t == self.T, "rollout buffer not full"
+        L, R, T, U, A, lib = self.lay, self.R, self.T, self.lay.U, self.lay.A, _lib.lib()
+        self._mm()
+        st = self._st
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        dpre = torch.tensor(self.done_pre, **f32)
+        dpost = torch.tensor(self.done_post, **f32)
+        if boot is None:
+            self.boot.zero_()
+        else:
+            self.boot.copy_(boot)
+        _lib.check(lib.tscl_returns(self._h, _p(self.rew_hist), _p(self.val_hist), _p(self.boot), _p(dpost),
+                                    C.c_float(self.gamma), C.c_int32(T), C.c_int64(R), _p(self.Rs), _p(self.Adv), st()))
+        self.G.zero_()
+        self.stats.zero_()
+        scale = 1.0 / (T * self.total_replicas)
+        keep = (1.0 - dpre).view(1, T, 1, 1)
+        n_obs = L.n_obs
+        for r0 in range(0, R, self.chunk):
+            rc = min(self.chunk, R - r0)
+            M = T * rc
+            b = self._bufs(rc)
+            if b["rc"] == rc:
+                X, ZG, Cc, H, Hp, dH, dX, dlog = (b[k] for k in ("X", "ZG", "C", "H", "Hp", "dH", "dX", "dlog"))
+            else:               # tail chunk: dense temporaries of the right shape
+                X, ZG, Cc, H, Hp, dH, dX, dlog = (torch.empty(U, M, s_, **f32) for s_ in
+                                                  (L.dx, 4 * L.h, L.h, L.h, L.h, L.h, L.dx, L.max_na))
+            obs0 = self.obs_hist[0, r0:]
+            _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs0), C.c_int64(M), C.c_int64(rc),
+                                         C.c_int64(R * n_obs), _p(X), st()))
+            torch.baddbmm(self.pv["bl"].unsqueeze(1), X, self.pv["wx"], out=ZG)
+            _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(H), _p(self.c_bw), _p(self.h_bw),
+                                             None, None, _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R),
+                                             C.c_int64(r0), st()))
+            _lib.check(lib.tscl_heads_loss(self._h, _p(self.P), _p(H), _p(self.act_hist[0, r0:]), _p(self.Rs[0, r0:]),
+                                           _p(self.Adv[0, r0:]), C.c_int64(M), C.c_int64(rc), C.c_int64(R * A),
+                                           C.c_float(self.v_coef), C.c_float(beta), C.c_float(scale), _p(dlog),
+                                           _p(dH), _p(self.stats), st()))
+            # head weight / bias gradients (plain batched GEMM + column sums)
+            self.gv["wo"].baddbmm_(H.transpose(1, 2), dlog)
+            self.gv["bo"].add_(dlog.sum(dim=1))
+            # h_{t-1} masked, the second operand of the recurrent weight gradient
+            Hp4, H4 = Hp.view(U, T, rc, L.h), H.view(U, T, rc, L.h)
+            Hp4[:, 1:].copy_(H4[:, :-1])
+            Hp4[:, 0].copy_(self.h_bw[:, r0:r0 + rc])
+            Hp4.mul_(keep)
+            _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
+                                             C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
+            dZ = ZG
+            self.gv["wx"].baddbmm_(X.transpose(1, 2), dZ)
+            self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)
+            self.gv["bl"].add_(dZ.sum(dim=1))
+            torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
+            _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
+                                       C.c_int64(R * n_obs), _p(self.G), st()))
+            self.kernel_launches += 5
+        if self.pg is not None:
+            torch.distributed.all_reduce(self.G, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        _lib.check(lib.tscl_clip_rmsprop(self._h, _p(self.P), _p(self.G), _p(self.MS), _p(self.agent_of),
+                                         C.c_float(self.max_grad_norm), C.c_float(lr), C.c_float(self.alpha),
+                                         C.c_float(self.eps), _p(self.norms), st()))
+        self.kernel_launches += 3
+        # states_bw <- states_fw (agents/policies.py:153); next rollout starts at slot 0
+        self.c_bw.copy_(self.c_fw); self.h_bw.copy_(self.h_fw)
+        self.obs_hist[0].copy_(self.obs_hist[T])
+        self.last_done = bool(self.done_post[-1])
+        self.t = 0

@@ -1,0 +1,739 @@
+// tsc_learn.cu — hand-written sm_100a kernels of the per-intersection A2C learner + C ABI
+// (include/tsc_learn.h).  fp32 storage and arithmetic (the reference is fp32 TF1).
+//
+//   fc_embed_kernel       relu(fc) front end of all 2A networks            agents/policies.py:191-201
+//   lstm_seq_fwd_kernel   T-step LSTM: recurrent GEMM h.Wh from smem + fused cell   agents/utils.py:88-116
+//   heads_kernel          softmax / value / categorical sampling           agents/policies.py:18-26, utils.py:155-157
+//   returns_kernel        n-step returns + advantages                      agents/utils.py:202-214
+//   heads_loss_kernel     A2C loss gradients at the heads                  agents/policies.py:41-52
+//   lstm_seq_bwd_kernel   BPTT: cell backward + dz.Wh^T from smem, carries in registers
+//   fc_bwd_kernel         front-end weight/bias gradients (ragged, tiny K)
+//   norm2_kernel / rmsprop_kernel   per-agent global-norm clip + TF1 RMSProp   agents/policies.py:54-61
+//
+// Layout conventions: unit u = 2*agent + net (0 = pi, 1 = V); time-major rows m = t*Rc + r.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tsc_learn.h"
+
+extern "C" const char* tsc_last_error(void);
+int tsc_set_error(const std::string& m);  // defined in tsc_sim.cu
+
+#define LCK(call)                                                                  \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) return tsc_set_error(std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define H64 64
+#define G4 256  // 4 * H64
+
+struct DDims {
+  int A, n_obs, max_na, fw, ff, ft, h, dx;
+  const int32_t *obs_off, *n_wave, *n_wait, *n_fp, *n_a;
+  const int64_t *off_fcw_w, *off_fcw_b, *off_fcf_w, *off_fcf_b, *off_fct_w, *off_fct_b;
+  int64_t off_wx, off_wh, off_bl, off_wo, off_bo, n_params;
+};
+
+struct tscl_handle {
+  int device = 0;
+  DDims d{};
+  std::vector<void*> owned;
+  int max_in = 0;      // max n_wave + n_wait + n_fp
+  int max_fcw = 0;     // max fc weight floats of a unit (incl. biases)
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ uint32_t lmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fc front end.  grid (ceil(M/64), 2A), 256 threads.
+#define FE_ROWS 64
+__global__ void __launch_bounds__(256)
+fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ obs, int64_t M,
+                int64_t rows_per_t, int64_t stride_t, float* __restrict__ X) {
+  extern __shared__ float sm[];
+  const int u = blockIdx.y, a = u >> 1, tid = threadIdx.x;
+  const int nw = d.n_wave[a], nt = d.n_wait[a], nf = d.ff > 0 ? d.n_fp[a] : 0;
+  const int n_in = nw + nt + nf;
+  float* sW = sm;                       // [nw][fw]
+  float* sF = sW + nw * d.fw;           // [nf][ff]
+  float* sT = sF + nf * d.ff;           // [nt][ft]
+  float* sB = sT + nt * d.ft;           // [dx]
+  float* sIn = sB + d.dx;               // [FE_ROWS][n_in]
+  for (int i = tid; i < nw * d.fw; i += 256) sW[i] = P[d.off_fcw_w[u] + i];
+  for (int i = tid; i < nf * d.ff; i += 256) sF[i] = P[d.off_fcf_w[u] + i];
+  for (int i = tid; i < nt * d.ft; i += 256) sT[i] = P[d.off_fct_w[u] + i];
+  for (int i = tid; i < d.fw; i += 256) sB[i] = P[d.off_fcw_b[u] + i];
+  for (int i = tid; i < d.ff; i += 256) sB[d.fw + i] = P[d.off_fcf_b[u] + i];
+  for (int i = tid; i < d.ft; i += 256) sB[d.fw + d.ff + i] = P[d.off_fct_b[u] + i];
+  const int64_t m0 = (int64_t)blockIdx.x * FE_ROWS;
+  const int ooff = d.obs_off[a];
+  for (int i = tid; i < FE_ROWS * n_in; i += 256) {
+    const int row = i / n_in, k = i - row * n_in;
+    const int64_t m = m0 + row;
+    float v = 0.f;
+    if (m < M) v = obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k];
+    sIn[i] = v;
+  }
+  __syncthreads();
+  const int dx = d.dx;
+  float* Xu = X + ((int64_t)u * M + m0) * dx;
+  for (int i = tid; i < FE_ROWS * dx; i += 256) {
+    const int row = i / dx, col = i - row * dx;
+    if (m0 + row >= M) break;
+    const float* in = sIn + row * n_in;
+    float acc = sB[col];
+    if (col < d.fw) {
+      for (int k = 0; k < nw; ++k) acc = fmaf(in[k], sW[k * d.fw + col], acc);
+    } else if (col < d.fw + d.ff) {
+      const int c = col - d.fw;
+      const float* inf_ = in + nw + nt;
+      for (int k = 0; k < nf; ++k) acc = fmaf(inf_[k], sF[k * d.ff + c], acc);
+    } else {
+      const int c = col - d.fw - d.ff;
+      const float* int_ = in + nw;
+      for (int k = 0; k < nt; ++k) acc = fmaf(int_[k], sT[k * d.ft + c], acc);
+    }
+    Xu[(int64_t)row * dx + col] = fmaxf(acc, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM sequence forward.  grid (ceil(Rc/32), 2A), 256 threads: thread (ty, tx) owns replicas
+// 4*ty .. 4*ty+3 and hidden units 2*tx, 2*tx+1 (all four gates), so the cell update is thread-local.
+#define LS_ROWS 32
+__global__ void __launch_bounds__(256)
+lstm_seq_fwd_kernel(const DDims d, const float* __restrict__ P, float* __restrict__ ZG, float* __restrict__ C,
+                    float* __restrict__ Hout, const float* __restrict__ c0, const float* __restrict__ h0,
+                    float* __restrict__ c1, float* __restrict__ h1, const float* __restrict__ done, int T,
+                    int64_t Rc, int64_t ld_state, int64_t r0) {
+  extern __shared__ float sm[];
+  float* sWh = sm;                 // [64][256]
+  float* sh = sm + H64 * G4;       // [32][64]
+  const int u = blockIdx.y, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5, j0 = 2 * tx;
+  const float* Wh = P + d.off_wh + (int64_t)u * H64 * G4;
+  for (int i = tid; i < H64 * G4 / 4; i += 256)
+    reinterpret_cast<float4*>(sWh)[i] = reinterpret_cast<const float4*>(Wh)[i];
+  const int64_t rbase = (int64_t)blockIdx.x * LS_ROWS;
+  float c[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t r = rbase + ty * 4 + q;
+    float2 cv = make_float2(0.f, 0.f), hv = make_float2(0.f, 0.f);
+    if (r < Rc) {
+      const int64_t s = ((int64_t)u * ld_state + r0 + r) * H64 + j0;
+      cv = *reinterpret_cast<const float2*>(c0 + s);
+      hv = *reinterpret_cast<const float2*>(h0 + s);
+    }
+    c[q][0] = cv.x; c[q][1] = cv.y;
+    *reinterpret_cast<float2*>(&sh[(ty * 4 + q) * H64 + j0]) = hv;
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const bool dn = done[t] != 0.f;
+    float acc[4][4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t r = rbase + ty * 4 + q;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float2 z = make_float2(0.f, 0.f);
+        if (r < Rc) z = *reinterpret_cast<const float2*>(ZG + (((int64_t)u * T + t) * Rc + r) * G4 + g * H64 + j0);
+        acc[q][g][0] = z.x; acc[q][g][1] = z.y;
+      }
+      if (dn) { c[q][0] = 0.f; c[q][1] = 0.f; }
+    }
+    if (!dn) {
+#pragma unroll 4
+      for (int k = 0; k < H64; ++k) {
+        float hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hv[q] = sh[(ty * 4 + q) * H64 + k];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float2 w = *reinterpret_cast<const float2*>(&sWh[k * G4 + g * H64 + j0]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[q][g][0] = fmaf(hv[q], w.x, acc[q][g][0]);
+            acc[q][g][1] = fmaf(hv[q], w.y, acc[q][g][1]);
+          }
+        }
+      }
+    }
+    __syncthreads();   // every read of sh for step t is done
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t r = rbase + ty * 4 + q;
+      float gi[2], gf[2], go[2], gu[2], hn[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        gi[e] = sigmoidf_(acc[q][0][e]); gf[e] = sigmoidf_(acc[q][1][e]);
+        go[e] = sigmoidf_(acc[q][2][e]); gu[e] = tanhf(acc[q][3][e]);
+        c[q][e] = gf[e] * c[q][e] + gi[e] * gu[e];
+        hn[e] = go[e] * tanhf(c[q][e]);
+      }
+      *reinterpret_cast<float2*>(&sh[(ty * 4 + q) * H64 + j0]) = make_float2(hn[0], hn[1]);
+      if (r < Rc) {
+        const int64_t m = ((int64_t)u * T + t) * Rc + r;
+        float* z = ZG + m * G4 + j0;
+        *reinterpret_cast<float2*>(z) = make_float2(gi[0], gi[1]);
+        *reinterpret_cast<float2*>(z + H64) = make_float2(gf[0], gf[1]);
+        *reinterpret_cast<float2*>(z + 2 * H64) = make_float2(go[0], go[1]);
+        *reinterpret_cast<float2*>(z + 3 * H64) = make_float2(gu[0], gu[1]);
+        if (C) *reinterpret_cast<float2*>(C + m * H64 + j0) = make_float2(c[q][0], c[q][1]);
+        if (Hout) *reinterpret_cast<float2*>(Hout + m * H64 + j0) = make_float2(hn[0], hn[1]);
+      }
+    }
+    __syncthreads();
+  }
+  if (c1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t r = rbase + ty * 4 + q;
+      if (r < Rc) {
+        const int64_t s = ((int64_t)u * ld_state + r0 + r) * H64 + j0;
+        *reinterpret_cast<float2*>(c1 + s) = make_float2(c[q][0], c[q][1]);
+        *reinterpret_cast<float2*>(h1 + s) = *reinterpret_cast<float2*>(&sh[(ty * 4 + q) * H64 + j0]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Heads of one control step.  grid (ceil(R/128), A), 128 threads, thread = replica.
+__global__ void __launch_bounds__(128)
+heads_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ Hs, int64_t R,
+             float* __restrict__ pi, float* __restrict__ val, int32_t* __restrict__ act, uint32_t seed_lo,
+             uint32_t seed_hi, uint32_t step, int64_t replica0) {
+  extern __shared__ float sm[];
+  const int a = blockIdx.y, tid = threadIdx.x, na = d.n_a[a], mna = d.max_na;
+  float* sWp = sm;                    // [64][mna]
+  float* sWv = sWp + H64 * mna;       // [64]
+  float* sb = sWv + H64;              // [mna + 1]
+  const float* Wp = P + d.off_wo + (int64_t)(2 * a) * H64 * mna;
+  const float* Wv = P + d.off_wo + (int64_t)(2 * a + 1) * H64 * mna;
+  for (int i = tid; i < H64 * mna; i += 128) sWp[i] = Wp[i];
+  for (int i = tid; i < H64; i += 128) sWv[i] = Wv[i * mna];
+  for (int i = tid; i < mna; i += 128) sb[i] = P[d.off_bo + (int64_t)(2 * a) * mna + i];
+  if (tid == 0) sb[mna] = P[d.off_bo + (int64_t)(2 * a + 1) * mna];
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * 128 + tid;
+  if (r >= R) return;
+  const float4* hp = reinterpret_cast<const float4*>(Hs + ((int64_t)(2 * a) * R + r) * H64);
+  const float4* hv = reinterpret_cast<const float4*>(Hs + ((int64_t)(2 * a + 1) * R + r) * H64);
+  float lg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) lg[j] = j < mna ? sb[j] : 0.f;
+  float v = sb[mna];
+  for (int k4 = 0; k4 < H64 / 4; ++k4) {
+    const float4 x = hp[k4], y = hv[k4];
+    const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k4 * 4 + e;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < mna) lg[j] = fmaf(xs[e], sWp[k * mna + j], lg[j]);
+      v = fmaf(ys[e], sWv[k], v);
+    }
+  }
+  float mx = -1e30f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) if (j < na) mx = fmaxf(mx, lg[j]);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { lg[j] = j < na ? __expf(lg[j] - mx) : 0.f; s += lg[j]; }
+  const float inv = 1.0f / s;
+  float* po = pi + ((int64_t)r * d.A + a) * mna;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) if (j < mna) po[j] = lg[j] * inv;
+  val[(int64_t)r * d.A + a] = v;
+  if (act) {
+    uint32_t hsh = lmix32(seed_lo ^ (step * 0x9E3779B1U));
+    hsh = lmix32(hsh ^ seed_hi ^ ((uint32_t)(replica0 + r) * 0x85EBCA77U));
+    hsh = lmix32(hsh ^ ((uint32_t)a * 0xC2B2AE3DU));
+    const float uu = (float)(hsh >> 8) * (1.0f / 16777216.0f);
+    float cum = 0.f;
+    int pick = na - 1;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < na) {
+        cum += lg[j] * inv;
+        if (!found && uu < cum) { pick = j; found = true; }
+      }
+    }
+    act[(int64_t)r * d.A + a] = pick;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void returns_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                               const float* __restrict__ boot, const float* __restrict__ done_post, float gamma,
+                               int T, int64_t RA, float* __restrict__ Rs, float* __restrict__ Adv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= RA) return;
+  float Rv = boot[i];
+  for (int t = T - 1; t >= 0; --t) {
+    Rv = rew[(int64_t)t * RA + i] + gamma * Rv * (1.0f - done_post[t]);
+    Rs[(int64_t)t * RA + i] = Rv;
+    Adv[(int64_t)t * RA + i] = Rv - val[(int64_t)t * RA + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss gradients at the heads.  grid (ceil(M/128), A), 128 threads, thread = row m.
+__global__ void __launch_bounds__(128)
+heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ Hm,
+                  const int32_t* __restrict__ act, const float* __restrict__ Rs, const float* __restrict__ Adv,
+                  int64_t M, int64_t Rc, int64_t stride_t, float v_coef, float beta, float scale,
+                  float* __restrict__ dlog, float* __restrict__ dH, float* __restrict__ stats) {
+  extern __shared__ float sm[];
+  const int a = blockIdx.y, tid = threadIdx.x, na = d.n_a[a], mna = d.max_na;
+  float* sWp = sm;
+  float* sWv = sWp + H64 * mna;
+  float* sb = sWv + H64;
+  const float* Wp = P + d.off_wo + (int64_t)(2 * a) * H64 * mna;
+  const float* Wv = P + d.off_wo + (int64_t)(2 * a + 1) * H64 * mna;
+  for (int i = tid; i < H64 * mna; i += 128) sWp[i] = Wp[i];
+  for (int i = tid; i < H64; i += 128) sWv[i] = Wv[i * mna];
+  for (int i = tid; i < mna; i += 128) sb[i] = P[d.off_bo + (int64_t)(2 * a) * mna + i];
+  if (tid == 0) sb[mna] = P[d.off_bo + (int64_t)(2 * a + 1) * mna];
+  __syncthreads();
+  const int64_t m = (int64_t)blockIdx.x * 128 + tid;
+  float pl = 0.f, vl = 0.f, el = 0.f;
+  if (m < M) {
+    const float4* hp = reinterpret_cast<const float4*>(Hm + ((int64_t)(2 * a) * M + m) * H64);
+    const float4* hv = reinterpret_cast<const float4*>(Hm + ((int64_t)(2 * a + 1) * M + m) * H64);
+    float lg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lg[j] = j < mna ? sb[j] : 0.f;
+    float v = sb[mna];
+    for (int k4 = 0; k4 < H64 / 4; ++k4) {
+      const float4 x = hp[k4], y = hv[k4];
+      const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k4 * 4 + e;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < mna) lg[j] = fmaf(xs[e], sWp[k * mna + j], lg[j]);
+        v = fmaf(ys[e], sWv[k], v);
+      }
+    }
+    float mx = -1e30f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < na) mx = fmaxf(mx, lg[j]);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lg[j] = j < na ? __expf(lg[j] - mx) : 0.f; s += lg[j]; }
+    const float inv = 1.0f / s;
+    const int64_t io = (m / Rc) * stride_t + (m % Rc) * d.A + a;
+    const int at = act[io];
+    const float adv = Adv[io], ret = Rs[io];
+    float lp[8], ent = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      lg[j] *= inv;                                             // pi_j
+      lp[j] = j < na ? __logf(fminf(fmaxf(lg[j], 1e-10f), 1.0f)) : 0.f;   // agents/policies.py:47
+      ent -= lg[j] * lp[j];
+    }
+    float dl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = 0.f;
+      if (j < na) g = scale * (-adv * ((j == at ? 1.f : 0.f) - lg[j]) + beta * lg[j] * (lp[j] + ent));
+      dl[j] = g;
+    }
+    const float dv = scale * v_coef * (v - ret);
+    float* dlp = dlog + ((int64_t)(2 * a) * M + m) * mna;
+    float* dlv = dlog + ((int64_t)(2 * a + 1) * M + m) * mna;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < mna) { dlp[j] = dl[j]; dlv[j] = j == 0 ? dv : 0.f; }
+    float4* dhp = reinterpret_cast<float4*>(dH + ((int64_t)(2 * a) * M + m) * H64);
+    float4* dhv = reinterpret_cast<float4*>(dH + ((int64_t)(2 * a + 1) * M + m) * H64);
+    for (int k4 = 0; k4 < H64 / 4; ++k4) {
+      float o[4], w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k4 * 4 + e;
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < mna) t = fmaf(dl[j], sWp[k * mna + j], t);
+        o[e] = t; w[e] = dv * sWv[k];
+      }
+      dhp[k4] = make_float4(o[0], o[1], o[2], o[3]);
+      dhv[k4] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    if (a == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (j == at) pl = -lp[j] * adv;
+      vl = 0.5f * v_coef * (ret - v) * (ret - v);
+      el = -beta * ent;
+    }
+  }
+  if (a == 0 && stats) {
+    for (int o = 16; o; o >>= 1) {
+      pl += __shfl_down_sync(0xffffffffu, pl, o);
+      vl += __shfl_down_sync(0xffffffffu, vl, o);
+      el += __shfl_down_sync(0xffffffffu, el, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&stats[0], pl * scale); atomicAdd(&stats[1], vl * scale); atomicAdd(&stats[2], el * scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BPTT through the LSTM.  Same thread mapping as the forward kernel.  smem: WhT [256][64] + dz [32][256].
+__global__ void __launch_bounds__(256)
+lstm_seq_bwd_kernel(const DDims d, const float* __restrict__ P, float* __restrict__ ZG, const float* __restrict__ C,
+                    const float* __restrict__ dH, const float* __restrict__ c0, const float* __restrict__ done, int T,
+                    int64_t Rc, int64_t ld_state, int64_t r0) {
+  extern __shared__ float sm[];
+  float* sWT = sm;                 // [256][64] : WhT[col][k]
+  float* sdz = sm + G4 * H64;      // [32][256]
+  const int u = blockIdx.y, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5, j0 = 2 * tx;
+  const float* Wh = P + d.off_wh + (int64_t)u * H64 * G4;
+  for (int i = tid; i < H64 * G4; i += 256) {
+    const int k = i / G4, col = i - k * G4;
+    sWT[col * H64 + k] = Wh[i];
+  }
+  const int64_t rbase = (int64_t)blockIdx.x * LS_ROWS;
+  float dc[4][2], dhc[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { dc[q][0] = dc[q][1] = 0.f; dhc[q][0] = dhc[q][1] = 0.f; }
+  __syncthreads();
+  for (int t = T - 1; t >= 0; --t) {
+    const float keep = 1.0f - done[t];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t r = rbase + ty * 4 + q;
+      float dz[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+      float dcp[2] = {0.f, 0.f};
+      if (r < Rc) {
+        const int64_t m = ((int64_t)u * T + t) * Rc + r;
+        float* z = ZG + m * G4 + j0;
+        const float2 gi = *reinterpret_cast<const float2*>(z), gf = *reinterpret_cast<const float2*>(z + H64);
+        const float2 go = *reinterpret_cast<const float2*>(z + 2 * H64), gu = *reinterpret_cast<const float2*>(z + 3 * H64);
+        const float2 ct = *reinterpret_cast<const float2*>(C + m * H64 + j0);
+        float2 cp;
+        if (t > 0) cp = *reinterpret_cast<const float2*>(C + (m - Rc) * H64 + j0);
+        else cp = *reinterpret_cast<const float2*>(c0 + ((int64_t)u * ld_state + r0 + r) * H64 + j0);
+        const float2 dh_in = *reinterpret_cast<const float2*>(dH + m * H64 + j0);
+        const float i_[2] = {gi.x, gi.y}, f_[2] = {gf.x, gf.y}, o_[2] = {go.x, go.y}, u_[2] = {gu.x, gu.y};
+        const float c_[2] = {ct.x, ct.y}, p_[2] = {cp.x * keep, cp.y * keep}, h_[2] = {dh_in.x, dh_in.y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float dh = h_[e] + dhc[q][e];
+          const float tc = tanhf(c_[e]);
+          const float dcc = dc[q][e] + dh * o_[e] * (1.0f - tc * tc);
+          dz[0][e] = dcc * u_[e] * i_[e] * (1.0f - i_[e]);
+          dz[1][e] = dcc * p_[e] * f_[e] * (1.0f - f_[e]);
+          dz[2][e] = dh * tc * o_[e] * (1.0f - o_[e]);
+          dz[3][e] = dcc * i_[e] * (1.0f - u_[e] * u_[e]);
+          dcp[e] = dcc * f_[e];
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(z + g * H64) = make_float2(dz[g][0], dz[g][1]);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<float2*>(&sdz[(ty * 4 + q) * G4 + g * H64 + j0]) = make_float2(dz[g][0], dz[g][1]);
+      dc[q][0] = dcp[0] * keep; dc[q][1] = dcp[1] * keep;
+    }
+    __syncthreads();
+    if (keep != 0.f && t > 0) {
+      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int col = 0; col < G4; ++col) {
+        const float2 w = *reinterpret_cast<const float2*>(&sWT[col * H64 + j0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float z = sdz[(ty * 4 + q) * G4 + col];
+          a0[q] = fmaf(z, w.x, a0[q]);
+          a1[q] = fmaf(z, w.y, a1[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { dhc[q][0] = a0[q] * keep; dhc[q][1] = a1[q] * keep; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { dhc[q][0] = 0.f; dhc[q][1] = 0.f; }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fc front-end backward.  grid (n_slabs, 2A), 256 threads; slab = FB_SLAB rows, staged FB_ROWS at a time.
+#define FB_SLAB 512
+#define FB_ROWS 16
+#define FB_MAXE 24
+__global__ void __launch_bounds__(256)
+fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restrict__ X, const float* __restrict__ dX,
+              int64_t M, int64_t rows_per_t, int64_t stride_t, float* __restrict__ G) {
+  extern __shared__ float sm[];
+  const int u = blockIdx.y, a = u >> 1, tid = threadIdx.x;
+  const int nw = d.n_wave[a], nt = d.n_wait[a], nf = d.ff > 0 ? d.n_fp[a] : 0;
+  const int n_in = nw + nt + nf, dx = d.dx;
+  const int eW = nw * d.fw, eF = nf * d.ff, eT = nt * d.ft, E = eW + eF + eT + dx;
+  float* sIn = sm;                       // [FB_ROWS][n_in]
+  float* sD = sm + FB_ROWS * n_in;       // [FB_ROWS][dx]
+  float acc[FB_MAXE];
+  int kin[FB_MAXE], col[FB_MAXE];        // -1 kin = bias element
+#pragma unroll
+  for (int q = 0; q < FB_MAXE; ++q) {
+    acc[q] = 0.f;
+    int e = tid + q * 256;
+    kin[q] = -2; col[q] = 0;
+    if (e < eW) { kin[q] = e / d.fw; col[q] = e % d.fw; }
+    else if (e < eW + eF) { e -= eW; kin[q] = nw + nt + e / d.ff; col[q] = d.fw + e % d.ff; }
+    else if (e < eW + eF + eT) { e -= eW + eF; kin[q] = nw + e / d.ft; col[q] = d.fw + d.ff + e % d.ft; }
+    else if (e < E) { kin[q] = -1; col[q] = e - (eW + eF + eT); }
+  }
+  const int ooff = d.obs_off[a];
+  const int64_t m_lo = (int64_t)blockIdx.x * FB_SLAB;
+  const int64_t m_hi = m_lo + FB_SLAB < M ? m_lo + FB_SLAB : M;
+  for (int64_t mb = m_lo; mb < m_hi; mb += FB_ROWS) {
+    for (int i = tid; i < FB_ROWS * n_in; i += 256) {
+      const int row = i / n_in, k = i - row * n_in;
+      const int64_t m = mb + row;
+      sIn[i] = m < m_hi ? obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k] : 0.f;
+    }
+    for (int i = tid; i < FB_ROWS * dx; i += 256) {
+      const int row = i / dx, c = i - row * dx;
+      const int64_t m = mb + row;
+      float v = 0.f;
+      if (m < m_hi) {
+        const int64_t o = ((int64_t)u * M + m) * dx + c;
+        v = X[o] > 0.f ? dX[o] : 0.f;
+      }
+      sD[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < FB_MAXE; ++q) {
+      if (kin[q] == -2) continue;
+      float s = 0.f;
+      if (kin[q] >= 0) {
+#pragma unroll
+        for (int row = 0; row < FB_ROWS; ++row) s = fmaf(sIn[row * n_in + kin[q]], sD[row * dx + col[q]], s);
+      } else {
+#pragma unroll
+        for (int row = 0; row < FB_ROWS; ++row) s += sD[row * dx + col[q]];
+      }
+      acc[q] += s;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < FB_MAXE; ++q) {
+    int e = tid + q * 256;
+    if (kin[q] == -2) continue;
+    int64_t off;
+    if (e < eW) off = d.off_fcw_w[u] + e;
+    else if (e < eW + eF) off = d.off_fcf_w[u] + (e - eW);
+    else if (e < eW + eF + eT) off = d.off_fct_w[u] + (e - eW - eF);
+    else {
+      const int c = e - (eW + eF + eT);
+      if (c < d.fw) off = d.off_fcw_b[u] + c;
+      else if (c < d.fw + d.ff) off = d.off_fcf_b[u] + (c - d.fw);
+      else off = d.off_fct_b[u] + (c - d.fw - d.ff);
+    }
+    atomicAdd(&G[off], acc[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void norm2_kernel(const float* __restrict__ g, const uint8_t* __restrict__ agent_of, int64_t n,
+                             float* __restrict__ norm2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  int a = -1;
+  if (i < n) { v = g[i]; v *= v; a = agent_of[i]; }
+  const int a0 = __shfl_sync(0xffffffffu, a, 0);
+  if (__all_sync(0xffffffffu, a == a0)) {
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && a0 >= 0) atomicAdd(&norm2[a0], v);
+  } else if (a >= 0) {
+    atomicAdd(&norm2[a], v);
+  }
+}
+__global__ void rmsprop_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ ms,
+                               const uint8_t* __restrict__ agent_of, int64_t n, const float* __restrict__ norm2,
+                               float max_norm, float lr, float alpha, float eps, float* __restrict__ norms) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int a = agent_of[i];
+  const float nrm = sqrtf(norm2[a]);
+  float scale = 1.0f;
+  if (max_norm > 0.f) scale = max_norm / fmaxf(nrm, max_norm);      // tf.clip_by_global_norm
+  const float gi = g[i] * scale;
+  const float m = alpha * ms[i] + (1.0f - alpha) * gi * gi;          // TF1 RMSProp: ms starts at 1
+  ms[i] = m;
+  p[i] -= lr * gi / sqrtf(m + eps);                                  // epsilon inside the sqrt
+  if (norms && (i == 0 || agent_of[i - 1] != a)) norms[a] = nrm;
+}
+
+// ================================================================================================
+template <class T>
+static int up(tscl_handle* h, const T* src, size_t n, const T** dst) {
+  void* p = nullptr;
+  LCK(cudaMalloc(&p, n ? n * sizeof(T) : 16));
+  if (n) LCK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  h->owned.push_back(p);
+  *dst = static_cast<const T*>(p);
+  return 0;
+}
+
+extern "C" int tscl_create(const tscl_dims* x, int32_t device, tscl_handle** out) {
+  if (!x || !out) return tsc_set_error("tscl_create: bad argument");
+  if (x->h != H64) return tsc_set_error("tscl_create: num_lstm must be 64");
+  if (x->max_na > 8) return tsc_set_error("tscl_create: max_na > 8");
+  if (x->dx != x->fw + x->ff + x->ft) return tsc_set_error("tscl_create: dx != fw + ff + ft");
+  LCK(cudaSetDevice(device));
+  tscl_handle* h = new tscl_handle();
+  h->device = device;
+  DDims& d = h->d;
+  d.A = x->n_agents; d.n_obs = x->n_obs; d.max_na = x->max_na; d.fw = x->fw; d.ff = x->ff; d.ft = x->ft;
+  d.h = x->h; d.dx = x->dx; d.off_wx = x->off_wx; d.off_wh = x->off_wh; d.off_bl = x->off_bl; d.off_wo = x->off_wo;
+  d.off_bo = x->off_bo; d.n_params = x->n_params;
+  const size_t A = x->n_agents, U = 2 * A;
+  int rc = 0;
+  rc |= up(h, x->obs_off, A, &d.obs_off); rc |= up(h, x->n_wave, A, &d.n_wave); rc |= up(h, x->n_wait, A, &d.n_wait);
+  rc |= up(h, x->n_fp, A, &d.n_fp); rc |= up(h, x->n_a, A, &d.n_a);
+  rc |= up(h, x->off_fcw_w, U, &d.off_fcw_w); rc |= up(h, x->off_fcw_b, U, &d.off_fcw_b);
+  rc |= up(h, x->off_fcf_w, U, &d.off_fcf_w); rc |= up(h, x->off_fcf_b, U, &d.off_fcf_b);
+  rc |= up(h, x->off_fct_w, U, &d.off_fct_w); rc |= up(h, x->off_fct_b, U, &d.off_fct_b);
+  if (rc) { tscl_destroy(h); return -1; }
+  for (size_t a = 0; a < A; ++a) {
+    const int nf = x->ff > 0 ? x->n_fp[a] : 0;
+    const int n_in = x->n_wave[a] + x->n_wait[a] + nf;
+    const int w = x->n_wave[a] * x->fw + nf * x->ff + x->n_wait[a] * x->ft + x->dx;
+    if (n_in > h->max_in) h->max_in = n_in;
+    if (w > h->max_fcw) h->max_fcw = w;
+  }
+  if (h->max_fcw > FB_MAXE * 256) { tscl_destroy(h); return tsc_set_error("tscl_create: fc layer too large for fc_bwd_kernel"); }
+  LCK(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (H64 * G4 + LS_ROWS * H64) * 4));
+  LCK(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (G4 * H64 + LS_ROWS * G4) * 4));
+  LCK(cudaFuncSetAttribute(fc_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (h->max_fcw + FE_ROWS * h->max_in) * 4));
+  *out = h;
+  return 0;
+}
+
+extern "C" int tscl_destroy(tscl_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return 0;
+}
+
+extern "C" int tscl_fc_embed(tscl_handle* h, const float* params, const float* obs, int64_t M, int64_t rows_per_t,
+                             int64_t stride_t, float* X, void* stream) {
+  if (!h || M <= 0) return tsc_set_error("tscl_fc_embed: bad argument");
+  LCK(cudaSetDevice(h->device));
+  dim3 grid((unsigned)((M + FE_ROWS - 1) / FE_ROWS), 2 * h->d.A);
+  fc_embed_kernel<<<grid, 256, (h->max_fcw + FE_ROWS * h->max_in) * 4, (cudaStream_t)stream>>>(
+      h->d, params, obs, M, rows_per_t, stride_t, X);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_lstm_seq_fwd(tscl_handle* h, const float* params, float* ZG, float* C, float* H, const float* c0,
+                                 const float* h0, float* c1, float* h1, const float* done, int32_t T, int64_t Rc,
+                                 int64_t ld_state, int64_t r0, void* stream) {
+  if (!h || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_fwd: bad argument");
+  LCK(cudaSetDevice(h->device));
+  dim3 grid((unsigned)((Rc + LS_ROWS - 1) / LS_ROWS), 2 * h->d.A);
+  lstm_seq_fwd_kernel<<<grid, 256, (H64 * G4 + LS_ROWS * H64) * 4, (cudaStream_t)stream>>>(
+      h->d, params, ZG, C, H, c0, h0, c1, h1, done, T, Rc, ld_state, r0);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_heads(tscl_handle* h, const float* params, const float* Hs, int64_t R, float* pi, float* val,
+                          int32_t* act, uint64_t seed, int64_t step, int64_t replica0, void* stream) {
+  if (!h || R <= 0) return tsc_set_error("tscl_heads: bad argument");
+  LCK(cudaSetDevice(h->device));
+  dim3 grid((unsigned)((R + 127) / 128), h->d.A);
+  const int smem = (H64 * h->d.max_na + H64 + h->d.max_na + 1) * 4;
+  heads_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(h->d, params, Hs, R, pi, val, act, (uint32_t)seed,
+                                                          (uint32_t)(seed >> 32), (uint32_t)step, replica0);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_returns(tscl_handle* h, const float* rew, const float* val, const float* boot,
+                            const float* done_post, float gamma, int32_t T, int64_t R, float* Rs, float* Adv,
+                            void* stream) {
+  if (!h) return tsc_set_error("tscl_returns: null handle");
+  LCK(cudaSetDevice(h->device));
+  const int64_t RA = R * h->d.A;
+  returns_kernel<<<(unsigned)((RA + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rew, val, boot, done_post, gamma, T, RA,
+                                                                                  Rs, Adv);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_heads_loss(tscl_handle* h, const float* params, const float* H, const int32_t* act,
+                               const float* Rs, const float* Adv, int64_t M, int64_t Rc, int64_t stride_t,
+                               float v_coef, float beta, float scale, float* dlog, float* dH, float* stats,
+                               void* stream) {
+  if (!h || M <= 0) return tsc_set_error("tscl_heads_loss: bad argument");
+  LCK(cudaSetDevice(h->device));
+  dim3 grid((unsigned)((M + 127) / 128), h->d.A);
+  const int smem = (H64 * h->d.max_na + H64 + h->d.max_na + 1) * 4;
+  heads_loss_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(h->d, params, H, act, Rs, Adv, M, Rc, stride_t, v_coef,
+                                                               beta, scale, dlog, dH, stats);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_lstm_seq_bwd(tscl_handle* h, const float* params, float* ZG, const float* C, const float* dH,
+                                 const float* c0, const float* done, int32_t T, int64_t Rc, int64_t ld_state,
+                                 int64_t r0, void* stream) {
+  if (!h || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_bwd: bad argument");
+  LCK(cudaSetDevice(h->device));
+  dim3 grid((unsigned)((Rc + LS_ROWS - 1) / LS_ROWS), 2 * h->d.A);
+  lstm_seq_bwd_kernel<<<grid, 256, (G4 * H64 + LS_ROWS * G4) * 4, (cudaStream_t)stream>>>(h->d, params, ZG, C, dH, c0,
+                                                                                           done, T, Rc, ld_state, r0);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* dX, int64_t M,
+                           int64_t rows_per_t, int64_t stride_t, float* grads, void* stream) {
+  if (!h || M <= 0) return tsc_set_error("tscl_fc_bwd: bad argument");
+  LCK(cudaSetDevice(h->device));
+  dim3 grid((unsigned)((M + FB_SLAB - 1) / FB_SLAB), 2 * h->d.A);
+  const int smem = FB_ROWS * (h->max_in + h->d.dx) * 4;
+  fc_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(h->d, obs, X, dX, M, rows_per_t, stride_t, grads);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_clip_rmsprop(tscl_handle* h, float* params, float* grads, float* ms, const uint8_t* agent_of,
+                                 float max_norm, float lr, float alpha, float eps, float* norms, void* stream) {
+  if (!h) return tsc_set_error("tscl_clip_rmsprop: null handle");
+  LCK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* norm2 = nullptr;
+  LCK(cudaMallocAsync(&norm2, sizeof(float) * h->d.A, st));
+  LCK(cudaMemsetAsync(norm2, 0, sizeof(float) * h->d.A, st));
+  const int64_t n = h->d.n_params;
+  norm2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(grads, agent_of, n, norm2);
+  rmsprop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, ms, agent_of, n, norm2, max_norm, lr, alpha,
+                                                              eps, norms);
+  LCK(cudaGetLastError());
+  LCK(cudaFreeAsync(norm2, st));
+  return 0;
+}

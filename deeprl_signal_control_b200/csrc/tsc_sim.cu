@@ -685,6 +685,7 @@ __global__ void tsc_live_kernel(const uint8_t* lane_cnt, int lpad, int L, int R,
 // ================================================================================================
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return -1; }
+int tsc_set_error(const std::string& m) { return fail(m); }   // shared with tsc_learn.cu
 #define CK(call)                                                                      \
   do {                                                                                \
     cudaError_t e__ = (call);                                                         \

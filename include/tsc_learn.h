@@ -1,0 +1,111 @@
+/*
+ * tsc_learn.h — C ABI of the per-intersection A2C learner kernels in libtsc (sm_100a).
+ *
+ * Replaces, for R lock-stepped replicas and all A agents at once, the TF1 graphs of the reference:
+ *   fc / lstm layers                         agents/utils.py:66-74, 88-116
+ *   LstmACPolicy / FPLstmACPolicy forward    agents/policies.py:99-136, 191-211
+ *   ACPolicy.prepare_loss + backward         agents/policies.py:41-61, 138-155
+ *   OnPolicyBuffer._add_R_Adv                agents/utils.py:202-214
+ *   clip_by_global_norm + RMSPropOptimizer   agents/policies.py:54-61  (TF1 semantics: ms starts
+ *                                            at 1, epsilon inside the sqrt, no momentum)
+ * Two networks per agent (pi and V, agents/policies.py:87-96) = 2A "units"; unit u = 2*agent + net.
+ *
+ * All pointers are caller-owned DEVICE pointers; `stream` is a cudaStream_t as void*.
+ * Every function returns 0 or <0 (message via tsc_last_error()).  The three plain time-batched
+ * GEMMs of the update (X.Wx, dZ.Wx^T, X^T.dZ) are NOT in this ABI: the host calls the vendor
+ * library for them until the tcgen05 kernels replace them.
+ */
+#ifndef TSC_LEARN_H_
+#define TSC_LEARN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Static shape/offset description of the A agents (host struct; arrays are HOST pointers, copied
+ * by tscl_create).  Observation row of agent i (envs/env.py:163-205):
+ *   [wave (n_wave[i]) | wait (n_wait[i]) | fingerprints (n_fp[i])] at obs_off[i]. */
+typedef struct tscl_dims {
+  int32_t n_agents;   /* A                                                                 */
+  int32_t n_obs;      /* row stride of the observation matrix                              */
+  int32_t max_na;     /* padded action dimension (row stride of pi / fingerprints)         */
+  int32_t fw, ff, ft; /* fc widths: num_fw, num_fp (0 = no fingerprint branch), num_ft     */
+  int32_t h;          /* num_lstm (must be 64)                                             */
+  int32_t dx;         /* fw + ff + ft                                                      */
+  const int32_t* obs_off;  /* [A]                                                          */
+  const int32_t* n_wave;   /* [A]                                                          */
+  const int32_t* n_wait;   /* [A]                                                          */
+  const int32_t* n_fp;     /* [A]                                                          */
+  const int32_t* n_a;      /* [A]                                                          */
+  /* offsets (in floats) into the flat parameter / gradient / RMS-slot vectors             */
+  const int64_t* off_fcw_w; /* [2A] ragged [n_wave][fw]   */ const int64_t* off_fcw_b; /* [2A] */
+  const int64_t* off_fcf_w; /* [2A] ragged [n_fp][ff]     */ const int64_t* off_fcf_b; /* [2A] */
+  const int64_t* off_fct_w; /* [2A] ragged [n_wait][ft]   */ const int64_t* off_fct_b; /* [2A] */
+  int64_t off_wx;  /* [2A][dx][4h] */
+  int64_t off_wh;  /* [2A][h][4h]  */
+  int64_t off_bl;  /* [2A][4h]     */
+  int64_t off_wo;  /* [2A][h][max_na]  (V units use column 0) */
+  int64_t off_bo;  /* [2A][max_na] */
+  int64_t n_params;
+} tscl_dims;
+
+typedef struct tscl_handle tscl_handle;
+
+int tscl_create(const tscl_dims* dims, int32_t device, tscl_handle** out);
+int tscl_destroy(tscl_handle* h);
+
+/* fc front end (agents/policies.py:191-201): X[u][m][0:dx] = relu(fc(...)) for m in [0, M).
+ * Row m reads obs + (m / rows_per_t) * stride_t + (m % rows_per_t) * n_obs  (floats). */
+int tscl_fc_embed(tscl_handle* h, const float* params, const float* obs, int64_t M, int64_t rows_per_t,
+                  int64_t stride_t, float* X, void* stream);
+
+/* LSTM over T steps (agents/utils.py:88-116): recurrent GEMM h.Wh + fused cell.
+ *   ZG   [2A][T*Rc][4h]  in: X.Wx + b (time-major rows m = t*Rc + r); out: gate activations i,f,o,u
+ *   C,H  [2A][T*Rc][h]   out (may be NULL when T == 1 and only states are wanted)
+ *   c0,h0 [2A][ld_state][h] initial state rows r0 .. r0+Rc;  c1,h1: final state (may alias c0,h0, may be NULL)
+ *   done [T] float (pre-step done: state is zeroed BEFORE the cell, agents/utils.py:104-105) */
+int tscl_lstm_seq_fwd(tscl_handle* h, const float* params, float* ZG, float* C, float* H, const float* c0,
+                      const float* h0, float* c1, float* h1, const float* done, int32_t T, int64_t Rc,
+                      int64_t ld_state, int64_t r0, void* stream);
+
+/* Heads for one control step (agents/policies.py:18-26, utils.py:155-157): softmax policy, value,
+ * categorical sample with the counter-based RNG keyed (seed, step, replica0 + r, agent).
+ *   Hs [2A][R][h] -> pi [R][A][max_na] (zero padded), val [R][A], act [R][A] (may be NULL) */
+int tscl_heads(tscl_handle* h, const float* params, const float* Hs, int64_t R, float* pi, float* val,
+               int32_t* act, uint64_t seed, int64_t step, int64_t replica0, void* stream);
+
+/* n-step returns (agents/utils.py:202-214): R_t = r_t + gamma*R_{t+1}*(1-done_post_t), Adv = R - v.
+ *   rew,val,Rs,Adv [T][R][A]; boot [R][A]; done_post [T] float */
+int tscl_returns(tscl_handle* h, const float* rew, const float* val, const float* boot, const float* done_post,
+                 float gamma, int32_t T, int64_t R, float* Rs, float* Adv, void* stream);
+
+/* Loss gradients at the heads for all (t, r) of a chunk (agents/policies.py:41-52):
+ *   H [2A][M][h], act/Rs/Adv rows m -> base + (m / Rc)*stride_t + (m % Rc)*A
+ *   dlog [2A][M][max_na] (out; V units use column 0), dH [2A][M][h] (out)
+ *   stats [4] += {policy_loss, value_loss, entropy_loss, count} of agent 0 (agents/policies.py:63-72)
+ *   scale = 1 / (n_step * total replicas): mean over the batch and over replicas */
+int tscl_heads_loss(tscl_handle* h, const float* params, const float* H, const int32_t* act, const float* Rs,
+                    const float* Adv, int64_t M, int64_t Rc, int64_t stride_t, float v_coef, float beta,
+                    float scale, float* dlog, float* dH, float* stats, void* stream);
+
+/* BPTT through the LSTM (reverse of tscl_lstm_seq_fwd).  ZG holds gate activations on entry and
+ * dZ (pre-activation gate gradients) on exit; dH holds head gradients on entry. */
+int tscl_lstm_seq_bwd(tscl_handle* h, const float* params, float* ZG, const float* C, const float* dH,
+                      const float* c0, const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
+                      void* stream);
+
+/* fc front-end backward: grads[...] += obs^T . (dX * (X > 0)) and bias sums, rows as tscl_fc_embed. */
+int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* dX, int64_t M,
+                int64_t rows_per_t, int64_t stride_t, float* grads, void* stream);
+
+/* Per-agent clip_by_global_norm(max_norm) + RMSProp step (TF1 semantics).  agent_of [n_params] u8.
+ * norms [A] receives the pre-clip global norms. */
+int tscl_clip_rmsprop(tscl_handle* h, float* params, float* grads, float* ms, const uint8_t* agent_of,
+                      float max_norm, float lr, float alpha, float eps, float* norms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSC_LEARN_H_ */

@@ -39,6 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_AGENTS = 25
+N_STEP = 120          # batch_size of config/config_ma2c_large.ini
 
 
 def parse():
@@ -50,6 +51,8 @@ def parse():
     p.add_argument("--replicas", type=int, default=8192)
     p.add_argument("--burnin", type=int, default=240)
     p.add_argument("--mode", default=None, choices=[None, "sim", "train"])
+    p.add_argument("--chunk", type=int, default=1024, help="replicas per BPTT chunk in the update")
+    p.add_argument("--fp32-gemm", action="store_true", help="plain fp32 (no TF32 tensor cores) in the learner GEMMs")
     p.add_argument("--seed", type=int, default=12)
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
@@ -144,7 +147,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    mode = args.mode or "sim"
+    mode = args.mode or "train"
     from deeprl_signal_control_b200.net.large_grid import build_large_grid
     from deeprl_signal_control_b200.net.tables import EnvParams
     net, par = build_large_grid(agent="ma2c"), EnvParams(agent="ma2c")
@@ -180,14 +183,6 @@ def main():
     from deeprl_signal_control_b200.sim import BatchedSim
     R = args.replicas
     sim = BatchedSim(net, par, R, device=local_rank)
-    seeds = np.arange(R, dtype=np.uint64) + np.uint64(args.seed + rank * R)
-    sim.reset(seeds)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    n_act_sets = 16
-    acts = [torch.randint(0, 5, (R, net.n_nodes), device=dev, dtype=torch.int32, generator=gen)
-            for _ in range(n_act_sets)]
-    fp = torch.rand(R, net.n_nodes, net.max_na, device=dev, generator=gen)
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,11 +191,39 @@ def main():
         torch.cuda.synchronize()
 
     launches = 0
+    trainer = None
+    if mode == "train":
+        from deeprl_signal_control_b200.agents.layout import PolicyLayout
+        from deeprl_signal_control_b200.agents.learner import BatchedA2C
+        from deeprl_signal_control_b200.agents.trainer import BatchedTrainer
+        # config/config_ma2c_large.ini [MODEL_CONFIG]
+        lay = PolicyLayout(net.n_s_ls, net.n_a_ls, net.n_w_ls, net.n_f_ls, net.node_obs_off, net.n_obs,
+                           fw=128, ft=32, ff=64, h=64)
+        model = BatchedA2C(lay, R, n_step=N_STEP, gamma=0.99, v_coef=0.5, max_grad_norm=40.0, alpha=0.99, eps=1e-5,
+                           reward_norm=2000.0, reward_clip=2.0, seed=args.seed, device=local_rank,
+                           chunk=args.chunk, replica0=rank * R, total_replicas=world * R,
+                           process_group=dist.group.WORLD if world > 1 else None, allow_tf32=not args.fp32_gemm)
+        trainer = BatchedTrainer(sim, model, "ma2c", lr=5e-4, beta=0.01, seed0=args.seed, replica0=rank * R)
 
-    def one_step(i):
-        nonlocal launches
-        sim.step(acts[i % n_act_sets], fp)
-        launches += 1
+        def one_step(i):
+            trainer.control_step()
+    else:
+        seeds = np.arange(R, dtype=np.uint64) + np.uint64(args.seed + rank * R)
+        sim.reset(seeds)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        n_act_sets = 16
+        acts = [torch.randint(0, 5, (R, net.n_nodes), device=dev, dtype=torch.int32, generator=gen)
+                for _ in range(n_act_sets)]
+        fp = torch.rand(R, net.n_nodes, net.max_na, device=dev, generator=gen)
+        sim_events = []
+
+        def one_step(i):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sim.step(acts[i % n_act_sets], fp)
+            e1.record()
+            sim_events.append((e0, e1))
 
     for i in range(args.burnin):
         one_step(i)
@@ -209,20 +232,29 @@ def main():
     live0 = sim.mean_live()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches = 0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if trainer is not None:
+        trainer.sim_events = []
+        l0 = trainer.model.kernel_launches
+        upd0 = trainer.n_updates
+    else:
+        sim_events.clear()
     barrier()
     t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
-        ev[i][0].record()
         one_step(i)
-        ev[i][1].record()
     t_end.record()
     barrier()
     total_ms = t_start.elapsed_time(t_end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    timed_launches = launches
+    evs = trainer.sim_events if trainer is not None else sim_events
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if trainer is not None:
+        timed_launches = args.steps + (trainer.model.kernel_launches - l0)
+        n_updates_timed = trainer.n_updates - upd0
+        trainer.sim_events = None
+    else:
+        timed_launches = args.steps
+        n_updates_timed = 0
     sampler.stop_flag = True
     sampler.join(timeout=2)
     live1 = sim.mean_live()
@@ -233,30 +265,43 @@ def main():
     total_ms_max = float(t.item())
     value = world * R * net.n_nodes * args.steps / (total_ms_max * 1e-3)
 
-    # ---------------- e2e through the host-buffer C-ABI call ---------------------------------
-    e2e_steps = max(3, min(args.steps, 20))
-    h_act = [torch.randint(0, 5, (R, net.n_nodes), dtype=torch.int32).pin_memory().numpy() for _ in range(4)]
-    h_fp = torch.rand(R, net.n_nodes, net.max_na).pin_memory().numpy()
-    sim._h_out = tuple(torch.from_numpy(a).pin_memory().numpy() for a in (
-        np.zeros((R, net.n_obs), np.float32), np.zeros((R, net.n_nodes), np.float32),
-        np.zeros(R, np.float32), np.zeros(R, np.uint8)))
-    for i in range(3):
-        sim.step_host(h_act[i % 4], h_fp)
-    barrier()
-    t0 = time.perf_counter()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(e2e_steps):
-        sim.step_host(h_act[i % 4], h_fp)
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    # ---------------- e2e: the environment driven through the host-buffer C-ABI call ------------
+    if trainer is not None:
+        e2e_steps = N_STEP                     # one full rollout + one update
+        for i in range(3):
+            trainer.control_step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            trainer.control_step_host()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4
+        d2h = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
+        e2e_api = ("BatchedTrainer.control_step_host: policy forward on device, actions+fingerprints D2H, "
+                   "tsc_step_host (H2D, kernel, D2H), obs+reward H2D, update every 120 steps")
+    else:
+        e2e_steps = max(3, min(args.steps, 20))
+        h_act = [torch.randint(0, 5, (R, net.n_nodes), dtype=torch.int32).pin_memory().numpy() for _ in range(4)]
+        h_fp = torch.rand(R, net.n_nodes, net.max_na).pin_memory().numpy()
+        sim._h_out = tuple(torch.from_numpy(a).pin_memory().numpy() for a in (
+            np.zeros((R, net.n_obs), np.float32), np.zeros((R, net.n_nodes), np.float32),
+            np.zeros(R, np.float32), np.zeros(R, np.uint8)))
+        for i in range(3):
+            sim.step_host(h_act[i % 4], h_fp)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            sim.step_host(h_act[i % 4], h_fp)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4
+        d2h = R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
+        e2e_api = "tsc_step_host (pinned host buffers)"
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * R * net.n_nodes * e2e_steps / (float(t.item()) * 1e-3)
-    h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4
-    d2h = R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
 
     if rank != 0:
         if world > 1:
@@ -277,7 +322,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "tsc_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "mean_live_vehicles_per_replica": v_live,
-                "kernel_ms_per_launch": kern_ms,
+                "kernel_ms_per_launch": kern_ms, "share_of_step": kern_ms * args.steps / total_ms,
                 "note": "kernel is issue-bound, not HBM-bound: ~1.2k instructions per vehicle-second x5 "
                         "fused sub-steps per 32 B of state traffic (DESIGN.md §5)"}
     cb = None
@@ -285,16 +330,21 @@ def main():
         cb, _, _, _ = cpu_reference(net, par, args, cores, budget_s=10.0)
     line = {"metric": "agent-env-steps/sec", "value": value, "unit": "agent-env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if (mode == "sim" or args.fp32_gemm) else "f32 (sim, cell, loss, optimizer) + tf32 GEMMs",
             "data": "synthetic",
             "config": {"workload": workload_name(R, mode), "replicas_per_gpu": R, "agents": net.n_nodes,
-                       "burnin_control_steps": args.burnin, "mode": mode,
+                       "burnin_control_steps": args.burnin, "mode": mode, "n_step": N_STEP,
+                       "updates_in_timed_region": n_updates_timed,
+                       "learner_gemm_library": "cuBLAS %s (3 plain batched GEMMs per update chunk + 1 per step)"
+                       % ("fp32" if args.fp32_gemm else "TF32 tensor cores, fp32 accumulate")
+                       if mode == "train" else None,
                        "l2": "inputs larger than L2: %.0f MB of replica state per GPU is streamed every step"
                              % (R * sim.info()["state_bytes_per_replica"] / 1e6),
                        "parallelism": "replica-dp%d" % world},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "tsc_step_host (pinned host buffers)"},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": timed_launches,
             "roofline": roofline, "cpu_baseline": cb}
     print(json.dumps(line))

@@ -36,7 +36,7 @@ class BatchedA2C:
                  v_coef: float = 0.5, max_grad_norm: float = 40.0, alpha: float = 0.99, eps: float = 1e-5,
                  reward_norm: float = 1.0, reward_clip: float = 0.0, seed: int = 0, device: int = 0,
                  chunk: int = 1024, replica0: int = 0, total_replicas: Optional[int] = None,
-                 process_group=None, allow_tf32: bool = False):
+                 process_group=None, allow_tf32: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedA2C needs a CUDA device (no CPU fallback exists)")
         self.lay, self.R, self.T = layout, int(n_replicas), int(n_step)
@@ -125,7 +125,7 @@ class BatchedA2C:
                                      _p(self.X1), self._st()))
         torch.baddbmm(self.pv["bl"].unsqueeze(1), self.X1, self.pv["wx"], out=self.Z1)
         c1, h1 = (self.c_fw, self.h_fw) if commit else (self.c_tmp, self.h_tmp)
-        _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(self.Z1), None, _p(self.H1), _p(self.c_fw),
+        _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(self.Z1), None, _p(self.H1), None, _p(self.c_fw),
                                          _p(self.h_fw), _p(c1), _p(h1), _p(dflag), C.c_int32(1), C.c_int64(R),
                                          C.c_int64(R), C.c_int64(0), self._st()))
         want_act = sample and commit
@@ -141,9 +141,10 @@ class BatchedA2C:
     def obs_slot(self, t: Optional[int] = None) -> torch.Tensor:
         return self.obs_hist[self.t if t is None else t]
 
-    def add_transition(self, reward: torch.Tensor, done_pre: bool, done_post: bool):
-        """Record step t: obs must already be in obs_slot(t) (the env writes there), actions and
-        values are the ones of the last forward().  agents/models.py:222-229."""
+    def add_transition(self, reward: torch.Tensor, done_pre: bool, done_post: bool,
+                       act: Optional[torch.Tensor] = None, val: Optional[torch.Tensor] = None):
+        """Record step t: obs must already be in obs_slot(t) (the env writes there); actions and
+        values default to the ones of the last forward().  agents/models.py:222-229."""
         t = self.t
         r = reward
         if self.reward_norm:
@@ -151,8 +152,8 @@ class BatchedA2C:
         if self.reward_clip:
             r = torch.clamp(r, -self.reward_clip, self.reward_clip)
         self.rew_hist[t].copy_(r)
-        self.act_hist[t].copy_(self.act)
-        self.val_hist[t].copy_(self.val)
+        self.act_hist[t].copy_(self.act if act is None else act)
+        self.val_hist[t].copy_(self.val if val is None else val)
         self.done_pre[t] = 1.0 if done_pre else 0.0
         self.done_post[t] = 1.0 if done_post else 0.0
         self.t += 1
@@ -187,7 +188,6 @@ class BatchedA2C:
         self.G.zero_()
         self.stats.zero_()
         scale = 1.0 / (T * self.total_replicas)
-        keep = (1.0 - dpre).view(1, T, 1, 1)
         n_obs = L.n_obs
         for r0 in range(0, R, self.chunk):
             rc = min(self.chunk, R - r0)
@@ -202,7 +202,7 @@ class BatchedA2C:
             _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs0), C.c_int64(M), C.c_int64(rc),
                                          C.c_int64(R * n_obs), _p(X), st()))
             torch.baddbmm(self.pv["bl"].unsqueeze(1), X, self.pv["wx"], out=ZG)
-            _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(H), _p(self.c_bw), _p(self.h_bw),
+            _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(H), _p(Hp), _p(self.c_bw), _p(self.h_bw),
                                              None, None, _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R),
                                              C.c_int64(r0), st()))
             _lib.check(lib.tscl_heads_loss(self._h, _p(self.P), _p(H), _p(self.act_hist[0, r0:]), _p(self.Rs[0, r0:]),
@@ -212,11 +212,6 @@ class BatchedA2C:
             # head weight / bias gradients (plain batched GEMM + column sums)
             self.gv["wo"].baddbmm_(H.transpose(1, 2), dlog)
             self.gv["bo"].add_(dlog.sum(dim=1))
-            # h_{t-1} masked, the second operand of the recurrent weight gradient
-            Hp4, H4 = Hp.view(U, T, rc, L.h), H.view(U, T, rc, L.h)
-            Hp4[:, 1:].copy_(H4[:, :-1])
-            Hp4[:, 0].copy_(self.h_bw[:, r0:r0 + rc])
-            Hp4.mul_(keep)
             _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
                                              C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
             dZ = ZG

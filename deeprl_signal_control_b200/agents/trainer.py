@@ -1,0 +1,116 @@
+"""Device-resident training loop: the batched counterpart of reference utils.py:Trainer.explore/run.
+
+Per control step (utils.py:146-165): policy/value forward -> fingerprint update (MA2C) -> action
+sampling -> env.step -> add_transition; per n_step: bootstrap value, backward (utils.py:186-190,
+288-291); per episode: env.reset(), model.reset(), pre-decision done = True (utils.py:277-281).
+Everything stays on the GPU: the simulator writes the next observation straight into the
+learner's rollout slot and reads actions / fingerprints from the learner's buffers.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ..sim import BatchedSim
+from .learner import BatchedA2C
+
+
+class BatchedTrainer:
+    def __init__(self, sim: BatchedSim, model: BatchedA2C, agent: str, lr: float, beta: float,
+                 seed0: int = 12, replica0: int = 0):
+        self.sim, self.model, self.agent = sim, model, agent
+        self.lr, self.beta = lr, beta
+        self.seed, self.replica0 = seed0, replica0
+        self.T_episode = int(np.ceil(sim.params.episode_length_sec / sim.params.control_interval_sec))
+        assert self.T_episode % model.T == 0                      # utils.py:121
+        self.step_in_episode = 0
+        self.done = True
+        self.episode_rewards = []
+        self._rew_acc = torch.zeros(sim.R, device=sim.device)
+        self.n_updates = 0
+        self.n_env_steps = 0
+        self._uniform_fp = None
+        self.sim_events = None        # list of (start, end) CUDA events around tsc_step when timing is on
+        self.start_episode()
+
+    def start_episode(self):
+        sim, m = self.sim, self.model
+        seeds = np.arange(sim.R, dtype=np.uint64) + np.uint64(self.seed + self.replica0)
+        self.seed += max(sim.R, 1)                                 # envs/env.py:560 (seed += 1 per episode, per replica)
+        sim.reset(seeds)
+        sim.set_train_mode(True)
+        m.reset()
+        fp = None
+        if self.agent == 'ma2c':
+            if self._uniform_fp is None:
+                n = sim.net
+                u = torch.zeros(sim.R, n.n_nodes, n.max_na, device=sim.device)
+                for i, na in enumerate(n.n_a_ls):
+                    u[:, i, :na] = 1.0 / na                       # envs/env.py:263-269
+                self._uniform_fp = u
+            fp = self._uniform_fp
+        assert m.t == 0
+        sim.observe(fp, obs_out=m.obs_slot(0))
+        self.step_in_episode = 0
+        self.done = True
+        self._rew_acc.zero_()
+
+    def control_step(self):
+        """One control step of all replicas (utils.py:146-165)."""
+        sim, m = self.sim, self.model
+        t = m.t
+        pi, val, act = m.forward(m.obs_slot(t), self.done)
+        fp = pi if self.agent == 'ma2c' else None                 # env.update_fingerprint(policy)
+        if self.sim_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _, reward, greward, _ = sim.step(act, fp, obs_out=m.obs_hist[t + 1])
+        if self.sim_events is not None:
+            e1.record()
+            self.sim_events.append((e0, e1))
+        self.step_in_episode += 1
+        new_done = self.step_in_episode >= self.T_episode         # lock-step: envs/env.py:577-579
+        m.add_transition(reward, self.done, new_done)
+        self._rew_acc.add_(greward)
+        self.done = new_done
+        self.n_env_steps += 1
+        if m.t == m.T:
+            self.update()
+
+    def control_step_host(self):
+        """Same step with the environment driven through the HOST-buffer C-ABI call (tsc_step_host),
+        i.e. the way a reference-style caller holds numpy arrays: actions / fingerprints D2H, env step
+        (H2D + kernel + D2H inside), observation / reward H2D into the learner."""
+        sim, m = self.sim, self.model
+        t = m.t
+        pi, val, act = m.forward(m.obs_slot(t), self.done)
+        act_h = act.cpu().numpy()
+        fp_h = pi.cpu().numpy() if self.agent == 'ma2c' else None
+        obs_h, rew_h, grew_h, _ = sim.step_host(act_h, fp_h)
+        m.obs_hist[t + 1].copy_(torch.from_numpy(obs_h), non_blocking=True)
+        reward = torch.from_numpy(rew_h).to(sim.device, non_blocking=True)
+        self.step_in_episode += 1
+        new_done = self.step_in_episode >= self.T_episode
+        m.add_transition(reward, self.done, new_done)
+        self._rew_acc.add_(torch.from_numpy(grew_h).to(sim.device, non_blocking=True))
+        self.done = new_done
+        self.n_env_steps += 1
+        if m.t == m.T:
+            self.update()
+
+    def update(self):
+        m = self.model
+        boot = None
+        if not self.done:
+            _, boot, _ = m.forward(m.obs_slot(m.T), False, out_type='v')    # utils.py:190
+        m.backward(boot, self.lr, self.beta)
+        self.n_updates += 1
+        if self.done:
+            self.episode_rewards.append(float((self._rew_acc / self.T_episode).mean()))   # utils.py:296-305
+            self.start_episode()
+
+    def run(self, n_control_steps: int):
+        for _ in range(n_control_steps):
+            self.control_step()

@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t lmix32(uint32_t h) {
 
 // ------------------------------------------------------------------------------------------------
 // fc front end.  grid (ceil(M/64), 2A), 256 threads.
-#define FE_ROWS 64
+#define FE_ROWS 128
 __global__ void __launch_bounds__(256)
 fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ obs, int64_t M,
                 int64_t rows_per_t, int64_t stride_t, float* __restrict__ X) {
@@ -111,7 +111,8 @@ fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restr
 #define LS_ROWS 32
 __global__ void __launch_bounds__(256)
 lstm_seq_fwd_kernel(const DDims d, const float* __restrict__ P, float* __restrict__ ZG, float* __restrict__ C,
-                    float* __restrict__ Hout, const float* __restrict__ c0, const float* __restrict__ h0,
+                    float* __restrict__ Hout, float* __restrict__ Hprev, const float* __restrict__ c0,
+                    const float* __restrict__ h0,
                     float* __restrict__ c1, float* __restrict__ h1, const float* __restrict__ done, int T,
                     int64_t Rc, int64_t ld_state, int64_t r0) {
   extern __shared__ float sm[];
@@ -149,6 +150,11 @@ lstm_seq_fwd_kernel(const DDims d, const float* __restrict__ P, float* __restric
         acc[q][g][0] = z.x; acc[q][g][1] = z.y;
       }
       if (dn) { c[q][0] = 0.f; c[q][1] = 0.f; }
+      if (Hprev && r < Rc) {
+        float2 hp = make_float2(0.f, 0.f);
+        if (!dn) hp = *reinterpret_cast<const float2*>(&sh[(ty * 4 + q) * H64 + j0]);
+        *reinterpret_cast<float2*>(Hprev + (((int64_t)u * T + t) * Rc + r) * H64 + j0) = hp;
+      }
     }
     if (!dn) {
 #pragma unroll 4
@@ -500,7 +506,7 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
     else if (e < E) { kin[q] = -1; col[q] = e - (eW + eF + eT); }
   }
   const int ooff = d.obs_off[a];
-  const int64_t m_lo = (int64_t)blockIdx.x * FB_SLAB;
+  for (int64_t m_lo = (int64_t)blockIdx.x * FB_SLAB; m_lo < M; m_lo += (int64_t)gridDim.x * FB_SLAB) {
   const int64_t m_hi = m_lo + FB_SLAB < M ? m_lo + FB_SLAB : M;
   for (int64_t mb = m_lo; mb < m_hi; mb += FB_ROWS) {
     for (int i = tid; i < FB_ROWS * n_in; i += 256) {
@@ -533,6 +539,7 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
       acc[q] += s;
     }
     __syncthreads();
+  }
   }
 #pragma unroll
   for (int q = 0; q < FB_MAXE; ++q) {
@@ -648,14 +655,14 @@ extern "C" int tscl_fc_embed(tscl_handle* h, const float* params, const float* o
   return 0;
 }
 
-extern "C" int tscl_lstm_seq_fwd(tscl_handle* h, const float* params, float* ZG, float* C, float* H, const float* c0,
-                                 const float* h0, float* c1, float* h1, const float* done, int32_t T, int64_t Rc,
-                                 int64_t ld_state, int64_t r0, void* stream) {
+extern "C" int tscl_lstm_seq_fwd(tscl_handle* h, const float* params, float* ZG, float* C, float* H, float* Hprev,
+                                 const float* c0, const float* h0, float* c1, float* h1, const float* done, int32_t T,
+                                 int64_t Rc, int64_t ld_state, int64_t r0, void* stream) {
   if (!h || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_fwd: bad argument");
   LCK(cudaSetDevice(h->device));
   dim3 grid((unsigned)((Rc + LS_ROWS - 1) / LS_ROWS), 2 * h->d.A);
   lstm_seq_fwd_kernel<<<grid, 256, (H64 * G4 + LS_ROWS * H64) * 4, (cudaStream_t)stream>>>(
-      h->d, params, ZG, C, H, c0, h0, c1, h1, done, T, Rc, ld_state, r0);
+      h->d, params, ZG, C, H, Hprev, c0, h0, c1, h1, done, T, Rc, ld_state, r0);
   LCK(cudaGetLastError());
   return 0;
 }
@@ -714,7 +721,9 @@ extern "C" int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, con
                            int64_t rows_per_t, int64_t stride_t, float* grads, void* stream) {
   if (!h || M <= 0) return tsc_set_error("tscl_fc_bwd: bad argument");
   LCK(cudaSetDevice(h->device));
-  dim3 grid((unsigned)((M + FB_SLAB - 1) / FB_SLAB), 2 * h->d.A);
+  int64_t nslab = (M + FB_SLAB - 1) / FB_SLAB;
+  if (nslab > 12) nslab = 12;          // 12 x 2A CTAs ~ 4 waves of 148 SMs; atomics per address <= 12
+  dim3 grid((unsigned)nslab, 2 * h->d.A);
   const int smem = FB_ROWS * (h->max_in + h->d.dx) * 4;
   fc_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(h->d, obs, X, dX, M, rows_per_t, stride_t, grads);
   LCK(cudaGetLastError());

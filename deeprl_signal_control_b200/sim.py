@@ -66,21 +66,27 @@ class BatchedSim:
     def set_train_mode(self, train: bool) -> None:
         _lib.check(_lib.lib().tsc_set_train_mode(self._h, C.c_int32(int(train))))
 
-    def observe(self, fp: Optional[torch.Tensor] = None) -> torch.Tensor:
-        _lib.check(_lib.lib().tsc_observe(self._h, _ptr(fp), _ptr(self.obs), self._stream()))
-        return self.obs
+    def observe(self, fp: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        obs = self.obs if obs_out is None else obs_out
+        _lib.check(_lib.lib().tsc_observe(self._h, _ptr(fp), _ptr(obs), self._stream()))
+        return obs
 
-    def step(self, action: torch.Tensor, fp: Optional[torch.Tensor] = None):
+    def step(self, action: torch.Tensor, fp: Optional[torch.Tensor] = None,
+             obs_out: Optional[torch.Tensor] = None):
         """action int32 [R, n_nodes] on the device; fp float32 [R, n_nodes, max_na] or None.
-        Returns views of the persistent output tensors (obs, reward, global_reward, done)."""
+        `obs_out` (contiguous [R, n_obs] device tensor) lets the caller receive the observation in
+        its own buffer (the learner's rollout slot) without a copy.
+        Returns the output tensors (obs, reward, global_reward, done)."""
         assert action.dtype == torch.int32 and action.is_cuda and action.is_contiguous()
         assert action.numel() == self.R * self.net.n_nodes
         if fp is not None:
             assert fp.dtype == torch.float32 and fp.is_contiguous()
             assert fp.numel() == self.R * self.net.n_nodes * self.net.max_na
-        _lib.check(_lib.lib().tsc_step(self._h, _ptr(action), _ptr(fp), _ptr(self.obs), _ptr(self.reward),
+        obs = self.obs if obs_out is None else obs_out
+        assert obs.is_contiguous() and obs.numel() == self.R * self.net.n_obs
+        _lib.check(_lib.lib().tsc_step(self._h, _ptr(action), _ptr(fp), _ptr(obs), _ptr(self.reward),
                                        _ptr(self.greward), _ptr(self.done), self._stream()))
-        return self.obs, self.reward, self.greward, self.done
+        return obs, self.reward, self.greward, self.done
 
     def step_host(self, action: np.ndarray, fp: Optional[np.ndarray] = None):
         """Host-buffer entry point (`tsc_step_host`): numpy in, numpy out, copies included."""

@@ -64,11 +64,12 @@ int tscl_fc_embed(tscl_handle* h, const float* params, const float* obs, int64_t
 /* LSTM over T steps (agents/utils.py:88-116): recurrent GEMM h.Wh + fused cell.
  *   ZG   [2A][T*Rc][4h]  in: X.Wx + b (time-major rows m = t*Rc + r); out: gate activations i,f,o,u
  *   C,H  [2A][T*Rc][h]   out (may be NULL when T == 1 and only states are wanted)
+ *   Hprev [2A][T*Rc][h]  out, may be NULL: the masked h_{t-1} each step consumed (operand of dWh)
  *   c0,h0 [2A][ld_state][h] initial state rows r0 .. r0+Rc;  c1,h1: final state (may alias c0,h0, may be NULL)
  *   done [T] float (pre-step done: state is zeroed BEFORE the cell, agents/utils.py:104-105) */
-int tscl_lstm_seq_fwd(tscl_handle* h, const float* params, float* ZG, float* C, float* H, const float* c0,
-                      const float* h0, float* c1, float* h1, const float* done, int32_t T, int64_t Rc,
-                      int64_t ld_state, int64_t r0, void* stream);
+int tscl_lstm_seq_fwd(tscl_handle* h, const float* params, float* ZG, float* C, float* H, float* Hprev,
+                      const float* c0, const float* h0, float* c1, float* h1, const float* done, int32_t T,
+                      int64_t Rc, int64_t ld_state, int64_t r0, void* stream);
 
 /* Heads for one control step (agents/policies.py:18-26, utils.py:155-157): softmax policy, value,
  * categorical sample with the counter-based RNG keyed (seed, step, replica0 + r, agent).

@@ -29,7 +29,7 @@ def test_forward_matches_oracle(ff):
     from oracle.learner_ref import unit_forward
     lay = _layout(ff)
     R = 37
-    m = BatchedA2C(lay, R, n_step=4, seed=3)
+    m = BatchedA2C(lay, R, n_step=4, seed=3, allow_tf32=False)
     P = m.P.cpu().numpy()
     # non-zero biases so that they are exercised
     P = P + np.random.default_rng(0).normal(0, 0.05, P.shape).astype(np.float32) * (P == 0)
@@ -86,7 +86,7 @@ def test_backward_gradients_match_autograd(ff, chunk):
     R, T = 37, 6
     gamma, v_coef, beta = 0.99, 0.5, 0.01
     m = BatchedA2C(lay, R, n_step=T, gamma=gamma, v_coef=v_coef, max_grad_norm=0.0, seed=7, chunk=chunk,
-                   reward_norm=3.0, reward_clip=2.0)
+                   reward_norm=3.0, reward_clip=2.0, allow_tf32=False)
     rng = np.random.default_rng(2)
     P0 = m.P.cpu().numpy().copy()
     # start the rollout from a non-zero recurrent state

@@ -53,55 +53,79 @@ __device__ __forceinline__ uint32_t lmix32(uint32_t h) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// fc front end.  grid (ceil(M/64), 2A), 256 threads.
-#define FE_ROWS 128
+// fc front end.  grid (n_row_groups, 2A), 256 threads.  Thread = output column (dx <= 256): its weight
+// column (<= 32 values) lives in registers, each staged row costs one broadcast LDS.128 per 4 FMAs.
+#define FE_ROWS 64
+#define FE_KW 32   // padded inputs of the wave layer
+#define FE_KF 16   // fingerprint layer
+#define FE_KT 16   // wait layer
+#define FE_KTOT (FE_KW + FE_KF + FE_KT)
 __global__ void __launch_bounds__(256)
 fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ obs, int64_t M,
                 int64_t rows_per_t, int64_t stride_t, float* __restrict__ X) {
-  extern __shared__ float sm[];
+  __shared__ __align__(16) float sIn[FE_ROWS * FE_KTOT];
   const int u = blockIdx.y, a = u >> 1, tid = threadIdx.x;
   const int nw = d.n_wave[a], nt = d.n_wait[a], nf = d.ff > 0 ? d.n_fp[a] : 0;
-  const int n_in = nw + nt + nf;
-  float* sW = sm;                       // [nw][fw]
-  float* sF = sW + nw * d.fw;           // [nf][ff]
-  float* sT = sF + nf * d.ff;           // [nt][ft]
-  float* sB = sT + nt * d.ft;           // [dx]
-  float* sIn = sB + d.dx;               // [FE_ROWS][n_in]
-  for (int i = tid; i < nw * d.fw; i += 256) sW[i] = P[d.off_fcw_w[u] + i];
-  for (int i = tid; i < nf * d.ff; i += 256) sF[i] = P[d.off_fcf_w[u] + i];
-  for (int i = tid; i < nt * d.ft; i += 256) sT[i] = P[d.off_fct_w[u] + i];
-  for (int i = tid; i < d.fw; i += 256) sB[i] = P[d.off_fcw_b[u] + i];
-  for (int i = tid; i < d.ff; i += 256) sB[d.fw + i] = P[d.off_fcf_b[u] + i];
-  for (int i = tid; i < d.ft; i += 256) sB[d.fw + d.ff + i] = P[d.off_fct_b[u] + i];
-  const int64_t m0 = (int64_t)blockIdx.x * FE_ROWS;
-  const int ooff = d.obs_off[a];
-  for (int i = tid; i < FE_ROWS * n_in; i += 256) {
-    const int row = i / n_in, k = i - row * n_in;
-    const int64_t m = m0 + row;
-    float v = 0.f;
-    if (m < M) v = obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k];
-    sIn[i] = v;
-  }
-  __syncthreads();
-  const int dx = d.dx;
-  float* Xu = X + ((int64_t)u * M + m0) * dx;
-  for (int i = tid; i < FE_ROWS * dx; i += 256) {
-    const int row = i / dx, col = i - row * dx;
-    if (m0 + row >= M) break;
-    const float* in = sIn + row * n_in;
-    float acc = sB[col];
+  const int dx = d.dx, col = tid;
+  // this thread's weight column
+  float w[FE_KW];
+  float bias = 0.f;
+  int kbase = 0, nk = 0;
+#pragma unroll
+  for (int k = 0; k < FE_KW; ++k) w[k] = 0.f;
+  if (col < dx) {
     if (col < d.fw) {
-      for (int k = 0; k < nw; ++k) acc = fmaf(in[k], sW[k * d.fw + col], acc);
+      nk = nw; kbase = 0;
+      for (int k = 0; k < FE_KW; ++k) if (k < nw) w[k] = P[d.off_fcw_w[u] + (int64_t)k * d.fw + col];
+      bias = P[d.off_fcw_b[u] + col];
     } else if (col < d.fw + d.ff) {
-      const int c = col - d.fw;
-      const float* inf_ = in + nw + nt;
-      for (int k = 0; k < nf; ++k) acc = fmaf(inf_[k], sF[k * d.ff + c], acc);
+      nk = nf; kbase = FE_KW;
+      for (int k = 0; k < FE_KF; ++k) if (k < nf) w[k] = P[d.off_fcf_w[u] + (int64_t)k * d.ff + (col - d.fw)];
+      bias = P[d.off_fcf_b[u] + (col - d.fw)];
     } else {
-      const int c = col - d.fw - d.ff;
-      const float* int_ = in + nw;
-      for (int k = 0; k < nt; ++k) acc = fmaf(int_[k], sT[k * d.ft + c], acc);
+      nk = nt; kbase = FE_KW + FE_KF;
+      for (int k = 0; k < FE_KT; ++k) if (k < nt) w[k] = P[d.off_fct_w[u] + (int64_t)k * d.ft + (col - d.fw - d.ff)];
+      bias = P[d.off_fct_b[u] + (col - d.fw - d.ff)];
     }
-    Xu[(int64_t)row * dx + col] = fmaxf(acc, 0.f);
+  }
+  const int nk4 = (nk + 3) >> 2;
+  const int ooff = d.obs_off[a];
+  const int n_in = nw + nt + nf;
+  for (int64_t m0 = (int64_t)blockIdx.x * FE_ROWS; m0 < M; m0 += (int64_t)gridDim.x * FE_ROWS) {
+    __syncthreads();
+    // stage rows: [wave | pad][fp | pad][wait | pad]
+    for (int i = tid; i < FE_ROWS * FE_KTOT; i += 256) sIn[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < FE_ROWS * n_in; i += 256) {
+      const int row = i / n_in, k = i - row * n_in;
+      const int64_t m = m0 + row;
+      if (m < M) {
+        const float v = obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k];
+        int dst;
+        if (k < nw) dst = k;
+        else if (k < nw + nt) dst = FE_KW + FE_KF + (k - nw);
+        else dst = FE_KW + (k - nw - nt);
+        sIn[row * FE_KTOT + dst] = v;
+      }
+    }
+    __syncthreads();
+    if (col < dx) {
+      const int rows = (M - m0) < FE_ROWS ? (int)(M - m0) : FE_ROWS;
+      float* Xu = X + ((int64_t)u * M + m0) * dx + col;
+      for (int row = 0; row < rows; ++row) {
+        const float4* in4 = reinterpret_cast<const float4*>(&sIn[row * FE_KTOT + kbase]);
+        float acc = bias;
+#pragma unroll
+        for (int k4 = 0; k4 < FE_KW / 4; ++k4) {
+          if (k4 < nk4) {
+            const float4 x = in4[k4];
+            acc = fmaf(x.x, w[4 * k4], acc); acc = fmaf(x.y, w[4 * k4 + 1], acc);
+            acc = fmaf(x.z, w[4 * k4 + 2], acc); acc = fmaf(x.w, w[4 * k4 + 3], acc);
+          }
+        }
+        Xu[(int64_t)row * dx] = fmaxf(acc, 0.f);
+      }
+    }
   }
 }
 
@@ -122,7 +146,8 @@ lstm_seq_fwd_kernel(const DDims d, const float* __restrict__ P, float* __restric
   const float* Wh = P + d.off_wh + (int64_t)u * H64 * G4;
   for (int i = tid; i < H64 * G4 / 4; i += 256)
     reinterpret_cast<float4*>(sWh)[i] = reinterpret_cast<const float4*>(Wh)[i];
-  const int64_t rbase = (int64_t)blockIdx.x * LS_ROWS;
+  for (int64_t rbase = (int64_t)blockIdx.x * LS_ROWS; rbase < Rc; rbase += (int64_t)gridDim.x * LS_ROWS) {
+  __syncthreads();   // previous tile done with sh
   float c[4][2];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -209,6 +234,7 @@ lstm_seq_fwd_kernel(const DDims d, const float* __restrict__ P, float* __restric
         *reinterpret_cast<float2*>(h1 + s) = *reinterpret_cast<float2*>(&sh[(ty * 4 + q) * H64 + j0]);
       }
     }
+  }
   }
 }
 
@@ -479,83 +505,69 @@ lstm_seq_bwd_kernel(const DDims d, const float* __restrict__ P, float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// fc front-end backward.  grid (n_slabs, 2A), 256 threads; slab = FB_SLAB rows, staged FB_ROWS at a time.
-#define FB_SLAB 512
-#define FB_ROWS 16
-#define FB_MAXE 24
+// fc front-end backward.  grid (n_groups, 2A), 256 threads.  Thread = column c of dX: accumulates
+// dW[k][c] for every input k of its layer (<= 32 registers) + the bias gradient; rows staged 32 at a time.
+#define FB_ROWS 32
 __global__ void __launch_bounds__(256)
 fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restrict__ X, const float* __restrict__ dX,
               int64_t M, int64_t rows_per_t, int64_t stride_t, float* __restrict__ G) {
-  extern __shared__ float sm[];
+  __shared__ __align__(16) float sIn[FB_ROWS * FE_KTOT];
   const int u = blockIdx.y, a = u >> 1, tid = threadIdx.x;
   const int nw = d.n_wave[a], nt = d.n_wait[a], nf = d.ff > 0 ? d.n_fp[a] : 0;
-  const int n_in = nw + nt + nf, dx = d.dx;
-  const int eW = nw * d.fw, eF = nf * d.ff, eT = nt * d.ft, E = eW + eF + eT + dx;
-  float* sIn = sm;                       // [FB_ROWS][n_in]
-  float* sD = sm + FB_ROWS * n_in;       // [FB_ROWS][dx]
-  float acc[FB_MAXE];
-  int kin[FB_MAXE], col[FB_MAXE];        // -1 kin = bias element
+  const int n_in = nw + nt + nf, dx = d.dx, col = tid;
+  int kbase = 0, nk = 0;
+  if (col < d.fw) { nk = nw; kbase = 0; }
+  else if (col < d.fw + d.ff) { nk = nf; kbase = FE_KW; }
+  else if (col < dx) { nk = nt; kbase = FE_KW + FE_KF; }
+  const int nk4 = (nk + 3) >> 2;
+  float acc[FE_KW];
 #pragma unroll
-  for (int q = 0; q < FB_MAXE; ++q) {
-    acc[q] = 0.f;
-    int e = tid + q * 256;
-    kin[q] = -2; col[q] = 0;
-    if (e < eW) { kin[q] = e / d.fw; col[q] = e % d.fw; }
-    else if (e < eW + eF) { e -= eW; kin[q] = nw + nt + e / d.ff; col[q] = d.fw + e % d.ff; }
-    else if (e < eW + eF + eT) { e -= eW + eF; kin[q] = nw + e / d.ft; col[q] = d.fw + d.ff + e % d.ft; }
-    else if (e < E) { kin[q] = -1; col[q] = e - (eW + eF + eT); }
-  }
+  for (int k = 0; k < FE_KW; ++k) acc[k] = 0.f;
+  float accb = 0.f;
   const int ooff = d.obs_off[a];
-  for (int64_t m_lo = (int64_t)blockIdx.x * FB_SLAB; m_lo < M; m_lo += (int64_t)gridDim.x * FB_SLAB) {
-  const int64_t m_hi = m_lo + FB_SLAB < M ? m_lo + FB_SLAB : M;
-  for (int64_t mb = m_lo; mb < m_hi; mb += FB_ROWS) {
+  for (int i = tid; i < FB_ROWS * FE_KTOT; i += 256) sIn[i] = 0.f;
+  for (int64_t m0 = (int64_t)blockIdx.x * FB_ROWS; m0 < M; m0 += (int64_t)gridDim.x * FB_ROWS) {
+    __syncthreads();
     for (int i = tid; i < FB_ROWS * n_in; i += 256) {
       const int row = i / n_in, k = i - row * n_in;
-      const int64_t m = mb + row;
-      sIn[i] = m < m_hi ? obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k] : 0.f;
-    }
-    for (int i = tid; i < FB_ROWS * dx; i += 256) {
-      const int row = i / dx, c = i - row * dx;
-      const int64_t m = mb + row;
+      const int64_t m = m0 + row;
       float v = 0.f;
-      if (m < m_hi) {
-        const int64_t o = ((int64_t)u * M + m) * dx + c;
-        v = X[o] > 0.f ? dX[o] : 0.f;
-      }
-      sD[i] = v;
+      if (m < M) v = obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k];
+      int dst;
+      if (k < nw) dst = k;
+      else if (k < nw + nt) dst = FE_KW + FE_KF + (k - nw);
+      else dst = FE_KW + (k - nw - nt);
+      sIn[row * FE_KTOT + dst] = v;
     }
     __syncthreads();
+    if (col < dx) {
+      const int rows = (M - m0) < FB_ROWS ? (int)(M - m0) : FB_ROWS;
+      const int64_t o0 = ((int64_t)u * M + m0) * dx + col;
+      for (int row = 0; row < rows; ++row) {
+        const int64_t o = o0 + (int64_t)row * dx;
+        const float g = X[o] > 0.f ? dX[o] : 0.f;       // relu mask
+        accb += g;
+        const float4* in4 = reinterpret_cast<const float4*>(&sIn[row * FE_KTOT + kbase]);
 #pragma unroll
-    for (int q = 0; q < FB_MAXE; ++q) {
-      if (kin[q] == -2) continue;
-      float s = 0.f;
-      if (kin[q] >= 0) {
-#pragma unroll
-        for (int row = 0; row < FB_ROWS; ++row) s = fmaf(sIn[row * n_in + kin[q]], sD[row * dx + col[q]], s);
-      } else {
-#pragma unroll
-        for (int row = 0; row < FB_ROWS; ++row) s += sD[row * dx + col[q]];
+        for (int k4 = 0; k4 < FE_KW / 4; ++k4) {
+          if (k4 < nk4) {
+            const float4 x = in4[k4];
+            acc[4 * k4] = fmaf(x.x, g, acc[4 * k4]); acc[4 * k4 + 1] = fmaf(x.y, g, acc[4 * k4 + 1]);
+            acc[4 * k4 + 2] = fmaf(x.z, g, acc[4 * k4 + 2]); acc[4 * k4 + 3] = fmaf(x.w, g, acc[4 * k4 + 3]);
+          }
+        }
       }
-      acc[q] += s;
     }
-    __syncthreads();
   }
-  }
+  if (col < dx) {
+    int64_t wo, bo; int ld, c;
+    if (col < d.fw) { wo = d.off_fcw_w[u]; bo = d.off_fcw_b[u]; ld = d.fw; c = col; }
+    else if (col < d.fw + d.ff) { wo = d.off_fcf_w[u]; bo = d.off_fcf_b[u]; ld = d.ff; c = col - d.fw; }
+    else { wo = d.off_fct_w[u]; bo = d.off_fct_b[u]; ld = d.ft; c = col - d.fw - d.ff; }
 #pragma unroll
-  for (int q = 0; q < FB_MAXE; ++q) {
-    int e = tid + q * 256;
-    if (kin[q] == -2) continue;
-    int64_t off;
-    if (e < eW) off = d.off_fcw_w[u] + e;
-    else if (e < eW + eF) off = d.off_fcf_w[u] + (e - eW);
-    else if (e < eW + eF + eT) off = d.off_fct_w[u] + (e - eW - eF);
-    else {
-      const int c = e - (eW + eF + eT);
-      if (c < d.fw) off = d.off_fcw_b[u] + c;
-      else if (c < d.fw + d.ff) off = d.off_fcf_b[u] + (c - d.fw);
-      else off = d.off_fct_b[u] + (c - d.fw - d.ff);
-    }
-    atomicAdd(&G[off], acc[q]);
+    for (int k = 0; k < FE_KW; ++k)
+      if (k < nk) atomicAdd(&G[wo + (int64_t)k * ld + c], acc[k]);
+    atomicAdd(&G[bo + c], accb);
   }
 }
 
@@ -628,10 +640,13 @@ extern "C" int tscl_create(const tscl_dims* x, int32_t device, tscl_handle** out
     if (n_in > h->max_in) h->max_in = n_in;
     if (w > h->max_fcw) h->max_fcw = w;
   }
-  if (h->max_fcw > FB_MAXE * 256) { tscl_destroy(h); return tsc_set_error("tscl_create: fc layer too large for fc_bwd_kernel"); }
+  for (size_t a = 0; a < A; ++a)
+    if (x->n_wave[a] > FE_KW || (x->ff > 0 && x->n_fp[a] > FE_KF) || x->n_wait[a] > FE_KT || x->dx > 256) {
+      tscl_destroy(h);
+      return tsc_set_error("tscl_create: fc input widths exceed the kernel limits (wave 32, fp 16, wait 16, dx 256)");
+    }
   LCK(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (H64 * G4 + LS_ROWS * H64) * 4));
   LCK(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (G4 * H64 + LS_ROWS * G4) * 4));
-  LCK(cudaFuncSetAttribute(fc_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (h->max_fcw + FE_ROWS * h->max_in) * 4));
   *out = h;
   return 0;
 }
@@ -648,8 +663,10 @@ extern "C" int tscl_fc_embed(tscl_handle* h, const float* params, const float* o
                              int64_t stride_t, float* X, void* stream) {
   if (!h || M <= 0) return tsc_set_error("tscl_fc_embed: bad argument");
   LCK(cudaSetDevice(h->device));
-  dim3 grid((unsigned)((M + FE_ROWS - 1) / FE_ROWS), 2 * h->d.A);
-  fc_embed_kernel<<<grid, 256, (h->max_fcw + FE_ROWS * h->max_in) * 4, (cudaStream_t)stream>>>(
+  int64_t ng = (M + FE_ROWS - 1) / FE_ROWS;
+  if (ng > 24) ng = 24;                 // 24 x 2A CTAs (~8 per SM): the weight column load is amortised over many rows
+  dim3 grid((unsigned)ng, 2 * h->d.A);
+  fc_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       h->d, params, obs, M, rows_per_t, stride_t, X);
   LCK(cudaGetLastError());
   return 0;
@@ -660,7 +677,9 @@ extern "C" int tscl_lstm_seq_fwd(tscl_handle* h, const float* params, float* ZG,
                                  int64_t Rc, int64_t ld_state, int64_t r0, void* stream) {
   if (!h || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_fwd: bad argument");
   LCK(cudaSetDevice(h->device));
-  dim3 grid((unsigned)((Rc + LS_ROWS - 1) / LS_ROWS), 2 * h->d.A);
+  int64_t nt = (Rc + LS_ROWS - 1) / LS_ROWS;
+  if (T == 1 && nt > 9) nt = 9;        // rollout step: 9 x 2A CTAs = 3 per SM, each walks many row tiles with Wh resident
+  dim3 grid((unsigned)nt, 2 * h->d.A);
   lstm_seq_fwd_kernel<<<grid, 256, (H64 * G4 + LS_ROWS * H64) * 4, (cudaStream_t)stream>>>(
       h->d, params, ZG, C, H, Hprev, c0, h0, c1, h1, done, T, Rc, ld_state, r0);
   LCK(cudaGetLastError());
@@ -721,11 +740,10 @@ extern "C" int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, con
                            int64_t rows_per_t, int64_t stride_t, float* grads, void* stream) {
   if (!h || M <= 0) return tsc_set_error("tscl_fc_bwd: bad argument");
   LCK(cudaSetDevice(h->device));
-  int64_t nslab = (M + FB_SLAB - 1) / FB_SLAB;
-  if (nslab > 12) nslab = 12;          // 12 x 2A CTAs ~ 4 waves of 148 SMs; atomics per address <= 12
-  dim3 grid((unsigned)nslab, 2 * h->d.A);
-  const int smem = FB_ROWS * (h->max_in + h->d.dx) * 4;
-  fc_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(h->d, obs, X, dX, M, rows_per_t, stride_t, grads);
+  int64_t ng = (M + FB_ROWS - 1) / FB_ROWS;
+  if (ng > 24) ng = 24;
+  dim3 grid((unsigned)ng, 2 * h->d.A);
+  fc_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, obs, X, dX, M, rows_per_t, stride_t, grads);
   LCK(cudaGetLastError());
   return 0;
 }

@@ -56,6 +56,8 @@ struct DevNet {
   const int32_t* src_lane;
   const int32_t* src_route;
   const uint8_t* src_due;
+  const int32_t* lane_src0;  // [n_lanes] first demand source entering at this lane or -1
+  const int32_t* src_next;   // [n_src]   next source on the same lane (ascending index) or -1
 };
 
 struct StepArgs {
@@ -186,6 +188,45 @@ __device__ __forceinline__ void block_scan(const int32_t* __restrict__ cnt, int3
   __syncthreads();
 }
 
+// The same scan split in two halves so that its two barriers can be shared with neighbouring phases:
+// part 1 (before the barrier) leaves warp totals in wsum, part 2 (after it) writes pre[].
+struct ScanCarry { int loc[4]; int incl; int s; };
+__device__ __forceinline__ ScanCarry scan_part1(const int32_t* __restrict__ cnt, int32_t* __restrict__ wsum, int n) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + TSC_THREADS - 1) / TSC_THREADS;
+  const int base = tid * per;
+  ScanCarry c;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int v = (j < per && base + j < n) ? cnt[base + j] : 0;
+    c.loc[j] = s;
+    s += v;
+  }
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  c.incl = incl; c.s = s;
+  return c;
+}
+__device__ __forceinline__ void scan_part2(const ScanCarry& c, int32_t* __restrict__ pre, const int32_t* __restrict__ wsum, int n) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int per = (n + TSC_THREADS - 1) / TSC_THREADS;
+  const int base = tid * per;
+  int woff = 0;
+#pragma unroll
+  for (int w = 0; w < TSC_THREADS / 32; ++w) woff += (w < warp) ? wsum[w] : 0;
+  const int excl = woff + c.incl - c.s;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < per && base + j < n) pre[base + j] = excl + c.loc[j];
+  if (tid == TSC_THREADS - 1) pre[n] = woff + c.incl;
+}
+
 // largest l in [0, n) with pre[l] <= k   (k < pre[n])
 __device__ __forceinline__ int find_lane(const int32_t* __restrict__ pre, int n, int k) {
   int lo = 0, hi = n;
@@ -276,10 +317,15 @@ tsc_step_kernel(const StepArgs A) {
   int n_dep_add = 0;  // per-thread partial (sources), reduced at the end via atomics
 
   // ---- sub-steps: each is one traci.simulationStep() (envs/env.py:461-471) -------------------
+  // Lane phases use BLOCKED ownership (thread tid owns lanes [tid*per, tid*per+per)), identical in every
+  // phase and in the scan, so data a thread only exchanges with itself needs no barrier:
+  //   [A1 + scan part 1] | [scan part 2 + A2] | B (1 barrier per batch + 1) | C | [D + E]  -> 6 barriers.
+  const int per = (L + TSC_THREADS - 1) / TSC_THREADS;
+  const int l_lo = tid * per, l_hi = min(L, l_lo + per);
   for (int sub = 0; sub < A.n_sub; ++sub) {
     const uint32_t t_abs = (uint32_t)cur_sec;
-    // A1: approach masks + reset per-lane scratch
-    for (int l = tid; l < L; l += TSC_THREADS) {
+    // A1: approach masks + reset of per-lane scratch (own lanes)
+    for (int l = l_lo; l < l_hi; ++l) {
       s_hflag[l] = 0; s_acc[l] = 0; s_cntadd[l] = 0;
       if (s_cnt[l] > 0) {
         const LaneC lc = n.lane[l];
@@ -296,10 +342,11 @@ tsc_step_kernel(const StepArgs A) {
         }
       }
     }
+    const ScanCarry sc = scan_part1(s_cnt, s_wsum, L);
     __syncthreads();
-    block_scan(s_cnt, s_pre, s_wsum, L);   // (two barriers inside; also orders A1 -> A2)
-    // A2: head-vehicle speed limit from the junction ahead
-    for (int l = tid; l < L; l += TSC_THREADS) {
+    scan_part2(sc, s_pre, s_wsum, L);
+    // A2: head-vehicle speed limit from the junction ahead (own lanes; reads other lanes' tails)
+    for (int l = l_lo; l < l_hi; ++l) {
       float lim = INF_SPEED;
       if (s_cnt[l] > 0) {
         const LaneC lc = n.lane[l];
@@ -421,8 +468,9 @@ tsc_step_kernel(const StepArgs A) {
       }
       __syncthreads();
     }
-    // C: junction transfers — one thread per destination lane, sources in merge-priority order
-    for (int t = tid; t < L; t += TSC_THREADS) {
+    // C: junction transfers — the owner of each destination lane pulls from its source lanes in
+    //    merge-priority order (no atomics).  Also: clear approach masks, switch yellow -> green.
+    for (int t = l_lo; t < l_hi; ++t) {
       const int q0 = __ldg(&n.lane_inl_off[t]), q1 = __ldg(&n.lane_inl_off[t + 1]);
       if (q0 == q1) continue;
       const LaneC tc = n.lane[t];
@@ -438,13 +486,13 @@ tsc_step_kernel(const StepArgs A) {
         const int link = __ldg(&n.lane_inl[q]);
         const int src = __ldg(&n.link[link].from);
         if (s_cnt[src] == 0 || s_hflag[src] != F_CROSS) continue;
-        const LaneC sc = n.lane[src];
-        const uint4 h = ring[sc.slot0 + s_head[src]];
+        const LaneC sc2 = n.lane[src];
+        const uint4 h = ring[sc2.slot0 + s_head[src]];
         const uint32_t route = M0_ROUTE(h.z), hop = M0_HOP(h.z);
         if (__ldg(&n.route_link[route * n.max_hops + hop]) != link) continue;
         if (__ldg(&n.route_lane[route * n.max_hops + hop + 1]) != t) continue;
         if (cur >= tc.cap) continue;
-        float x = __uint_as_float(h.x) - sc.len;
+        float x = __uint_as_float(h.x) - sc2.len;
         if (have_tail) {
           float lim = tail_x - c.veh_len;
           lim = lim - c.min_gap;
@@ -462,10 +510,18 @@ tsc_step_kernel(const StepArgs A) {
       }
       s_cntadd[t] = cur - s_cnt[t];
     }
+    for (int i = tid; i < N; i += TSC_THREADS) {
+      s_appr[i] = 0;
+      // green part starts after the yellow sub-steps (envs/env.py:571-573)
+      if (sub + 1 == c.yellow_interval_sec) node_signal(n, i, s_act[i], s_prev[i], false, s_opn, s_maj, s_yel);
+    }
     __syncthreads();
-    // D: pops, arrivals, refused crossings; E-prologue: clear approach masks
-    for (int l = tid; l < L; l += TSC_THREADS) {
+    // D + E (own lanes only, so no barrier in between and none before the next A1):
+    // D pops / arrivals / refused crossings; E insertion (departPos random_free restated on the free
+    // tail segment; at most one insertion per lane per second, lowest source index first)
+    for (int l = l_lo; l < l_hi; ++l) {
       int cl = s_cnt[l];
+      const LaneC lc = n.lane[l];
       if (cl > 0) {
         const uint8_t f = s_hflag[l];
         bool pop = false;
@@ -473,7 +529,6 @@ tsc_step_kernel(const StepArgs A) {
         else if (f == F_CROSS) {
           if (s_acc[l]) pop = true;
           else {
-            const LaneC lc = n.lane[l];
             uint4* h = &ring[lc.slot0 + s_head[l]];
             h->x = __float_as_uint(lc.len - 0.01f);
             h->y = __float_as_uint(0.0f);
@@ -481,79 +536,60 @@ tsc_step_kernel(const StepArgs A) {
         }
         if (pop) {
           int hd = s_head[l] + 1;
-          if (hd >= __ldg(&n.lane[l].cap)) hd = 0;
+          if (hd >= lc.cap) hd = 0;
           s_head[l] = hd;
           cl--;
         }
       }
-      s_cnt[l] = cl + s_cntadd[l];
-    }
-    for (int i = tid; i < N; i += TSC_THREADS) s_appr[i] = 0;
-    __syncthreads();
-    // E: insertion (departPos random_free restated on the free tail segment; <= 1 per lane per s)
-    {
-      int b_new = 0; bool owner = false; int q = tid;
-      if (q < n.n_src) {
+      cl += s_cntadd[l];
+      int q = __ldg(&n.lane_src0[l]);
+      if (q >= 0) {
         const bool in_h = (int)t_abs < n.horizon;
-        b_new = s_backlog[q] + (in_h ? (int)__ldg(&n.src_due[t_abs * n.n_src + q]) : 0);
-        if (b_new > 65535) b_new = 65535;
-        owner = b_new > 0;
-        if (n.src_shared) {
-          const int myl = __ldg(&n.src_lane[q]);
-          for (int p = 0; p < q; ++p)
-            if (__ldg(&n.src_lane[p]) == myl) {
-              int bp = s_backlog[p] + (in_h ? (int)__ldg(&n.src_due[t_abs * n.n_src + p]) : 0);
-              if (bp > 0) owner = false;
+        bool lane_free = true;   // the lane belongs to the first source (by index) with a backlog
+        for (; q >= 0; q = __ldg(&n.src_next[q])) {
+          int b_new = s_backlog[q] + (in_h ? (int)__ldg(&n.src_due[t_abs * n.n_src + q]) : 0);
+          if (b_new > 65535) b_new = 65535;
+          if (b_new > 0 && lane_free) {
+            lane_free = false;
+            bool ok = cl < lc.cap;
+            float free_back = lc.len;
+            if (ok && cl > 0) {
+              int idx = s_head[l] + cl - 1;
+              if (idx >= lc.cap) idx -= lc.cap;
+              free_back = __uint_as_float(ring[lc.slot0 + idx].x) - c.veh_len;
+              free_back = free_back - c.min_gap;
             }
+            if (ok && !(free_back < c.veh_len)) {
+              const uint32_t qq = (uint32_t)q;
+              const float u = u01(rng_u32(seed_lo, seed_hi, t_abs, qq, (1u << 16)));
+              const float pos = c.veh_len + u * (free_back - c.veh_len);
+              float su = 0.0f;
+              for (uint32_t j = 1; j <= 4; ++j) su = su + u01(rng_u32(seed_lo, seed_hi, t_abs, qq, (1u << 16) | j));
+              const float sfr = 1.0f + (c.speed_dev * 1.7320508f) * (su - 2.0f);
+              int sfq = (int)((sfr - 0.5f) * 256.0f);
+              if (sfq < 0) sfq = 0;
+              if (sfq > 255) sfq = 255;
+              int idx = s_head[l] + cl;
+              if (idx >= lc.cap) idx -= lc.cap;
+              uint4 e;
+              e.x = __float_as_uint(pos);
+              e.y = __float_as_uint(0.0f);
+              e.z = ((uint32_t)__ldg(&n.src_route[q]) << 16) | ((uint32_t)sfq << 24);
+              e.w = t_abs & 4095u;
+              ring[lc.slot0 + idx] = e;
+              cl++;
+              b_new--;
+              n_dep_add++;
+            }
+          }
+          s_backlog[q] = b_new;
         }
       }
-      if (n.src_shared) __syncthreads();
-      if (q < n.n_src) {
-        if (owner) {
-          const int lane = __ldg(&n.src_lane[q]);
-          const LaneC lc = n.lane[lane];
-          const int cnt = s_cnt[lane];
-          bool ok = cnt < lc.cap;
-          float free_back = lc.len;
-          if (ok && cnt > 0) {
-            int idx = s_head[lane] + cnt - 1;
-            if (idx >= lc.cap) idx -= lc.cap;
-            free_back = __uint_as_float(ring[lc.slot0 + idx].x) - c.veh_len;
-            free_back = free_back - c.min_gap;
-          }
-          if (ok && !(free_back < c.veh_len)) {
-            const uint32_t qq = (uint32_t)q;
-            const float u = u01(rng_u32(seed_lo, seed_hi, t_abs, qq, (1u << 16)));
-            const float pos = c.veh_len + u * (free_back - c.veh_len);
-            float su = 0.0f;
-            for (uint32_t j = 1; j <= 4; ++j) su = su + u01(rng_u32(seed_lo, seed_hi, t_abs, qq, (1u << 16) | j));
-            const float sfr = 1.0f + (c.speed_dev * 1.7320508f) * (su - 2.0f);
-            int sfq = (int)((sfr - 0.5f) * 256.0f);
-            if (sfq < 0) sfq = 0;
-            if (sfq > 255) sfq = 255;
-            int idx = s_head[lane] + cnt;
-            if (idx >= lc.cap) idx -= lc.cap;
-            uint4 e;
-            e.x = __float_as_uint(pos);
-            e.y = __float_as_uint(0.0f);
-            e.z = ((uint32_t)__ldg(&n.src_route[q]) << 16) | ((uint32_t)sfq << 24);
-            e.w = t_abs & 4095u;
-            ring[lc.slot0 + idx] = e;
-            s_cnt[lane] = cnt + 1;
-            b_new--;
-            n_dep_add++;
-          }
-        }
-        s_backlog[q] = b_new;
-      }
+      s_cnt[l] = cl;
     }
     cur_sec++;
-    // green part starts after the yellow sub-steps (envs/env.py:571-573)
-    if (sub + 1 == c.yellow_interval_sec)
-      for (int i = tid; i < N; i += TSC_THREADS)
-        node_signal(n, i, s_act[i], s_prev[i], false, s_opn, s_maj, s_yel);
-    __syncthreads();
   }
+  __syncthreads();
   if (n_dep_add) atomicAdd(&s_misc[3], n_dep_add);
 
   // ---- detector reads (envs/env.py:325-407): one thread per detector lane ---------------------
@@ -775,6 +811,15 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   rc |= upload(h, net->src_lane, (size_t)net->n_src, &d.src_lane);
   rc |= upload(h, net->src_route, (size_t)net->n_src, &d.src_route);
   rc |= upload(h, net->src_due, (size_t)net->horizon * net->n_src, &d.src_due);
+  {
+    std::vector<int32_t> lane_src0(net->n_lanes, -1), src_next(net->n_src > 0 ? net->n_src : 1, -1);
+    for (int q = net->n_src - 1; q >= 0; --q) {      // descending, so the lists come out in ascending index order
+      src_next[q] = lane_src0[net->src_lane[q]];
+      lane_src0[net->src_lane[q]] = q;
+    }
+    rc |= upload(h, lane_src0.data(), lane_src0.size(), &d.lane_src0);
+    rc |= upload(h, src_next.data(), src_next.size(), &d.src_next);
+  }
   h->args.cfg = *cfg;
   h->args.ctl_words = (CTL_FIXED + N + net->n_src + 3) & ~3;
   h->meas_words = 3 * net->n_det + N;

@@ -36,7 +36,7 @@ class BatchedA2C:
                  v_coef: float = 0.5, max_grad_norm: float = 40.0, alpha: float = 0.99, eps: float = 1e-5,
                  reward_norm: float = 1.0, reward_clip: float = 0.0, seed: int = 0, device: int = 0,
                  chunk: int = 1024, replica0: int = 0, total_replicas: Optional[int] = None,
-                 process_group=None, allow_tf32: bool = True):
+                 process_group=None, allow_tf32: bool = True, use_tc: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedA2C needs a CUDA device (no CPU fallback exists)")
         self.lay, self.R, self.T = layout, int(n_replicas), int(n_step)
@@ -89,6 +89,10 @@ class BatchedA2C:
         self._one = torch.zeros(1, **f32)
         self._upd_bufs = None
         self.kernel_launches = 0
+        # fused tensor-core forward (csrc/tsc_policy_tc.cu): bf16 image of [Wx;Wh], refreshed after every update
+        self.use_tc = bool(use_tc) and (L.dx % 16 == 0)
+        self.Wp = torch.zeros(U, (L.dx + L.h) // 8, 4 * L.h, 8, dtype=torch.bfloat16, device=self.dev)
+        self.pack_weights()
 
     def close(self):
         if getattr(self, "_h", None) is not None:
@@ -104,6 +108,11 @@ class BatchedA2C:
     def _st(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
+    def pack_weights(self):
+        if self.use_tc:
+            _lib.check(_lib.lib().tscl_pack_weights(self._h, _p(self.P), _p(self.Wp), self._st()))
+            self.kernel_launches += 1
+
     def _mm(self):
         # cuBLAS fp32 (or TF32 when allowed) for the plain batched GEMMs
         torch.backends.cuda.matmul.allow_tf32 = bool(self.allow_tf32)
@@ -118,8 +127,20 @@ class BatchedA2C:
         """One decision for all replicas/agents.  obs [R, n_obs] device tensor.  Returns
         (pi [R, A, max_na], val [R, A], act [R, A] or None); 'v' does not advance the state."""
         L, R, lib = self.lay, self.R, _lib.lib()
-        self._mm()
         commit = "p" in out_type
+        want_act = sample and commit
+        if self.use_tc:
+            c1, h1 = (self.c_fw, self.h_fw) if commit else (self.c_tmp, self.h_tmp)
+            _lib.check(lib.tscl_policy_step(self._h, _p(self.P), _p(self.Wp), _p(obs), C.c_int64(R), _p(self.c_fw),
+                                            _p(self.h_fw), _p(c1), _p(h1), _p(self.pi), _p(self.val),
+                                            _p(self.act) if want_act else None, C.c_int32(1 if done else 0),
+                                            C.c_uint64(self.seed), C.c_int64(self.n_forward), C.c_int64(self.replica0),
+                                            None, C.c_int32(0), self._st()))
+            self.kernel_launches += 1
+            if commit:
+                self.n_forward += 1
+            return self.pi, self.val, (self.act if want_act else None)
+        self._mm()
         dflag = self._one.fill_(1.0 if done else 0.0)
         _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs), C.c_int64(R), C.c_int64(R), C.c_int64(0),
                                      _p(self.X1), self._st()))
@@ -128,7 +149,6 @@ class BatchedA2C:
         _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(self.Z1), None, _p(self.H1), None, _p(self.c_fw),
                                          _p(self.h_fw), _p(c1), _p(h1), _p(dflag), C.c_int32(1), C.c_int64(R),
                                          C.c_int64(R), C.c_int64(0), self._st()))
-        want_act = sample and commit
         _lib.check(lib.tscl_heads(self._h, _p(self.P), _p(self.H1), C.c_int64(R), _p(self.pi), _p(self.val),
                                   _p(self.act) if want_act else None, C.c_uint64(self.seed),
                                   C.c_int64(self.n_forward), C.c_int64(self.replica0), self._st()))
@@ -228,6 +248,7 @@ class BatchedA2C:
                                          C.c_float(self.max_grad_norm), C.c_float(lr), C.c_float(self.alpha),
                                          C.c_float(self.eps), _p(self.norms), st()))
         self.kernel_launches += 3
+        self.pack_weights()
         # states_bw <- states_fw (agents/policies.py:153); next rollout starts at slot 0
         self.c_bw.copy_(self.c_fw); self.h_bw.copy_(self.h_fw)
         self.obs_hist[0].copy_(self.obs_hist[T])

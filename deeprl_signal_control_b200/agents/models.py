@@ -130,6 +130,7 @@ class IA2C:
         if save_file is not None and os.path.exists(os.path.join(model_dir, save_file)):
             ck = torch.load(os.path.join(model_dir, save_file))
             self.batched.P.copy_(ck['params']); self.batched.MS.copy_(ck['rms'])
+            self.batched.pack_weights()
             logging.info('Checkpoint loaded: %s' % save_file)
             return True
         logging.error('Can not find old checkpoint for %s' % model_dir)

@@ -543,17 +543,27 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
     if (col < dx) {
       const int rows = (M - m0) < FB_ROWS ? (int)(M - m0) : FB_ROWS;
       const int64_t o0 = ((int64_t)u * M + m0) * dx + col;
-      for (int row = 0; row < rows; ++row) {
-        const int64_t o = o0 + (int64_t)row * dx;
-        const float g = X[o] > 0.f ? dX[o] : 0.f;       // relu mask
-        accb += g;
-        const float4* in4 = reinterpret_cast<const float4*>(&sIn[row * FE_KTOT + kbase]);
+      // rows in groups of 8: all 16 global loads of a group are issued before they are consumed
+      for (int r0 = 0; r0 < rows; r0 += 8) {
+        float g[8];
 #pragma unroll
-        for (int k4 = 0; k4 < FE_KW / 4; ++k4) {
-          if (k4 < nk4) {
-            const float4 x = in4[k4];
-            acc[4 * k4] = fmaf(x.x, g, acc[4 * k4]); acc[4 * k4 + 1] = fmaf(x.y, g, acc[4 * k4 + 1]);
-            acc[4 * k4 + 2] = fmaf(x.z, g, acc[4 * k4 + 2]); acc[4 * k4 + 3] = fmaf(x.w, g, acc[4 * k4 + 3]);
+        for (int j = 0; j < 8; ++j) {
+          const int64_t o = o0 + (int64_t)(r0 + j) * dx;
+          float xv = 0.f, dv = 0.f;
+          if (r0 + j < rows) { xv = __ldg(X + o); dv = __ldg(dX + o); }
+          g[j] = xv > 0.f ? dv : 0.f;                   // relu mask
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          accb += g[j];
+          const float4* in4 = reinterpret_cast<const float4*>(&sIn[(r0 + j) * FE_KTOT + kbase]);
+#pragma unroll
+          for (int k4 = 0; k4 < FE_KW / 4; ++k4) {
+            if (k4 < nk4) {
+              const float4 x = in4[k4];
+              acc[4 * k4] = fmaf(x.x, g[j], acc[4 * k4]); acc[4 * k4 + 1] = fmaf(x.y, g[j], acc[4 * k4 + 1]);
+              acc[4 * k4 + 2] = fmaf(x.z, g[j], acc[4 * k4 + 2]); acc[4 * k4 + 3] = fmaf(x.w, g[j], acc[4 * k4 + 3]);
+            }
           }
         }
       }
@@ -601,6 +611,11 @@ __global__ void rmsprop_kernel(float* __restrict__ p, float* __restrict__ g, flo
   p[i] -= lr * gi / sqrtf(m + eps);                                  // epsilon inside the sqrt
   if (norms && (i == 0 || agent_of[i - 1] != a)) norms[a] = nrm;
 }
+
+// accessors for tsc_policy_tc.cu (DDimsTC there mirrors DDims member for member)
+struct DDimsTC;
+const DDimsTC* tscl_dims_of(tscl_handle* h) { return reinterpret_cast<const DDimsTC*>(&h->d); }
+int tscl_device_of(tscl_handle* h) { return h->device; }
 
 // ================================================================================================
 template <class T>

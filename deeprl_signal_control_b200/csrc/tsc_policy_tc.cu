@@ -1,0 +1,439 @@
+// tsc_policy_tc.cu — fused per-control-step policy forward on the 5th-gen tensor cores (sm_100a).
+//
+// One persistent CTA (256 threads, 1 per SM, ~223 KB smem) walks (unit, 128-replica tile) work items:
+//   1. SIMT fc front end (agents/policies.py:191-201): relu(fc) of the observation slice, written as
+//      bf16 straight into the A-operand tile in shared memory (UMMA K-major, no swizzle), followed by
+//      the previous hidden state h (masked by the pre-decision done flag, agents/utils.py:104-105);
+//   2. one elected thread issues K/16 `tcgen05.mma.cta_group::1.kind::f16` (M=128, N=256, bf16 x bf16
+//      -> fp32) against the packed [Wx;Wh] operand that stays resident in shared memory; the
+//      accumulator lives in TMEM (256 columns); completion via tcgen05.commit -> mbarrier;
+//   3. epilogue: every thread owns one replica row (TMEM lane) and 32 hidden units: tcgen05.ld of the
+//      four gate pre-activations, bias, LSTM cell (agents/utils.py:106-113), state write-back, head
+//      dot products (agents/policies.py:18-26), then softmax / value / categorical sample
+//      (utils.py:155-157) for the row.
+// Replaces per step: fc_embed_kernel + library GEMM + lstm_seq_fwd_kernel(T=1) + heads_kernel.
+//
+// Operand layouts (bytes, 16-byte "core rows", no swizzle; cute canonical ((8,n),2):((1,SBO),LBO)):
+//   A tile  [KC][128 rows][16 B]   : LBO = 2048 (next K chunk of 8 bf16), SBO = 128 (next 8 rows)
+//   B tile  [KC][256 cols][16 B]   : LBO = 4096,                          SBO = 128
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/tsc_learn.h"
+
+int tsc_set_error(const std::string& m);
+#define PCK(call)                                                                  \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) return tsc_set_error(std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DDimsTC {   // mirror of DDims in tsc_learn.cu (kept in sync by tscl_handle)
+  int A, n_obs, max_na, fw, ff, ft, h, dx;
+  const int32_t *obs_off, *n_wave, *n_wait, *n_fp, *n_a;
+  const int64_t *off_fcw_w, *off_fcw_b, *off_fcf_w, *off_fcf_b, *off_fct_w, *off_fct_b;
+  int64_t off_wx, off_wh, off_bl, off_wo, off_bo, n_params;
+};
+const DDimsTC* tscl_dims_of(tscl_handle* h);   // defined in tsc_learn.cu
+int tscl_device_of(tscl_handle* h);
+
+#define TC_M 128
+#define TC_N 256
+#define TC_H 64
+#define TC_THREADS 256
+#define TC_STAGE_ROWS 16
+#define TC_KW 32
+#define TC_KF 16
+#define TC_KT 16
+#define TC_KTOT (TC_KW + TC_KF + TC_KT)
+
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);   // version = 1 (Blackwell), no swizzle
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ uint32_t pmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+  return h;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pack [Wx;Wh] of every unit into the bf16 UMMA B-operand image  Wp[u][kc][n][8]
+__global__ void pack_wxh_kernel(const DDimsTC d, const float* __restrict__ P, __nv_bfloat16* __restrict__ Wp) {
+  const int u = blockIdx.y;
+  const int K = d.dx + TC_H, KC = K / 8;
+  const float* Wx = P + d.off_wx + (int64_t)u * d.dx * TC_N;
+  const float* Wh = P + d.off_wh + (int64_t)u * TC_H * TC_N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < KC * TC_N; i += gridDim.x * blockDim.x) {
+    const int kc = i / TC_N, n = i - kc * TC_N;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      const float w = k < d.dx ? Wx[(int64_t)k * TC_N + n] : Wh[(int64_t)(k - d.dx) * TC_N + n];
+      v[e] = __float2bfloat16_rn(w);
+    }
+    *reinterpret_cast<uint4*>(Wp + (((int64_t)u * KC + kc) * TC_N + n) * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+struct StepTC {
+  const float* P;
+  const __nv_bfloat16* Wp;
+  const float* obs;        // [R][n_obs]
+  const float* c_in;       // [2A][R][64]
+  const float* h_in;
+  float* c_out;
+  float* h_out;
+  float* pi;               // [R][A][max_na]
+  float* val;              // [R][A]
+  int32_t* act;            // [R][A] or null
+  float* zdbg;             // [2A][R][256] raw accumulators (debug) or null
+  int64_t R;
+  int done;                // pre-decision done flag
+  int swap_lbo_sbo;        // debug: exchange the two descriptor strides
+  uint32_t seed_lo, seed_hi, step;
+  int64_t replica0;
+};
+
+extern __shared__ __align__(1024) unsigned char tc_smem[];
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+policy_step_tc_kernel(const DDimsTC d, const StepTC a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = d.dx + TC_H, KC = K / 8, KS = K / 16;
+  // ---- shared memory carve-up ----
+  unsigned char* sB = tc_smem;                                  // KC * 4096
+  unsigned char* sA = sB + (size_t)KC * 4096;                   // KC * 2048
+  float* sStage = reinterpret_cast<float*>(sA + (size_t)KC * 2048);   // 16 x 64 floats; aliased by sRed [128][8]
+  float* sWo = sStage + TC_STAGE_ROWS * TC_KTOT;                // [64][8]
+  float* sBo = sWo + TC_H * 8;                                  // [8]
+  float* sBias = sBo + 8;                                       // [256]
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sBias + TC_N);   // mbarrier
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);      // TMEM base address
+  float* sRed = sStage;
+
+  const uint32_t bar = smem_u32(sBar);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  // instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+  const int64_t n_tiles = (a.R + TC_M - 1) / TC_M;
+  const int64_t n_items = n_tiles * 2 * d.A;
+  const int64_t it_lo = n_items * blockIdx.x / gridDim.x, it_hi = n_items * (blockIdx.x + 1) / gridDim.x;
+  int cur_u = -1;
+  uint32_t parity = 0;
+  // per-thread fc role: output column `col` of X
+  const int col = tid;
+  float w[TC_KW];
+  float bias = 0.f;
+  int kbase = 0, nk4 = 0, nw = 0, nt = 0, nf = 0, ooff = 0, n_in = 0, na = 0;
+
+  for (int64_t it = it_lo; it < it_hi; ++it) {
+    const int u = (int)(it / n_tiles);
+    const int64_t r0 = (it - (int64_t)u * n_tiles) * TC_M;
+    const int ag = u >> 1;
+    if (u != cur_u) {
+      cur_u = u;
+      __syncthreads();
+      // B operand image of this unit: plain 16-byte copies (async proxy will read it: fence below)
+      const uint4* src = reinterpret_cast<const uint4*>(a.Wp + (int64_t)u * KC * TC_N * 8);
+      uint4* dst = reinterpret_cast<uint4*>(sB);
+      for (int i = tid; i < KC * TC_N; i += TC_THREADS) dst[i] = src[i];
+      nw = d.n_wave[ag]; nt = d.n_wait[ag]; nf = d.ff > 0 ? d.n_fp[ag] : 0;
+      n_in = nw + nt + nf; ooff = d.obs_off[ag]; na = d.n_a[ag];
+#pragma unroll
+      for (int k = 0; k < TC_KW; ++k) w[k] = 0.f;
+      int nk = 0;
+      if (col < d.dx) {
+        if (col < d.fw) {
+          nk = nw; kbase = 0;
+#pragma unroll
+          for (int k = 0; k < TC_KW; ++k) if (k < nw) w[k] = a.P[d.off_fcw_w[u] + (int64_t)k * d.fw + col];
+          bias = a.P[d.off_fcw_b[u] + col];
+        } else if (col < d.fw + d.ff) {
+          nk = nf; kbase = TC_KW;
+#pragma unroll
+          for (int k = 0; k < TC_KF; ++k) if (k < nf) w[k] = a.P[d.off_fcf_w[u] + (int64_t)k * d.ff + (col - d.fw)];
+          bias = a.P[d.off_fcf_b[u] + (col - d.fw)];
+        } else {
+          nk = nt; kbase = TC_KW + TC_KF;
+#pragma unroll
+          for (int k = 0; k < TC_KT; ++k) if (k < nt) w[k] = a.P[d.off_fct_w[u] + (int64_t)k * d.ft + (col - d.fw - d.ff)];
+          bias = a.P[d.off_fct_b[u] + (col - d.fw - d.ff)];
+        }
+      }
+      nk4 = (nk + 3) >> 2;
+      for (int i = tid; i < TC_H * 8; i += TC_THREADS) {
+        const int k = i >> 3, j = i & 7;
+        sWo[i] = j < d.max_na ? a.P[d.off_wo + ((int64_t)u * TC_H + k) * d.max_na + j] : 0.f;
+      }
+      if (tid < 8) sBo[tid] = tid < d.max_na ? a.P[d.off_bo + (int64_t)u * d.max_na + tid] : 0.f;
+      for (int i = tid; i < TC_N; i += TC_THREADS) sBias[i] = a.P[d.off_bl + (int64_t)u * TC_N + i];
+    }
+    // ---- 1. A tile: fc front end (cols 0..dx) in 16-row sub-blocks, then h_prev (cols dx..dx+64) ----
+    for (int sb = 0; sb < TC_M / TC_STAGE_ROWS; ++sb) {
+      __syncthreads();
+      for (int i = tid; i < TC_STAGE_ROWS * TC_KTOT; i += TC_THREADS) sStage[i] = 0.f;
+      __syncthreads();
+      for (int i = tid; i < TC_STAGE_ROWS * n_in; i += TC_THREADS) {
+        const int row = i / n_in, k = i - row * n_in;
+        const int64_t r = r0 + sb * TC_STAGE_ROWS + row;
+        if (r < a.R) {
+          int dst;
+          if (k < nw) dst = k;
+          else if (k < nw + nt) dst = TC_KW + TC_KF + (k - nw);
+          else dst = TC_KW + (k - nw - nt);
+          sStage[row * TC_KTOT + dst] = a.obs[r * d.n_obs + ooff + k];
+        }
+      }
+      __syncthreads();
+      if (col < d.dx) {
+        __nv_bfloat16* acol = reinterpret_cast<__nv_bfloat16*>(sA + (size_t)(col >> 3) * 2048) + (col & 7);
+#pragma unroll 4
+        for (int row = 0; row < TC_STAGE_ROWS; ++row) {
+          const float4* in4 = reinterpret_cast<const float4*>(&sStage[row * TC_KTOT + kbase]);
+          float acc = bias;
+#pragma unroll
+          for (int k4 = 0; k4 < TC_KW / 4; ++k4) {
+            if (k4 < nk4) {
+              const float4 x = in4[k4];
+              acc = fmaf(x.x, w[4 * k4], acc); acc = fmaf(x.y, w[4 * k4 + 1], acc);
+              acc = fmaf(x.z, w[4 * k4 + 2], acc); acc = fmaf(x.w, w[4 * k4 + 3], acc);
+            }
+          }
+          acol[(sb * TC_STAGE_ROWS + row) * 8] = __float2bfloat16_rn(fmaxf(acc, 0.f));
+        }
+      }
+    }
+    {   // h_prev -> A columns dx .. dx+63 : thread = (row, 32-column half)
+      const int row = tid >> 1, half = tid & 1;
+      const int64_t r = r0 + row;
+      const bool live = r < a.R && !a.done;
+      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * a.R + (r < a.R ? r : 0)) * TC_H + half * 32);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        __align__(16) __nv_bfloat16 v[8];
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+        if (live) { x0 = hp[2 * c8]; x1 = hp[2 * c8 + 1]; }
+        v[0] = __float2bfloat16_rn(x0.x); v[1] = __float2bfloat16_rn(x0.y); v[2] = __float2bfloat16_rn(x0.z); v[3] = __float2bfloat16_rn(x0.w);
+        v[4] = __float2bfloat16_rn(x1.x); v[5] = __float2bfloat16_rn(x1.y); v[6] = __float2bfloat16_rn(x1.z); v[7] = __float2bfloat16_rn(x1.w);
+        const int kc = (d.dx >> 3) + half * 4 + c8;
+        *reinterpret_cast<uint4*>(sA + (size_t)kc * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+      }
+    }
+    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 2. MMA: D[128 x 256] = A[128 x K] . B[K x 256] ----
+    if (warp == 0) {
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+        for (int ks = 0; ks < KS; ++ks) {
+          uint64_t da, db;
+          if (!a.swap_lbo_sbo) {
+            da = make_desc(aA + ks * 2 * 2048, 2048, 128);
+            db = make_desc(aB + ks * 2 * 4096, 4096, 128);
+          } else {
+            da = make_desc(aA + ks * 2 * 2048, 128, 2048);
+            db = make_desc(aB + ks * 2 * 4096, 128, 4096);
+          }
+          umma_bf16(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- 3. epilogue: thread = (row = TMEM lane, 32 hidden units) ----
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int row = q * 32 + lane;
+      const int64_t r = r0 + row;
+      const bool valid = r < a.R;
+      const int64_t srow = ((int64_t)u * a.R + (valid ? r : 0)) * TC_H + half * 32;
+      float lg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) lg[j] = 0.f;
+#pragma unroll
+      for (int jb = 0; jb < 2; ++jb) {
+        float zi[16], zf[16], zo[16], zu[16];
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + jb * 16);
+        tmem_ld16(tbase, zi); tmem_ld16(tbase + 64, zf); tmem_ld16(tbase + 128, zo); tmem_ld16(tbase + 192, zu);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a.zdbg && valid) {
+          float* z = a.zdbg + ((int64_t)u * a.R + r) * TC_N + half * 32 + jb * 16;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { z[e] = zi[e]; z[64 + e] = zf[e]; z[128 + e] = zo[e]; z[192 + e] = zu[e]; }
+        }
+        float cprev[16];
+        if (valid && !a.done) {
+          const float4* cp = reinterpret_cast<const float4*>(a.c_in + srow + jb * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 x = cp[e4];
+            cprev[4 * e4] = x.x; cprev[4 * e4 + 1] = x.y; cprev[4 * e4 + 2] = x.z; cprev[4 * e4 + 3] = x.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cprev[e] = 0.f;
+        }
+        float cn[16], hn[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int j = half * 32 + jb * 16 + e;
+          const float gi = sigm(zi[e] + sBias[j]), gf = sigm(zf[e] + sBias[64 + j]);
+          const float go = sigm(zo[e] + sBias[128 + j]), gu = tanhf(zu[e] + sBias[192 + j]);
+          cn[e] = gf * cprev[e] + gi * gu;
+          hn[e] = go * tanhf(cn[e]);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
+        }
+        if (valid) {
+          float4* co = reinterpret_cast<float4*>(a.c_out + srow + jb * 16);
+          float4* ho = reinterpret_cast<float4*>(a.h_out + srow + jb * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            co[e4] = make_float4(cn[4 * e4], cn[4 * e4 + 1], cn[4 * e4 + 2], cn[4 * e4 + 3]);
+            ho[e4] = make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
+          }
+        }
+      }
+      // all TMEM reads of this tile are done before the next tile's MMA may overwrite the accumulator
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();     // also: sStage (aliased by sRed) is free
+      if (half == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
+      }
+      __syncthreads();
+      if (half == 0 && valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lg[j] += sRed[row * 8 + j] + sBo[j];
+        if ((u & 1) == 0) {        // policy unit
+          float mx = -1e30f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < na) mx = fmaxf(mx, lg[j]);
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lg[j] = j < na ? __expf(lg[j] - mx) : 0.f; s += lg[j]; }
+          const float inv = 1.0f / s;
+          float* po = a.pi + ((int64_t)r * d.A + ag) * d.max_na;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < d.max_na) po[j] = lg[j] * inv;
+          if (a.act) {
+            uint32_t hsh = pmix32(a.seed_lo ^ (a.step * 0x9E3779B1U));
+            hsh = pmix32(hsh ^ a.seed_hi ^ ((uint32_t)(a.replica0 + r) * 0x85EBCA77U));
+            hsh = pmix32(hsh ^ ((uint32_t)ag * 0xC2B2AE3DU));
+            const float uu = (float)(hsh >> 8) * (1.0f / 16777216.0f);
+            float cum = 0.f;
+            int pick = na - 1;
+            bool found = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < na) { cum += lg[j] * inv; if (!found && uu < cum) { pick = j; found = true; } }
+            a.act[(int64_t)r * d.A + ag] = pick;
+          }
+        } else {
+          a.val[(int64_t)r * d.A + ag] = lg[0];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+// ===================================================================================================
+static size_t tc_smem_bytes(int K) {
+  const int KC = K / 8;
+  return (size_t)KC * 4096 + (size_t)KC * 2048 + (TC_STAGE_ROWS * TC_KTOT + TC_H * 8 + 8 + TC_N) * 4 + 16;
+}
+
+extern "C" int tscl_pack_weights(tscl_handle* h, const float* params, void* wpack_bf16, void* stream) {
+  if (!h || !params || !wpack_bf16) return tsc_set_error("tscl_pack_weights: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  if ((d.dx % 16) != 0) return tsc_set_error("tscl_pack_weights: dx must be a multiple of 16");
+  dim3 grid(8, 2 * d.A);
+  pack_wxh_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, params, (__nv_bfloat16*)wpack_bf16);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs,
+                                int64_t R, const float* c_in, const float* h_in, float* c_out, float* h_out, float* pi,
+                                float* val, int32_t* act, int32_t done, uint64_t seed, int64_t step, int64_t replica0,
+                                float* zdbg, int32_t swap_lbo_sbo, void* stream) {
+  if (!h || !params || !wpack_bf16 || !obs || R <= 0) return tsc_set_error("tscl_policy_step: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  const int K = d.dx + TC_H;
+  if ((d.dx % 16) != 0 || d.dx > TC_THREADS) return tsc_set_error("tscl_policy_step: unsupported dx");
+  const size_t smem = tc_smem_bytes(K);
+  if (smem > 232448) return tsc_set_error("tscl_policy_step: operand tiles exceed shared memory");
+  static int attr_dev = -1;
+  if (attr_dev != tscl_device_of(h)) {
+    PCK(cudaFuncSetAttribute(policy_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = tscl_device_of(h);
+  }
+  int n_sm = 0;
+  PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
+  const int64_t n_items = ((R + TC_M - 1) / TC_M) * 2 * d.A;
+  const int grid = (int)(n_items < n_sm ? n_items : n_sm);
+  StepTC a;
+  a.P = params; a.Wp = (const __nv_bfloat16*)wpack_bf16; a.obs = obs; a.c_in = c_in; a.h_in = h_in; a.c_out = c_out;
+  a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done;
+  a.swap_lbo_sbo = swap_lbo_sbo; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
+  a.step = (uint32_t)step; a.replica0 = replica0;
+  policy_step_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  PCK(cudaGetLastError());
+  return 0;
+}

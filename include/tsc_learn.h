@@ -106,6 +106,20 @@ int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* d
 int tscl_clip_rmsprop(tscl_handle* h, float* params, float* grads, float* ms, const uint8_t* agent_of,
                       float max_norm, float lr, float alpha, float eps, float* norms, void* stream);
 
+/* ---- fused tensor-core policy forward (tcgen05 + TMEM), csrc/tsc_policy_tc.cu -------------------------
+ * tscl_pack_weights: [Wx;Wh] of every unit -> bf16 UMMA operand image wpack [2A][(dx+h)/8][4h][8]
+ *   (call after every optimizer step).
+ * tscl_policy_step: one decision for R replicas and all agents in ONE kernel: fc front end, gate GEMM on
+ *   the tensor cores (bf16 operands, fp32 accumulate in TMEM), LSTM cell, heads, softmax, sampling.
+ *   Replaces LstmACPolicy.forward / FPLstmACPolicy.forward for a whole batch (agents/policies.py:125-136).
+ *   c_in/h_in/c_out/h_out [2A][R][h] (out may alias in); pi [R][A][max_na]; val [R][A]; act [R][A] or NULL;
+ *   zdbg [2A][R][4h] raw gate accumulators (debug) or NULL; swap_lbo_sbo: debug switch, pass 0. */
+int tscl_pack_weights(tscl_handle* h, const float* params, void* wpack_bf16, void* stream);
+int tscl_policy_step(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs, int64_t R,
+                     const float* c_in, const float* h_in, float* c_out, float* h_out, float* pi, float* val,
+                     int32_t* act, int32_t done, uint64_t seed, int64_t step, int64_t replica0, float* zdbg,
+                     int32_t swap_lbo_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

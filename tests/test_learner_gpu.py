@@ -29,7 +29,7 @@ def test_forward_matches_oracle(ff):
     from oracle.learner_ref import unit_forward
     lay = _layout(ff)
     R = 37
-    m = BatchedA2C(lay, R, n_step=4, seed=3, allow_tf32=False)
+    m = BatchedA2C(lay, R, n_step=4, seed=3, allow_tf32=False, use_tc=False)
     P = m.P.cpu().numpy()
     # non-zero biases so that they are exercised
     P = P + np.random.default_rng(0).normal(0, 0.05, P.shape).astype(np.float32) * (P == 0)
@@ -68,7 +68,7 @@ def test_sampling_follows_policy():
     from deeprl_signal_control_b200.agents.learner import BatchedA2C
     lay = _layout(64)
     R = 4096
-    m = BatchedA2C(lay, R, n_step=4, seed=5)
+    m = BatchedA2C(lay, R, n_step=4, seed=5, use_tc=False)
     obs = torch.rand(1, lay.n_obs, device="cuda").expand(R, -1).contiguous()
     pi, val, act = m.forward(obs, True)
     torch.cuda.synchronize()
@@ -86,7 +86,7 @@ def test_backward_gradients_match_autograd(ff, chunk):
     R, T = 37, 6
     gamma, v_coef, beta = 0.99, 0.5, 0.01
     m = BatchedA2C(lay, R, n_step=T, gamma=gamma, v_coef=v_coef, max_grad_norm=0.0, seed=7, chunk=chunk,
-                   reward_norm=3.0, reward_clip=2.0, allow_tf32=False)
+                   reward_norm=3.0, reward_clip=2.0, allow_tf32=False, use_tc=False)
     rng = np.random.default_rng(2)
     P0 = m.P.cpu().numpy().copy()
     # start the rollout from a non-zero recurrent state

@@ -1,0 +1,96 @@
+"""GPU: the fused tcgen05 policy-forward kernel (tscl_policy_step) vs the fp32 kernels / the oracle.
+
+The tensor-core path multiplies bf16-rounded operands with fp32 accumulation, so
+  * raw gate accumulators are compared with a torch matmul of the SAME bf16-rounded operands
+    (rtol 1e-3, atol 2e-3: only the summation order differs);
+  * policy / value / state are compared with the fp32 SIMT path at atol 3e-2 (bf16 operand rounding)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _layout(ff):
+    from deeprl_signal_control_b200.agents.layout import PolicyLayout
+    n_w = [6, 6, 6]
+    n_f = [8, 12, 16] if ff else [0, 0, 0]
+    n_wave = [18, 24, 30]
+    n_s = [w + t + f for w, t, f in zip(n_wave, n_w, n_f)]
+    off = np.concatenate([[0], np.cumsum(n_s)]).astype(np.int32)
+    return PolicyLayout(n_s, [5, 4, 5], n_w, n_f, off, int(off[-1]) + 3, fw=128, ft=32, ff=ff, h=64, max_na=5)
+
+
+def _run_tc(m, obs, done, zdbg, swap):
+    from deeprl_signal_control_b200 import _lib
+    from deeprl_signal_control_b200.agents.learner import _p
+    _lib.check(_lib.lib().tscl_policy_step(m._h, _p(m.P), _p(m.Wp), _p(obs), C.c_int64(m.R), _p(m.c_fw), _p(m.h_fw),
+                                           _p(m.c_tmp), _p(m.h_tmp), _p(m.pi), _p(m.val), _p(m.act),
+                                           C.c_int32(int(done)), C.c_uint64(7), C.c_int64(0), C.c_int64(0),
+                                           _p(zdbg), C.c_int32(swap), m._st()))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("ff", [64, 0])
+def test_gate_accumulators_match_bf16_matmul(ff):
+    from deeprl_signal_control_b200 import _lib
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C, _p
+    lay = _layout(ff)
+    R = 300                                     # 2 full tiles + a ragged one
+    m = BatchedA2C(lay, R, n_step=2, seed=11)
+    rng = np.random.default_rng(0)
+    m.h_fw.copy_(torch.from_numpy(rng.uniform(-1, 1, tuple(m.h_fw.shape)).astype(np.float32)))
+    m.c_fw.copy_(torch.from_numpy(rng.normal(0, 0.5, tuple(m.c_fw.shape)).astype(np.float32)))
+    obs = torch.from_numpy((rng.random((R, lay.n_obs)) * 2).astype(np.float32)).cuda()
+    # reference operands: X from the fp32 fc kernel, rounded to bf16 exactly like the fused kernel does
+    _lib.check(_lib.lib().tscl_fc_embed(m._h, _p(m.P), _p(obs), C.c_int64(R), C.c_int64(R), C.c_int64(0), _p(m.X1), m._st()))
+    Xb = m.X1.to(torch.bfloat16).float()
+    Hb = m.h_fw.to(torch.bfloat16).float()
+    Wx = m.pv["wx"].to(torch.bfloat16).float()
+    Wh = m.pv["wh"].to(torch.bfloat16).float()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    z_ref = torch.bmm(Xb, Wx) + torch.bmm(Hb, Wh)
+    zdbg = torch.zeros(lay.U, R, 256, device="cuda")
+    _run_tc(m, obs, False, zdbg, 0)
+    err0 = float((zdbg - z_ref).abs().max())
+    if err0 > 5e-2:                             # diagnose a descriptor-stride mix-up in one GPU run
+        z1 = torch.zeros_like(zdbg)
+        _run_tc(m, obs, False, z1, 1)
+        err1 = float((z1 - z_ref).abs().max())
+        raise AssertionError("tcgen05 gate GEMM mismatch: max err %.4f (LBO/SBO swapped: %.4f)" % (err0, err1))
+    torch.testing.assert_close(zdbg, z_ref, rtol=1e-3, atol=2e-3)
+    # done flag zeroes h and c inside the cell (agents/utils.py:104-105)
+    _run_tc(m, obs, True, zdbg, 0)
+    torch.testing.assert_close(zdbg, torch.bmm(Xb, Wx), rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("ff", [64, 0])
+def test_fused_forward_matches_fp32_path(ff):
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C
+    lay = _layout(ff)
+    R = 515
+    a = BatchedA2C(lay, R, n_step=2, seed=3, use_tc=True)
+    b = BatchedA2C(lay, R, n_step=2, seed=3, use_tc=False, allow_tf32=False)
+    assert a.use_tc and torch.equal(a.P, b.P)
+    rng = np.random.default_rng(1)
+    for step, done in enumerate([True, False, False, True, False, False]):
+        obs = torch.from_numpy((rng.random((R, lay.n_obs)) * 2).astype(np.float32)).cuda()
+        pa, va, aa = a.forward(obs, done)
+        pb, vb, ab = b.forward(obs, done)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(pa, pb, rtol=0, atol=3e-2)
+        torch.testing.assert_close(va, vb, rtol=0, atol=5e-2)
+        torch.testing.assert_close(a.h_fw, b.h_fw, rtol=0, atol=3e-2)
+        torch.testing.assert_close(a.c_fw, b.c_fw, rtol=0, atol=6e-2)
+        assert int(aa.min()) >= 0 and all(int(aa[:, i].max()) < int(lay.n_a[i]) for i in range(lay.A))
+        np.testing.assert_allclose(pa.sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
+        # value-only forward leaves the recurrent state untouched
+        cf = a.c_fw.clone()
+        a.forward(obs, False, out_type="v")
+        assert torch.equal(cf, a.c_fw)
+        # keep the two models on the same trajectory
+        a.c_fw.copy_(b.c_fw); a.h_fw.copy_(b.h_fw)
+    # identical probabilities -> identical inverse-CDF samples wherever u is not within the bf16 error of a boundary
+    assert float((aa == ab).float().mean()) > 0.97

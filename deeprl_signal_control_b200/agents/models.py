@@ -142,3 +142,145 @@ class MA2C(IA2C):
 
     def __init__(self, n_s_ls, n_a_ls, n_w_ls, n_f_ls, total_step, model_config, seed=0, **kw):
         super().__init__(n_s_ls, n_a_ls, n_w_ls, total_step, model_config, seed=seed, n_f_ls=n_f_ls, **kw)
+
+
+class IQL:
+    """Independent Q-learning (agents/models.py:264-376, agents/policies.py:285-389): per-agent
+    linear ('lr', LRQPolicy) or two-layer ('dqn', DeepQPolicy) Q network, epsilon-greedy exploration,
+    1-step TD target WITHOUT a target network (policies.py:318-322), Adam, replay buffer, 10
+    minibatches per agent per backward() (models.py:337-345).
+
+    This is BASELINE config 1 ("reference plumbing", single env): it runs on PyTorch tensor ops
+    (device tensors + torch.optim.Adam), not on hand-written kernels — it is not part of the measured
+    hot path."""
+    name = 'iql'
+
+    def __init__(self, n_s_ls, n_a_ls, n_w_ls, total_step, model_config, seed=0, model_type='dqn', device=None):
+        from .utils import ReplayBuffer
+        self.model_type = model_type
+        self.n_agent = len(n_s_ls)
+        self.reward_clip = model_config.getfloat('reward_clip')
+        self.reward_norm = model_config.getfloat('reward_norm')
+        self.n_s_ls, self.n_a_ls, self.n_w_ls = list(n_s_ls), list(n_a_ls), list(n_w_ls)
+        self.n_step = model_config.getint('batch_size')
+        self.sess = None
+        self.total_step = total_step
+        self.dev = torch.device(device if device is not None else ('cuda' if torch.cuda.is_available() else 'cpu'))
+        self.gamma = model_config.getfloat('gamma')
+        self.max_grad_norm = model_config.getfloat('max_grad_norm')
+        rng = np.random.RandomState(seed)
+        self._np_rng = np.random.RandomState(seed + 1)
+        from .layout import ortho_init
+        self.nets, self.opts = [], []
+        for n_s, n_a, n_w in zip(self.n_s_ls, self.n_a_ls, self.n_w_ls):
+            layers = {}
+            if model_type == 'dqn':
+                n_fc, n_h = model_config.getint('num_fc'), model_config.getint('num_h')
+                if n_w == 0:
+                    layers['q_fcw'] = (n_s, n_fc); width = n_fc
+                else:
+                    layers['q_fcw'] = (n_s - n_w, n_fc); layers['q_fct'] = (n_w, n_fc // 4); width = n_fc + n_fc // 4
+                layers['q_fc_0'] = (width, n_h); layers['q'] = (n_h, n_a)
+            else:
+                layers['q'] = (n_s, n_a)
+            params = {}
+            for k, shp in layers.items():
+                params[k + '/w'] = torch.tensor(ortho_init(rng, shp), device=self.dev, requires_grad=True)
+                params[k + '/b'] = torch.zeros(shp[1], device=self.dev, requires_grad=True)
+            self.nets.append(params)
+        if total_step:
+            lr_init = model_config.getfloat('lr_init')
+            lr_decay = model_config.get('lr_decay')
+            self.lr_scheduler = Scheduler(lr_init, decay=lr_decay) if lr_decay == 'constant' else \
+                Scheduler(lr_init, model_config.getfloat('lr_min'), total_step, decay=lr_decay)
+            eps_init = model_config.getfloat('epsilon_init')
+            eps_decay = model_config.get('epsilon_decay')
+            self.eps_scheduler = Scheduler(eps_init, decay=eps_decay) if eps_decay == 'constant' else \
+                Scheduler(eps_init, model_config.getfloat('epsilon_min'),
+                          total_step * model_config.getfloat('epsilon_ratio'), decay=eps_decay)
+            buffer_size = model_config.getfloat('buffer_size')
+            self.trans_buffer_ls = [ReplayBuffer(buffer_size, self.n_step) for _ in range(self.n_agent)]
+            self.opts = [torch.optim.Adam(list(p.values()), lr=lr_init) for p in self.nets]
+
+    def _q(self, i, S):
+        p, n_w = self.nets[i], self.n_w_ls[i]
+        if self.model_type != 'dqn':
+            return S @ p['q/w'] + p['q/b']
+        if n_w == 0:
+            h = torch.relu(S @ p['q_fcw/w'] + p['q_fcw/b'])
+        else:
+            n_s = S.shape[1] - n_w
+            h = torch.cat([torch.relu(S[:, :n_s] @ p['q_fcw/w'] + p['q_fcw/b']),
+                           torch.relu(S[:, n_s:] @ p['q_fct/w'] + p['q_fct/b'])], 1)
+        h = torch.relu(h @ p['q_fc_0/w'] + p['q_fc_0/b'])
+        return h @ p['q/w'] + p['q/b']
+
+    def forward(self, obs, mode='act', stochastic=False):
+        if mode == 'explore':
+            eps = self.eps_scheduler.get(1)
+        action, qs_ls = [], []
+        for i in range(self.n_agent):
+            with torch.no_grad():
+                qs = self._q(i, torch.as_tensor(np.asarray(obs[i], np.float32)[None], device=self.dev))[0].cpu().numpy()
+            if mode == 'explore' and self._np_rng.random_sample() < eps:
+                action.append(int(self._np_rng.randint(self.n_a_ls[i])))
+            elif not stochastic:
+                action.append(int(np.argmax(qs)))
+            else:
+                pq = qs / np.sum(qs)
+                action.append(int(self._np_rng.choice(np.arange(len(pq)), p=pq)))
+            qs_ls.append(qs)
+        return action, qs_ls
+
+    def add_transition(self, obs, actions, rewards, next_obs, done):
+        rewards = np.asarray(rewards, np.float64)
+        if self.reward_norm:
+            rewards = rewards / self.reward_norm
+        if self.reward_clip:
+            rewards = np.clip(rewards, -self.reward_clip, self.reward_clip)
+        for i in range(self.n_agent):
+            self.trans_buffer_ls[i].add_transition(obs[i], actions[i], rewards[i], next_obs[i], done)
+
+    def backward(self, summary_writer=None, global_step=None):
+        cur_lr = self.lr_scheduler.get(self.n_step)
+        if self.trans_buffer_ls[0].size < self.trans_buffer_ls[0].batch_size:
+            return
+        for i in range(self.n_agent):
+            for g in self.opts[i].param_groups:
+                g['lr'] = cur_lr
+            for _ in range(10):
+                obs, acts, next_obs, rs, dones = self.trans_buffer_ls[i].sample_transition()
+                S = torch.as_tensor(obs.astype(np.float32), device=self.dev)
+                S1 = torch.as_tensor(next_obs.astype(np.float32), device=self.dev)
+                A = torch.as_tensor(acts.astype(np.int64), device=self.dev)
+                R = torch.as_tensor(rs.astype(np.float32), device=self.dev)
+                D = torch.as_tensor(dones.astype(bool), device=self.dev)
+                q0 = self._q(i, S).gather(1, A[:, None])[:, 0]
+                with torch.no_grad():
+                    tq = torch.where(D, R, R + self.gamma * self._q(i, S1).max(1)[0])
+                loss = ((q0 - tq) ** 2).mean()
+                self.opts[i].zero_grad()
+                loss.backward()
+                if self.max_grad_norm > 0:
+                    torch.nn.utils.clip_grad_norm_(list(self.nets[i].values()), self.max_grad_norm)
+                self.opts[i].step()
+
+    def reset(self):
+        return
+
+    def save(self, model_dir, global_step):
+        torch.save({'nets': [{k: v.detach().cpu() for k, v in p.items()} for p in self.nets], 'step': int(global_step)},
+                   os.path.join(model_dir, 'checkpoint-%d.pt' % int(global_step)))
+
+    def load(self, model_dir, checkpoint=None):
+        files = [f for f in os.listdir(model_dir)] if os.path.exists(model_dir) else []
+        steps = [int(f.split('.')[0].split('-')[1]) for f in files if f.startswith('checkpoint-')]
+        if checkpoint is None and not steps:
+            logging.error('Can not find old checkpoint for %s' % model_dir)
+            return False
+        step = int(checkpoint) if checkpoint is not None else max(steps)
+        ck = torch.load(os.path.join(model_dir, 'checkpoint-%d.pt' % step))
+        for p, q in zip(self.nets, ck['nets']):
+            for k in p:
+                p[k].data.copy_(q[k])
+        return True

@@ -84,7 +84,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// MUFU tanh (tanh.approx.f32, max rel. error ~2^-11: below the bf16 operand rounding of this path)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 __device__ __forceinline__ uint32_t pmix32(uint32_t h) {
   h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
   return h;
@@ -330,9 +336,9 @@ policy_step_tc_kernel(const DDimsTC d, const StepTC a) {
         for (int e = 0; e < 16; ++e) {
           const int j = half * 32 + jb * 16 + e;
           const float gi = sigm(zi[e] + sBias[j]), gf = sigm(zf[e] + sBias[64 + j]);
-          const float go = sigm(zo[e] + sBias[128 + j]), gu = tanhf(zu[e] + sBias[192 + j]);
+          const float go = sigm(zo[e] + sBias[128 + j]), gu = tanh_fast(zu[e] + sBias[192 + j]);
           cn[e] = gf * cprev[e] + gi * gu;
-          hn[e] = go * tanhf(cn[e]);
+          hn[e] = go * tanh_fast(cn[e]);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
         }

@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libtsc.so")
+LIB_PATH = os.environ.get("TSC_LIB", os.path.join(CSRC, "libtsc.so"))   # TSC_LIB: tuning variants only
 _lib = None
 
 # every symbol include/tsc.h declares
@@ -21,7 +21,7 @@ SYMBOLS = ["tsc_last_error", "tsc_create", "tsc_destroy", "tsc_reset", "tsc_set_
            # include/tsc_learn.h
            "tscl_create", "tscl_destroy", "tscl_fc_embed", "tscl_lstm_seq_fwd", "tscl_heads", "tscl_returns",
            "tscl_heads_loss", "tscl_lstm_seq_bwd", "tscl_fc_bwd", "tscl_clip_rmsprop",
-           "tscl_pack_weights", "tscl_policy_step"]
+           "tscl_pack_weights", "tscl_policy_step", "tscl_policy_step_v2"]
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:

@@ -91,7 +91,9 @@ class BatchedA2C:
         self.kernel_launches = 0
         # fused tensor-core forward (csrc/tsc_policy_tc.cu): bf16 image of [Wx;Wh], refreshed after every update
         self.use_tc = bool(use_tc) and (L.dx % 16 == 0)
-        self.Wp = torch.zeros(U, (L.dx + L.h) // 8, 4 * L.h, 8, dtype=torch.bfloat16, device=self.dev)
+        self.tc_v2 = self.use_tc and (L.dx % 32 == 0)          # fc front end on the tensor cores too
+        self.Wp = torch.zeros(U, ((L.dx + L.h) // 8) * 4 * L.h * 8 + 8 * L.dx * 8, dtype=torch.bfloat16,
+                              device=self.dev)
         self.pack_weights()
 
     def close(self):
@@ -131,11 +133,14 @@ class BatchedA2C:
         want_act = sample and commit
         if self.use_tc:
             c1, h1 = (self.c_fw, self.h_fw) if commit else (self.c_tmp, self.h_tmp)
-            _lib.check(lib.tscl_policy_step(self._h, _p(self.P), _p(self.Wp), _p(obs), C.c_int64(R), _p(self.c_fw),
-                                            _p(self.h_fw), _p(c1), _p(h1), _p(self.pi), _p(self.val),
-                                            _p(self.act) if want_act else None, C.c_int32(1 if done else 0),
-                                            C.c_uint64(self.seed), C.c_int64(self.n_forward), C.c_int64(self.replica0),
-                                            None, C.c_int32(0), self._st()))
+            args = (self._h, _p(self.P), _p(self.Wp), _p(obs), C.c_int64(R), _p(self.c_fw), _p(self.h_fw), _p(c1),
+                    _p(h1), _p(self.pi), _p(self.val), _p(self.act) if want_act else None,
+                    C.c_int32(1 if done else 0), C.c_uint64(self.seed), C.c_int64(self.n_forward),
+                    C.c_int64(self.replica0), None)
+            if self.tc_v2:
+                _lib.check(lib.tscl_policy_step_v2(*args, self._st()))
+            else:
+                _lib.check(lib.tscl_policy_step(*args, C.c_int32(0), self._st()))
             self.kernel_launches += 1
             if commit:
                 self.n_forward += 1

@@ -97,6 +97,9 @@ __device__ __forceinline__ uint32_t pmix32(uint32_t h) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// per-unit stride of the packed image: main [KC][256][8] followed by the fc image [8][dx][8]
+__host__ __device__ inline int64_t wp_stride(int dx) { return (int64_t)((dx + TC_H) / 8) * TC_N * 8 + (int64_t)8 * dx * 8; }
+
 // pack [Wx;Wh] of every unit into the bf16 UMMA B-operand image  Wp[u][kc][n][8]
 __global__ void pack_wxh_kernel(const DDimsTC d, const float* __restrict__ P, __nv_bfloat16* __restrict__ Wp) {
   const int u = blockIdx.y;
@@ -112,7 +115,29 @@ __global__ void pack_wxh_kernel(const DDimsTC d, const float* __restrict__ P, __
       const float w = k < d.dx ? Wx[(int64_t)k * TC_N + n] : Wh[(int64_t)(k - d.dx) * TC_N + n];
       v[e] = __float2bfloat16_rn(w);
     }
-    *reinterpret_cast<uint4*>(Wp + (((int64_t)u * KC + kc) * TC_N + n) * 8) = *reinterpret_cast<const uint4*>(v);
+    *reinterpret_cast<uint4*>(Wp + (int64_t)u * wp_stride(d.dx) + ((int64_t)kc * TC_N + n) * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+
+// block-diagonal fc weights as UMMA B operand: rows k = {wave 0..31 | fp 32..47 | wait 48..63}, cols = X columns
+__global__ void pack_fc_kernel(const DDimsTC d, const float* __restrict__ P, __nv_bfloat16* __restrict__ Wp) {
+  const int u = blockIdx.y, ag = u >> 1;
+  const int nw = d.n_wave[ag], nt = d.n_wait[ag], nf = d.ff > 0 ? d.n_fp[ag] : 0;
+  __nv_bfloat16* W0 = Wp + (int64_t)u * wp_stride(d.dx) + (int64_t)((d.dx + TC_H) / 8) * TC_N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 8 * d.dx; i += gridDim.x * blockDim.x) {
+    const int kc = i / d.dx, n = i - kc * d.dx;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      float w = 0.f;
+      if (n < d.fw) { if (k < TC_KW && k < nw) w = P[d.off_fcw_w[u] + (int64_t)k * d.fw + n]; }
+      else if (n < d.fw + d.ff) { const int kk = k - TC_KW; if (kk >= 0 && kk < TC_KF && kk < nf) w = P[d.off_fcf_w[u] + (int64_t)kk * d.ff + (n - d.fw)]; }
+      else { const int kk = k - TC_KW - TC_KF; if (kk >= 0 && kk < nt) w = P[d.off_fct_w[u] + (int64_t)kk * d.ft + (n - d.fw - d.ff)]; }
+      v[e] = __float2bfloat16_rn(w);
+    }
+    *reinterpret_cast<uint4*>(W0 + ((int64_t)kc * d.dx + n) * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -187,7 +212,7 @@ policy_step_tc_kernel(const DDimsTC d, const StepTC a) {
       cur_u = u;
       __syncthreads();
       // B operand image of this unit: plain 16-byte copies (async proxy will read it: fence below)
-      const uint4* src = reinterpret_cast<const uint4*>(a.Wp + (int64_t)u * KC * TC_N * 8);
+      const uint4* src = reinterpret_cast<const uint4*>(a.Wp + (int64_t)u * wp_stride(d.dx));
       uint4* dst = reinterpret_cast<uint4*>(sB);
       for (int i = tid; i < KC * TC_N; i += TC_THREADS) dst[i] = src[i];
       nw = d.n_wave[ag]; nt = d.n_wait[ag]; nf = d.ff > 0 ? d.n_fp[ag] : 0;
@@ -410,6 +435,7 @@ extern "C" int tscl_pack_weights(tscl_handle* h, const float* params, void* wpac
   if ((d.dx % 16) != 0) return tsc_set_error("tscl_pack_weights: dx must be a multiple of 16");
   dim3 grid(8, 2 * d.A);
   pack_wxh_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, params, (__nv_bfloat16*)wpack_bf16);
+  pack_fc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, params, (__nv_bfloat16*)wpack_bf16);
   PCK(cudaGetLastError());
   return 0;
 }
@@ -440,6 +466,300 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
   a.swap_lbo_sbo = swap_lbo_sbo; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.step = (uint32_t)step; a.replica0 = replica0;
   policy_step_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+// ===================================================================================================
+// v2: the fc front end also runs on the tensor cores.
+//   A0 = observation slice tile [128 x 64] (wave32|fp16|wait16, bf16) staged in the LAST 8 K-chunks of the A tile,
+//   B0 = block-diagonal fc weights [64 x dx] staged in the FIRST chunks of the A tile (both regions are dead
+//        until the fc result is written / the h part is loaded), D0 = TMEM columns 256..256+dx;
+//   TMEM -> registers -> (+bias, relu, bf16) -> A tile chunks 0..dx/8, then h_prev -> last 8 chunks, then the
+//   gate MMA and the epilogue exactly as in v1.  Two tcgen05.commit per tile on one mbarrier.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = d.dx + TC_H, KC = K / 8, KS = K / 16, KCX = d.dx / 8;
+  unsigned char* sB = tc_smem;                                  // KC * 4096
+  unsigned char* sA = sB + (size_t)KC * 4096;                   // KC * 2048
+  float* sRed = reinterpret_cast<float*>(sA + (size_t)KC * 2048);   // [128][8]
+  float* sWo = sRed + TC_M * 8;                                 // [64][8]
+  float* sBo = sWo + TC_H * 8;                                  // [8]
+  float* sBias = sBo + 8;                                       // [256]  lstm bias
+  float* sBias0 = sBias + TC_N;                                 // [256]  fc biases
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sBias0 + TC_N);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
+  const uint32_t bar = smem_u32(sBar);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.dx >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  const int64_t n_tiles = (a.R + TC_M - 1) / TC_M;
+  const int64_t n_items = n_tiles * 2 * d.A;
+  const int64_t it_lo = n_items * blockIdx.x / gridDim.x, it_hi = n_items * (blockIdx.x + 1) / gridDim.x;
+  int cur_u = -1;
+  uint32_t parity = 0;
+  int nw = 0, nt = 0, nf = 0, ooff = 0, na = 0;
+  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+
+  for (int64_t it = it_lo; it < it_hi; ++it) {
+    const int u = (int)(it / n_tiles);
+    const int64_t r0 = (it - (int64_t)u * n_tiles) * TC_M;
+    const int ag = u >> 1;
+    const __nv_bfloat16* Wu = a.Wp + (int64_t)u * wp_stride(d.dx);
+    __syncthreads();      // previous tile fully retired (sRed, sA, TMEM readers)
+    if (u != cur_u) {
+      cur_u = u;
+      const uint4* src = reinterpret_cast<const uint4*>(Wu);
+      uint4* dst = reinterpret_cast<uint4*>(sB);
+      for (int i = tid; i < KC * TC_N; i += TC_THREADS) dst[i] = src[i];
+      nw = d.n_wave[ag]; nt = d.n_wait[ag]; nf = d.ff > 0 ? d.n_fp[ag] : 0;
+      ooff = d.obs_off[ag]; na = d.n_a[ag];
+      for (int i = tid; i < TC_H * 8; i += TC_THREADS) {
+        const int k = i >> 3, j = i & 7;
+        sWo[i] = j < d.max_na ? a.P[d.off_wo + ((int64_t)u * TC_H + k) * d.max_na + j] : 0.f;
+      }
+      if (tid < 8) sBo[tid] = tid < d.max_na ? a.P[d.off_bo + (int64_t)u * d.max_na + tid] : 0.f;
+      for (int i = tid; i < TC_N; i += TC_THREADS) {
+        sBias[i] = a.P[d.off_bl + (int64_t)u * TC_N + i];
+        float b0 = 0.f;
+        if (i < d.fw) b0 = a.P[d.off_fcw_b[u] + i];
+        else if (i < d.fw + d.ff) b0 = a.P[d.off_fcf_b[u] + (i - d.fw)];
+        else if (i < d.dx) b0 = a.P[d.off_fct_b[u] + (i - d.fw - d.ff)];
+        sBias0[i] = b0;
+      }
+    }
+    // ---- 1a. B0 (fc weights) -> first chunks of the A tile; 1b. observation slice -> last 8 chunks ----
+    {
+      const uint4* src0 = reinterpret_cast<const uint4*>(Wu + (int64_t)KC * TC_N * 8);
+      uint4* dst0 = reinterpret_cast<uint4*>(sA);
+      for (int i = tid; i < 8 * d.dx; i += TC_THREADS) dst0[i] = src0[i];
+      // thread = (row, 16-byte chunk) : 128 x 8 pairs, 4 per thread
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int pair = p * TC_THREADS + tid;
+        const int row = pair & 127, ch = pair >> 7;          // consecutive threads -> consecutive rows
+        const int64_t r = r0 + row;
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = ch * 8 + e;
+          int src = -1;
+          if (c < TC_KW) { if (c < nw) src = c; }
+          else if (c < TC_KW + TC_KF) { if (c - TC_KW < nf) src = nw + nt + (c - TC_KW); }
+          else { if (c - TC_KW - TC_KF < nt) src = nw + (c - TC_KW - TC_KF); }
+          float x = 0.f;
+          if (src >= 0 && r < a.R) x = __ldg(a.obs + r * d.n_obs + ooff + src);
+          v[e] = __float2bfloat16_rn(x);
+        }
+        *reinterpret_cast<uint4*>(sA + (size_t)(KC - 8 + ch) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 2. MMA0: D0[128 x dx] = A0[128 x 64] . B0[64 x dx]  (TMEM columns 256..) ----
+    if (warp == 0) {
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t da = make_desc(aA + (KC - 8 + 2 * ks) * 2048, 2048, 128);
+          const uint64_t db = make_desc(aA + ks * 2 * (d.dx * 16), d.dx * 16, 128);
+          umma_bf16(tmem + 256, da, db, idesc0, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- 3. X = relu(D0 + b) as bf16 -> A tile chunks 0..dx/8 ; h_prev -> last 8 chunks ----
+    {
+      const int q = warp & 3, hw = warp >> 2;
+      const int row = q * 32 + lane;
+      const int ncol = d.dx >> 1;                      // columns per half (multiple of 16)
+      for (int c0 = hw * ncol; c0 < (hw + 1) * ncol; c0 += 16) {
+        float z[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
+        *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+        *reinterpret_cast<uint4*>(sA + (size_t)((c0 >> 3) + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
+      }
+    }
+    {
+      const int row = tid >> 1, half = tid & 1;
+      const int64_t r = r0 + row;
+      const bool live = r < a.R && !a.done;
+      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * a.R + (r < a.R ? r : 0)) * TC_H + half * 32);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        __align__(16) __nv_bfloat16 v[8];
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+        if (live) { x0 = hp[2 * c8]; x1 = hp[2 * c8 + 1]; }
+        v[0] = __float2bfloat16_rn(x0.x); v[1] = __float2bfloat16_rn(x0.y); v[2] = __float2bfloat16_rn(x0.z); v[3] = __float2bfloat16_rn(x0.w);
+        v[4] = __float2bfloat16_rn(x1.x); v[5] = __float2bfloat16_rn(x1.y); v[6] = __float2bfloat16_rn(x1.z); v[7] = __float2bfloat16_rn(x1.w);
+        *reinterpret_cast<uint4*>(sA + (size_t)(KCX + half * 4 + c8) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 4. MMA1: gates D1[128 x 256] = [X | h][128 x K] . [Wx;Wh][K x 256] ----
+    if (warp == 0) {
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ks = 0; ks < KS; ++ks)
+          umma_bf16(tmem, make_desc(aA + ks * 2 * 2048, 2048, 128), make_desc(aB + ks * 2 * 4096, 4096, 128), idesc1,
+                    ks > 0 ? 1u : 0u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- 5. epilogue (identical to v1) ----
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int row = q * 32 + lane;
+      const int64_t r = r0 + row;
+      const bool valid = r < a.R;
+      const int64_t srow = ((int64_t)u * a.R + (valid ? r : 0)) * TC_H + half * 32;
+      float lg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) lg[j] = 0.f;
+#pragma unroll
+      for (int jb = 0; jb < 2; ++jb) {
+        float zi[16], zf[16], zo[16], zu[16];
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + jb * 16);
+        tmem_ld16(tbase, zi); tmem_ld16(tbase + 64, zf); tmem_ld16(tbase + 128, zo); tmem_ld16(tbase + 192, zu);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a.zdbg && valid) {
+          float* z = a.zdbg + ((int64_t)u * a.R + r) * TC_N + half * 32 + jb * 16;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { z[e] = zi[e]; z[64 + e] = zf[e]; z[128 + e] = zo[e]; z[192 + e] = zu[e]; }
+        }
+        float cprev[16];
+        if (valid && !a.done) {
+          const float4* cp = reinterpret_cast<const float4*>(a.c_in + srow + jb * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 x = cp[e4];
+            cprev[4 * e4] = x.x; cprev[4 * e4 + 1] = x.y; cprev[4 * e4 + 2] = x.z; cprev[4 * e4 + 3] = x.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cprev[e] = 0.f;
+        }
+        float cn[16], hn[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int j = half * 32 + jb * 16 + e;
+          const float gi = sigm(zi[e] + sBias[j]), gf = sigm(zf[e] + sBias[64 + j]);
+          const float go = sigm(zo[e] + sBias[128 + j]), gu = tanh_fast(zu[e] + sBias[192 + j]);
+          cn[e] = gf * cprev[e] + gi * gu;
+          hn[e] = go * tanh_fast(cn[e]);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
+        }
+        if (valid) {
+          float4* co = reinterpret_cast<float4*>(a.c_out + srow + jb * 16);
+          float4* ho = reinterpret_cast<float4*>(a.h_out + srow + jb * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            co[e4] = make_float4(cn[4 * e4], cn[4 * e4 + 1], cn[4 * e4 + 2], cn[4 * e4 + 3]);
+            ho[e4] = make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (half == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
+      }
+      __syncthreads();
+      if (half == 0 && valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lg[j] += sRed[row * 8 + j] + sBo[j];
+        if ((u & 1) == 0) {
+          float mx = -1e30f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < na) mx = fmaxf(mx, lg[j]);
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lg[j] = j < na ? __expf(lg[j] - mx) : 0.f; s += lg[j]; }
+          const float inv = 1.0f / s;
+          float* po = a.pi + ((int64_t)r * d.A + ag) * d.max_na;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < d.max_na) po[j] = lg[j] * inv;
+          if (a.act) {
+            uint32_t hsh = pmix32(a.seed_lo ^ (a.step * 0x9E3779B1U));
+            hsh = pmix32(hsh ^ a.seed_hi ^ ((uint32_t)(a.replica0 + r) * 0x85EBCA77U));
+            hsh = pmix32(hsh ^ ((uint32_t)ag * 0xC2B2AE3DU));
+            const float uu = (float)(hsh >> 8) * (1.0f / 16777216.0f);
+            float cum = 0.f;
+            int pick = na - 1;
+            bool found = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < na) { cum += lg[j] * inv; if (!found && uu < cum) { pick = j; found = true; } }
+            a.act[(int64_t)r * d.A + ag] = pick;
+          }
+        } else {
+          a.val[(int64_t)r * d.A + ag] = lg[0];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+static size_t tc2_smem_bytes(int K) {
+  const int KC = K / 8;
+  return (size_t)KC * 4096 + (size_t)KC * 2048 + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + 16;
+}
+
+extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs,
+                                   int64_t R, const float* c_in, const float* h_in, float* c_out, float* h_out,
+                                   float* pi, float* val, int32_t* act, int32_t done, uint64_t seed, int64_t step,
+                                   int64_t replica0, float* zdbg, void* stream) {
+  if (!h || !params || !wpack_bf16 || !obs || R <= 0) return tsc_set_error("tscl_policy_step_v2: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  const int K = d.dx + TC_H;
+  if ((d.dx % 32) != 0 || d.dx > 256) return tsc_set_error("tscl_policy_step_v2: dx must be a multiple of 32, <= 256");
+  if (8 * d.dx * 16 > (d.dx / 8) * 2048) return tsc_set_error("tscl_policy_step_v2: fc operand does not fit its staging region");
+  const size_t smem = tc2_smem_bytes(K);
+  if (smem > 232448) return tsc_set_error("tscl_policy_step_v2: operand tiles exceed shared memory");
+  static int attr_dev = -1;
+  if (attr_dev != tscl_device_of(h)) {
+    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = tscl_device_of(h);
+  }
+  int n_sm = 0;
+  PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
+  const int64_t n_items = ((R + TC_M - 1) / TC_M) * 2 * d.A;
+  const int grid = (int)(n_items < n_sm ? n_items : n_sm);
+  StepTC a;
+  a.P = params; a.Wp = (const __nv_bfloat16*)wpack_bf16; a.obs = obs; a.c_in = c_in; a.h_in = h_in; a.c_out = c_out;
+  a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done; a.swap_lbo_sbo = 0;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.step = (uint32_t)step; a.replica0 = replica0;
+  policy_step_tc2_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
 }

@@ -25,7 +25,12 @@
 
 #include "../../include/tsc.h"
 
+#ifndef TSC_THREADS
 #define TSC_THREADS 256
+#endif
+#ifndef TSC_MIN_BLOCKS
+#define TSC_MIN_BLOCKS 3   /* 3 CTAs/SM is the shared-memory limit for the 5x5 grid (70.9 KB each) */
+#endif
 #define INF_SPEED 1.0e9f
 #define F_CROSS 1
 #define F_ARRIVE 2
@@ -255,7 +260,7 @@ __device__ __forceinline__ void node_signal(const DevNet& n, int i, int a, int p
 // ------------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-__global__ void __launch_bounds__(TSC_THREADS)
+__global__ void __launch_bounds__(TSC_THREADS, TSC_MIN_BLOCKS)
 tsc_step_kernel(const StepArgs A) {
   const DevNet& n = A.net;
   const tsc_cfg& c = A.cfg;
@@ -708,6 +713,56 @@ __global__ void tsc_reset_kernel(uint8_t* lane_cnt, int32_t* ctl, int32_t* meas,
   for (int w = threadIdx.x; w < meas_words; w += blockDim.x) meas[(size_t)rep * meas_words + w] = 0;
 }
 
+// _measure_traffic_step (envs/env.py:409-437) for every replica: one CTA per replica over the compact state.
+// stats[r] = {n_live, n_departed_total, n_arrived_total, avg_wait, avg_speed, avg_queue, std_queue, backlog}
+// avg/std_queue: lane halting number (speed < 0.1 m/s, whole lane) over the detector lanes (envs/env.py:422-427).
+__global__ void tsc_stats_kernel(const DevNet n, const uint4* __restrict__ veh, const uint8_t* __restrict__ lane_cnt,
+                                 const int32_t* __restrict__ ctl, int ctl_words, float* __restrict__ stats) {
+  extern __shared__ int32_t sh[];
+  int32_t* s_pre = sh;                 // [L + 1]
+  int32_t* s_halt = sh + n.n_lanes + 1; // [L]
+  __shared__ float red[3];
+  const int rep = blockIdx.x, tid = threadIdx.x, L = n.n_lanes;
+  const uint8_t* cnt = lane_cnt + (size_t)rep * n.lpad;
+  if (tid == 0) {
+    int s = 0;
+    for (int l = 0; l < L; ++l) { s_pre[l] = s; s += cnt[l]; }
+    s_pre[L] = s;
+    red[0] = red[1] = 0.f;
+  }
+  for (int l = tid; l < L; l += blockDim.x) s_halt[l] = 0;
+  __syncthreads();
+  const int V = s_pre[L];
+  float w = 0.f, sp = 0.f;
+  for (int k = tid; k < V; k += blockDim.x) {
+    const uint4 v = veh[(size_t)rep * n.n_slots + k];
+    w += (float)(v.z & 1023u);
+    sp += __uint_as_float(v.y);
+    if (__uint_as_float(v.y) < 0.1f) {
+      int lo = 0, hi = L;
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= k) lo = mid; else hi = mid; }
+      atomicAdd(&s_halt[lo], 1);
+    }
+  }
+  atomicAdd(&red[0], w); atomicAdd(&red[1], sp);
+  __syncthreads();
+  if (tid == 0) {
+    const int32_t* c = ctl + (size_t)rep * ctl_words;
+    float q = 0.f, q2 = 0.f;
+    for (int d = 0; d < n.n_det; ++d) { const float h = (float)s_halt[n.det_lane[d]]; q += h; q2 += h * h; }
+    const float nd = (float)(n.n_det > 0 ? n.n_det : 1);
+    const float mq = q / nd;
+    float var = q2 / nd - mq * mq;
+    if (var < 0.f) var = 0.f;
+    int backlog = 0;
+    for (int s2 = 0; s2 < n.n_src; ++s2) backlog += c[CTL_FIXED + n.n_nodes + s2];
+    float* o = stats + (size_t)rep * 8;
+    o[0] = (float)V; o[1] = (float)c[3]; o[2] = (float)c[4];
+    o[3] = V > 0 ? red[0] / (float)V : 0.f; o[4] = V > 0 ? red[1] / (float)V : 0.f;
+    o[5] = mq; o[6] = sqrtf(var); o[7] = (float)backlog;
+  }
+}
+
 __global__ void tsc_live_kernel(const uint8_t* lane_cnt, int lpad, int L, int R, unsigned long long* out) {
   unsigned long long s = 0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)R * lpad; i += (size_t)gridDim.x * blockDim.x)
@@ -841,7 +896,7 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   size_t sm = (size_t)net->n_slots * 16;
   sm += (size_t)L * 4 * 2 + ((size_t)L + 1) * 4 + (size_t)L * 4 * 2 + (size_t)L * 2;
   sm = (sm + 3) & ~(size_t)3;
-  sm += (size_t)N * 4 * 6 + (size_t)net->n_src * 4 + (size_t)net->n_det * 12 + (size_t)N * 4 + 16 * 4;
+  sm += (size_t)N * 4 * 6 + (size_t)net->n_src * 4 + (size_t)net->n_det * 12 + (size_t)N * 4 + (8 + TSC_THREADS / 32) * 4;
   h->smem = (int)sm;
   if (sm > 227 * 1024) { tsc_destroy(h); return fail("tsc_create: replica state exceeds 227 KB of shared memory"); }
   CK(cudaFuncSetAttribute(tsc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
@@ -976,7 +1031,11 @@ extern "C" int tsc_mean_live(tsc_handle* h, double* mean_live) {
 }
 
 extern "C" int tsc_get_traffic_stats(tsc_handle* h, float* stats_dev, void* stream) {
-  (void)stats_dev; (void)stream;
-  if (!h) return fail("tsc_get_traffic_stats: null handle");
-  return fail("tsc_get_traffic_stats: not implemented in this round (SURVEY §8f.1)");
+  if (!h || !stats_dev) return fail("tsc_get_traffic_stats: bad argument");
+  CK(cudaSetDevice(h->device));
+  const DevNet& d = h->args.net;
+  tsc_stats_kernel<<<h->R, 128, (2 * d.n_lanes + 1) * 4, (cudaStream_t)stream>>>(d, h->args.veh, h->args.lane_cnt,
+                                                                                   h->args.ctl, h->args.ctl_words, stats_dev);
+  CK(cudaGetLastError());
+  return 0;
 }

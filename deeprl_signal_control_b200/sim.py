@@ -121,6 +121,13 @@ class BatchedSim:
                                              _np(veh, C.c_uint32), C.byref(nv)))
         return cnt, veh[:nv.value].copy()
 
+    def traffic_stats(self) -> torch.Tensor:
+        """[R, 8] = n_live, departed, arrived, avg_wait, avg_speed, avg_queue, std_queue, backlog
+        (the fields of reference _measure_traffic_step, envs/env.py:409-437)."""
+        out = torch.zeros(self.R, 8, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().tsc_get_traffic_stats(self._h, _ptr(out), self._stream()))
+        return out
+
     def mean_live(self) -> float:
         v = C.c_double(0)
         _lib.check(_lib.lib().tsc_mean_live(self._h, C.byref(v)))

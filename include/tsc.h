@@ -158,7 +158,8 @@ int tsc_get_counts(tsc_handle* h, int32_t* veh_dev /*[R][n_det]*/, int32_t* halt
 
 /* Per-replica traffic statistics of the last simulated second (_measure_traffic_step,
  * envs/env.py:409-437): stats_dev float [R][8] =
- * {n_live, n_departed_total, n_arrived_total, avg_wait, avg_speed, avg_queue, std_queue, backlog} */
+ * {n_live, n_departed_total, n_arrived_total, avg_wait, avg_speed, avg_queue, std_queue, backlog};
+ * avg/std_queue = lane halting number (speed < 0.1 m/s) over the detector lanes. */
 int tsc_get_traffic_stats(tsc_handle* h, float* stats_dev, void* stream);
 
 /* Debug / parity: copy replica r's full vehicle state to the host in canonical form:

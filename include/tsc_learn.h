@@ -107,8 +107,8 @@ int tscl_clip_rmsprop(tscl_handle* h, float* params, float* grads, float* ms, co
                       float max_norm, float lr, float alpha, float eps, float* norms, void* stream);
 
 /* ---- fused tensor-core policy forward (tcgen05 + TMEM), csrc/tsc_policy_tc.cu -------------------------
- * tscl_pack_weights: [Wx;Wh] of every unit -> bf16 UMMA operand image wpack [2A][(dx+h)/8][4h][8]
- *   (call after every optimizer step).
+ * tscl_pack_weights: per unit, [Wx;Wh] -> bf16 UMMA operand image [(dx+h)/8][4h][8] followed by the
+ *   block-diagonal fc image [8][dx][8]; wpack holds 2A such records (call after every optimizer step).
  * tscl_policy_step: one decision for R replicas and all agents in ONE kernel: fc front end, gate GEMM on
  *   the tensor cores (bf16 operands, fp32 accumulate in TMEM), LSTM cell, heads, softmax, sampling.
  *   Replaces LstmACPolicy.forward / FPLstmACPolicy.forward for a whole batch (agents/policies.py:125-136).
@@ -119,6 +119,15 @@ int tscl_policy_step(tscl_handle* h, const float* params, const void* wpack_bf16
                      const float* c_in, const float* h_in, float* c_out, float* h_out, float* pi, float* val,
                      int32_t* act, int32_t done, uint64_t seed, int64_t step, int64_t replica0, float* zdbg,
                      int32_t swap_lbo_sbo, void* stream);
+
+/* v2 of the fused forward: the fc front end runs on the tensor cores as well (observation slice tile x
+ * block-diagonal fc weights -> TMEM -> relu/bf16 -> A operand).  Same arguments as tscl_policy_step
+ * (without the descriptor debug switch); needs dx % 32 == 0.  wpack must come from tscl_pack_weights. */
+int tscl_policy_step_v2(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs, int64_t R,
+                        const float* c_in, const float* h_in, float* c_out, float* h_out, float* pi, float* val,
+                        int32_t* act, int32_t done, uint64_t seed, int64_t step, int64_t replica0, float* zdbg,
+                        void* stream);
+/* bf16 elements per unit in the packed image: ((dx+h)/8)*4h*8 + 8*dx*8 */
 
 #ifdef __cplusplus
 }

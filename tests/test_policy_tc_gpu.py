@@ -23,13 +23,15 @@ def _layout(ff):
     return PolicyLayout(n_s, [5, 4, 5], n_w, n_f, off, int(off[-1]) + 3, fw=128, ft=32, ff=ff, h=64, max_na=5)
 
 
-def _run_tc(m, obs, done, zdbg, swap):
+def _run_tc(m, obs, done, zdbg, swap, v2=False):
     from deeprl_signal_control_b200 import _lib
     from deeprl_signal_control_b200.agents.learner import _p
-    _lib.check(_lib.lib().tscl_policy_step(m._h, _p(m.P), _p(m.Wp), _p(obs), C.c_int64(m.R), _p(m.c_fw), _p(m.h_fw),
-                                           _p(m.c_tmp), _p(m.h_tmp), _p(m.pi), _p(m.val), _p(m.act),
-                                           C.c_int32(int(done)), C.c_uint64(7), C.c_int64(0), C.c_int64(0),
-                                           _p(zdbg), C.c_int32(swap), m._st()))
+    args = (m._h, _p(m.P), _p(m.Wp), _p(obs), C.c_int64(m.R), _p(m.c_fw), _p(m.h_fw), _p(m.c_tmp), _p(m.h_tmp),
+            _p(m.pi), _p(m.val), _p(m.act), C.c_int32(int(done)), C.c_uint64(7), C.c_int64(0), C.c_int64(0), _p(zdbg))
+    if v2:
+        _lib.check(_lib.lib().tscl_policy_step_v2(*args, m._st()))
+    else:
+        _lib.check(_lib.lib().tscl_policy_step(*args, C.c_int32(swap), m._st()))
     torch.cuda.synchronize()
 
 
@@ -64,6 +66,25 @@ def test_gate_accumulators_match_bf16_matmul(ff):
     # done flag zeroes h and c inside the cell (agents/utils.py:104-105)
     _run_tc(m, obs, True, zdbg, 0)
     torch.testing.assert_close(zdbg, torch.bmm(Xb, Wx), rtol=1e-3, atol=2e-3)
+    # v2 (fc front end on the tensor cores): reference with bf16-rounded observations and fc weights
+    v = lay.views(m.P)
+    Xs = []
+    for u in range(lay.U):
+        a = u // 2
+        o0 = int(lay.obs_off[a]); nw, nt, nf = int(lay.n_wave[a]), int(lay.n_wait[a]), int(lay.n_fp[a])
+        ob = obs.to(torch.bfloat16).float()
+        parts = [torch.relu(ob[:, o0:o0 + nw] @ v["fcw_w%d" % u].to(torch.bfloat16).float() + v["fcw_b%d" % u])]
+        if lay.ff > 0:
+            parts.append(torch.relu(ob[:, o0 + nw + nt:o0 + nw + nt + nf] @ v["fcf_w%d" % u].to(torch.bfloat16).float() + v["fcf_b%d" % u]))
+        parts.append(torch.relu(ob[:, o0 + nw:o0 + nw + nt] @ v["fct_w%d" % u].to(torch.bfloat16).float() + v["fct_b%d" % u]))
+        Xs.append(torch.cat(parts, 1))
+    X2 = torch.stack(Xs).to(torch.bfloat16).float()
+    z2_ref = torch.bmm(X2, Wx) + torch.bmm(Hb, Wh)
+    z2 = torch.zeros_like(zdbg)
+    _run_tc(m, obs, False, z2, 0, v2=True)
+    # a bf16 rounding flip of one X element moves z by <= |w| * 2^-8 * |x|: allow a few of them
+    assert float((z2 - z2_ref).abs().max()) < 4e-2, float((z2 - z2_ref).abs().max())
+    assert float((z2 - z2_ref).abs().mean()) < 2e-3
 
 
 @pytest.mark.parametrize("ff", [64, 0])

@@ -97,3 +97,27 @@ def test_host_entry_point_matches_device_entry_point(grid_ma2c):
         np.testing.assert_array_equal(o1.cpu().numpy(), o2)
         np.testing.assert_array_equal(r1.cpu().numpy(), r2)
         np.testing.assert_array_equal(g1.cpu().numpy(), g2)
+
+
+def test_traffic_stats_match_state_dump(grid_ma2c):
+    """tsc_get_traffic_stats (envs/env.py:409-437) against the same quantities computed from the state dump."""
+    net, par = grid_ma2c
+    from deeprl_signal_control_b200.sim import BatchedSim
+    R = 3
+    sim = BatchedSim(net, par, R)
+    sim.reset(np.arange(R, dtype=np.uint64) + np.uint64(77))
+    rng = np.random.default_rng(9)
+    for _ in range(150):
+        sim.step(torch.from_numpy(rng.integers(0, 5, (R, net.n_nodes), dtype=np.int32)).cuda())
+    st = sim.traffic_stats().cpu().numpy()
+    for r in range(R):
+        cnt, veh = sim.dump_state(r)
+        spd = veh[:, 1].copy().view(np.float32); wait = (veh[:, 2] & 1023).astype(np.float64)
+        lane_of = np.repeat(np.arange(net.n_lanes), cnt)
+        halt = np.bincount(lane_of[spd < 0.1], minlength=net.n_lanes)[net.det_lane]
+        assert st[r, 0] == len(veh) and len(veh) > 50
+        np.testing.assert_allclose(st[r, 3], wait.mean(), rtol=1e-5)
+        np.testing.assert_allclose(st[r, 4], spd.mean(), rtol=1e-4)
+        np.testing.assert_allclose(st[r, 5], halt.mean(), rtol=1e-5)
+        np.testing.assert_allclose(st[r, 6], halt.std(), rtol=1e-3, atol=1e-4)
+        assert st[r, 1] - st[r, 2] == len(veh)          # departed - arrived = live

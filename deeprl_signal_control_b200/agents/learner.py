@@ -36,7 +36,8 @@ class BatchedA2C:
                  v_coef: float = 0.5, max_grad_norm: float = 40.0, alpha: float = 0.99, eps: float = 1e-5,
                  reward_norm: float = 1.0, reward_clip: float = 0.0, seed: int = 0, device: int = 0,
                  chunk: int = 1024, replica0: int = 0, total_replicas: Optional[int] = None,
-                 process_group=None, allow_tf32: bool = True, use_tc: bool = True):
+                 process_group=None, allow_tf32: bool = True, use_tc: bool = True,
+                 store_acts: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedA2C needs a CUDA device (no CPU fallback exists)")
         self.lay, self.R, self.T = layout, int(n_replicas), int(n_step)
@@ -95,6 +96,19 @@ class BatchedA2C:
         self.Wp = torch.zeros(U, ((L.dx + L.h) // 8) * 4 * L.h * 8 + 8 * L.dx * 8, dtype=torch.bfloat16,
                               device=self.dev)
         self.pack_weights()
+        # bf16 activation store of the rollout's own forward pass (written by the v2 kernel): the update then
+        # back-propagates through it instead of recomputing fc + gate GEMM + LSTM forward.
+        need = U * T * R * (L.dx + 4 * L.h + 2 * L.h) * 2
+        if store_acts is None:
+            free, _ = torch.cuda.mem_get_info(self.dev)
+            store_acts = self.tc_v2 and need < 0.5 * free
+        self.store_acts = bool(store_acts) and self.tc_v2
+        self.st_x = self.st_g = self.st_c = self.st_h = None
+        if self.store_acts:
+            bf = dict(dtype=torch.bfloat16, device=self.dev)
+            self.st_x = torch.zeros(U, T, R, L.dx, **bf); self.st_g = torch.zeros(U, T, R, 4 * L.h, **bf)
+            self.st_c = torch.zeros(U, T, R, L.h, **bf); self.st_h = torch.zeros(U, T, R, L.h, **bf)
+        self._acts_ok = [False] * T      # step t of the current rollout was produced by a storing forward()
 
     def close(self):
         if getattr(self, "_h", None) is not None:
@@ -138,7 +152,12 @@ class BatchedA2C:
                     C.c_int32(1 if done else 0), C.c_uint64(self.seed), C.c_int64(self.n_forward),
                     C.c_int64(self.replica0), None)
             if self.tc_v2:
-                _lib.check(lib.tscl_policy_step_v2(*args, self._st()))
+                store = self.store_acts and commit and self.t < self.T
+                st = (_p(self.st_x), _p(self.st_g), _p(self.st_c), _p(self.st_h)) if store else (None,) * 4
+                _lib.check(lib.tscl_policy_step_v2(*args, *st, C.c_int32(self.t if store else 0), C.c_int32(self.T),
+                                                   self._st()))
+                if commit and self.t < self.T:
+                    self._acts_ok[self.t] = store
             else:
                 _lib.check(lib.tscl_policy_step(*args, C.c_int32(0), self._st()))
             self.kernel_launches += 1
@@ -213,6 +232,8 @@ class BatchedA2C:
         self.G.zero_()
         self.stats.zero_()
         scale = 1.0 / (T * self.total_replicas)
+        keep = (1.0 - dpre).view(1, T, 1, 1)
+        use_store = self.store_acts and all(self._acts_ok)
         n_obs = L.n_obs
         for r0 in range(0, R, self.chunk):
             rc = min(self.chunk, R - r0)
@@ -224,12 +245,24 @@ class BatchedA2C:
                 X, ZG, Cc, H, Hp, dH, dX, dlog = (torch.empty(U, M, s_, **f32) for s_ in
                                                   (L.dx, 4 * L.h, L.h, L.h, L.h, L.h, L.dx, L.max_na))
             obs0 = self.obs_hist[0, r0:]
-            _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs0), C.c_int64(M), C.c_int64(rc),
-                                         C.c_int64(R * n_obs), _p(X), st()))
-            torch.baddbmm(self.pv["bl"].unsqueeze(1), X, self.pv["wx"], out=ZG)
-            _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(H), _p(Hp), _p(self.c_bw), _p(self.h_bw),
-                                             None, None, _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R),
-                                             C.c_int64(r0), st()))
+            if use_store:
+                # activations of the rollout's forward pass (bf16 store -> fp32 chunk buffers, strided copy)
+                sl = slice(r0, r0 + rc)
+                X.view(U, T, rc, L.dx).copy_(self.st_x[:, :, sl])
+                ZG.view(U, T, rc, 4 * L.h).copy_(self.st_g[:, :, sl])
+                Cc.view(U, T, rc, L.h).copy_(self.st_c[:, :, sl])
+                H4, Hp4 = H.view(U, T, rc, L.h), Hp.view(U, T, rc, L.h)
+                H4.copy_(self.st_h[:, :, sl])
+                Hp4[:, 1:].copy_(H4[:, :-1])
+                Hp4[:, 0].copy_(self.h_bw[:, sl])
+                Hp4.mul_(keep)
+            else:
+                _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs0), C.c_int64(M), C.c_int64(rc),
+                                             C.c_int64(R * n_obs), _p(X), st()))
+                torch.baddbmm(self.pv["bl"].unsqueeze(1), X, self.pv["wx"], out=ZG)
+                _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(H), _p(Hp), _p(self.c_bw),
+                                                 _p(self.h_bw), None, None, _p(dpre), C.c_int32(T), C.c_int64(rc),
+                                                 C.c_int64(R), C.c_int64(r0), st()))
             _lib.check(lib.tscl_heads_loss(self._h, _p(self.P), _p(H), _p(self.act_hist[0, r0:]), _p(self.Rs[0, r0:]),
                                            _p(self.Adv[0, r0:]), C.c_int64(M), C.c_int64(rc), C.c_int64(R * A),
                                            C.c_float(self.v_coef), C.c_float(beta), C.c_float(scale), _p(dlog),
@@ -246,7 +279,7 @@ class BatchedA2C:
             torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
             _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
                                        C.c_int64(R * n_obs), _p(self.G), st()))
-            self.kernel_launches += 5
+            self.kernel_launches += 3 if use_store else 5
         if self.pg is not None:
             torch.distributed.all_reduce(self.G, op=torch.distributed.ReduceOp.SUM, group=self.pg)
         _lib.check(lib.tscl_clip_rmsprop(self._h, _p(self.P), _p(self.G), _p(self.MS), _p(self.agent_of),
@@ -259,3 +292,4 @@ class BatchedA2C:
         self.obs_hist[0].copy_(self.obs_hist[T])
         self.last_done = bool(self.done_post[-1])
         self.t = 0
+        self._acts_ok = [False] * T

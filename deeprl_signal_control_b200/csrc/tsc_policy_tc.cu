@@ -158,6 +158,9 @@ struct StepTC {
   int swap_lbo_sbo;        // debug: exchange the two descriptor strides
   uint32_t seed_lo, seed_hi, step;
   int64_t replica0;
+  // optional activation store for the update (v2 only): bf16 [2A][T][R][w], w = dx / 256 / 64 / 64
+  __nv_bfloat16 *st_x, *st_g, *st_c, *st_h;
+  int t, T;
 };
 
 extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -465,6 +468,7 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
   a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done;
   a.swap_lbo_sbo = swap_lbo_sbo; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.step = (uint32_t)step; a.replica0 = replica0;
+  a.st_x = a.st_g = a.st_c = a.st_h = nullptr; a.t = 0; a.T = 1;
   policy_step_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
@@ -598,6 +602,10 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         for (int e = 0; e < 16; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
         *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
         *reinterpret_cast<uint4*>(sA + (size_t)((c0 >> 3) + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
+        if (a.st_x && r0 + row < a.R) {
+          uint4* o = reinterpret_cast<uint4*>(a.st_x + ((((int64_t)u * a.T + a.t) * a.R + r0 + row) * d.dx + c0));
+          o[0] = *reinterpret_cast<const uint4*>(v); o[1] = *reinterpret_cast<const uint4*>(v + 8);
+        }
       }
     }
     {
@@ -666,6 +674,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
           for (int e = 0; e < 16; ++e) cprev[e] = 0.f;
         }
         float cn[16], hn[16];
+        __align__(16) __nv_bfloat16 gbuf[4][16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int j = half * 32 + jb * 16 + e;
@@ -673,8 +682,26 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
           const float go = sigm(zo[e] + sBias[128 + j]), gu = tanh_fast(zu[e] + sBias[192 + j]);
           cn[e] = gf * cprev[e] + gi * gu;
           hn[e] = go * tanh_fast(cn[e]);
+          gbuf[0][e] = __float2bfloat16_rn(gi); gbuf[1][e] = __float2bfloat16_rn(gf);
+          gbuf[2][e] = __float2bfloat16_rn(go); gbuf[3][e] = __float2bfloat16_rn(gu);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
+        }
+        if (valid && a.st_g) {
+          const int64_t m = ((int64_t)u * a.T + a.t) * a.R + r;
+          const int jo = half * 32 + jb * 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4* o = reinterpret_cast<uint4*>(a.st_g + m * TC_N + g * 64 + jo);
+            o[0] = *reinterpret_cast<const uint4*>(&gbuf[g][0]); o[1] = *reinterpret_cast<const uint4*>(&gbuf[g][8]);
+          }
+          __align__(16) __nv_bfloat16 cb[16], hb[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { cb[e] = __float2bfloat16_rn(cn[e]); hb[e] = __float2bfloat16_rn(hn[e]); }
+          uint4* oc = reinterpret_cast<uint4*>(a.st_c + m * TC_H + jo);
+          uint4* oh = reinterpret_cast<uint4*>(a.st_h + m * TC_H + jo);
+          oc[0] = *reinterpret_cast<const uint4*>(cb); oc[1] = *reinterpret_cast<const uint4*>(cb + 8);
+          oh[0] = *reinterpret_cast<const uint4*>(hb); oh[1] = *reinterpret_cast<const uint4*>(hb + 8);
         }
         if (valid) {
           float4* co = reinterpret_cast<float4*>(a.c_out + srow + jb * 16);
@@ -737,7 +764,8 @@ static size_t tc2_smem_bytes(int K) {
 extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs,
                                    int64_t R, const float* c_in, const float* h_in, float* c_out, float* h_out,
                                    float* pi, float* val, int32_t* act, int32_t done, uint64_t seed, int64_t step,
-                                   int64_t replica0, float* zdbg, void* stream) {
+                                   int64_t replica0, float* zdbg, void* st_x, void* st_g, void* st_c, void* st_h,
+                                   int32_t t, int32_t T, void* stream) {
   if (!h || !params || !wpack_bf16 || !obs || R <= 0) return tsc_set_error("tscl_policy_step_v2: bad argument");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
@@ -759,6 +787,8 @@ extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const vo
   a.P = params; a.Wp = (const __nv_bfloat16*)wpack_bf16; a.obs = obs; a.c_in = c_in; a.h_in = h_in; a.c_out = c_out;
   a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done; a.swap_lbo_sbo = 0;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.step = (uint32_t)step; a.replica0 = replica0;
+  a.st_x = (__nv_bfloat16*)st_x; a.st_g = (__nv_bfloat16*)st_g; a.st_c = (__nv_bfloat16*)st_c; a.st_h = (__nv_bfloat16*)st_h;
+  a.t = t; a.T = T > 0 ? T : 1;
   policy_step_tc2_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;

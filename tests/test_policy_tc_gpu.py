@@ -29,7 +29,7 @@ def _run_tc(m, obs, done, zdbg, swap, v2=False):
     args = (m._h, _p(m.P), _p(m.Wp), _p(obs), C.c_int64(m.R), _p(m.c_fw), _p(m.h_fw), _p(m.c_tmp), _p(m.h_tmp),
             _p(m.pi), _p(m.val), _p(m.act), C.c_int32(int(done)), C.c_uint64(7), C.c_int64(0), C.c_int64(0), _p(zdbg))
     if v2:
-        _lib.check(_lib.lib().tscl_policy_step_v2(*args, m._st()))
+        _lib.check(_lib.lib().tscl_policy_step_v2(*args, None, None, None, None, C.c_int32(0), C.c_int32(1), m._st()))
     else:
         _lib.check(_lib.lib().tscl_policy_step(*args, C.c_int32(swap), m._st()))
     torch.cuda.synchronize()
@@ -115,3 +115,38 @@ def test_fused_forward_matches_fp32_path(ff):
         a.c_fw.copy_(b.c_fw); a.h_fw.copy_(b.h_fw)
     # identical probabilities -> identical inverse-CDF samples wherever u is not within the bf16 error of a boundary
     assert float((aa == ab).float().mean()) > 0.97
+
+
+def test_update_from_stored_activations_matches_recompute():
+    """The update that back-propagates through the rollout's stored bf16 activations must agree with the
+    update that recomputes the forward pass (same rollout, same parameters) within bf16 noise."""
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C
+    lay = _layout(64)
+    R, T = 200, 6
+    kw = dict(n_step=T, gamma=0.99, v_coef=0.5, max_grad_norm=0.0, seed=9, chunk=128, reward_norm=2.0,
+              reward_clip=2.0, allow_tf32=False)
+    a = BatchedA2C(lay, R, use_tc=True, store_acts=True, **kw)
+    b = BatchedA2C(lay, R, use_tc=True, store_acts=False, **kw)
+    assert a.store_acts and not b.store_acts
+    rng = np.random.default_rng(5)
+    dones = [True, False, False, True, False, False]
+    for t in range(T):
+        obs = torch.from_numpy((rng.random((R, lay.n_obs)) * 2).astype(np.float32)).cuda()
+        rew = torch.from_numpy(rng.normal(0, 3, (R, lay.A)).astype(np.float32)).cuda()
+        for m in (a, b):
+            m.obs_slot().copy_(obs)
+            m.forward(m.obs_slot(), dones[t])
+            m.add_transition(rew, dones[t], dones[t + 1] if t + 1 < T else False)
+    assert torch.equal(a.act_hist, b.act_hist)
+    boot = torch.from_numpy(rng.normal(0, 1, (R, lay.A)).astype(np.float32)).cuda()
+    a.backward(boot, lr=0.0, beta=0.01); b.backward(boot, lr=0.0, beta=0.01)
+    torch.cuda.synchronize()
+    ga, gb = lay.views(a.G.cpu().numpy()), lay.views(b.G.cpu().numpy())
+    for k in ga:
+        if gb[k].size == 0:
+            continue
+        scale = max(np.abs(gb[k]).max(), 1e-8)
+        assert np.abs(ga[k] - gb[k]).max() / scale < 4e-2, (k, np.abs(ga[k] - gb[k]).max() / scale)
+    # and the overall direction is the same
+    va, vb = a.G.flatten(), b.G.flatten()
+    assert float(torch.dot(va, vb) / (va.norm() * vb.norm())) > 0.999

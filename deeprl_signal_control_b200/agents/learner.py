@@ -102,12 +102,13 @@ class BatchedA2C:
         if store_acts is None:
             free, _ = torch.cuda.mem_get_info(self.dev)
             store_acts = self.tc_v2 and need < 0.5 * free
-        self.store_acts = bool(store_acts) and self.tc_v2
+        self.store_acts = bool(store_acts) and self.tc_v2 and (R % self.chunk == 0)
         self.st_x = self.st_g = self.st_c = self.st_h = None
-        if self.store_acts:
+        if self.store_acts:       # [U][R/chunk][T][chunk][w]: every update chunk is one contiguous block
             bf = dict(dtype=torch.bfloat16, device=self.dev)
-            self.st_x = torch.zeros(U, T, R, L.dx, **bf); self.st_g = torch.zeros(U, T, R, 4 * L.h, **bf)
-            self.st_c = torch.zeros(U, T, R, L.h, **bf); self.st_h = torch.zeros(U, T, R, L.h, **bf)
+            nc, rc_ = R // self.chunk, self.chunk
+            self.st_x = torch.zeros(U, nc, T, rc_, L.dx, **bf); self.st_g = torch.zeros(U, nc, T, rc_, 4 * L.h, **bf)
+            self.st_c = torch.zeros(U, nc, T, rc_, L.h, **bf); self.st_h = torch.zeros(U, nc, T, rc_, L.h, **bf)
         self._acts_ok = [False] * T      # step t of the current rollout was produced by a storing forward()
 
     def close(self):
@@ -155,7 +156,7 @@ class BatchedA2C:
                 store = self.store_acts and commit and self.t < self.T
                 st = (_p(self.st_x), _p(self.st_g), _p(self.st_c), _p(self.st_h)) if store else (None,) * 4
                 _lib.check(lib.tscl_policy_step_v2(*args, *st, C.c_int32(self.t if store else 0), C.c_int32(self.T),
-                                                   self._st()))
+                                                   C.c_int64(self.chunk), self._st()))
                 if commit and self.t < self.T:
                     self._acts_ok[self.t] = store
             else:
@@ -247,12 +248,12 @@ class BatchedA2C:
             obs0 = self.obs_hist[0, r0:]
             if use_store:
                 # activations of the rollout's forward pass (bf16 store -> fp32 chunk buffers, strided copy)
-                sl = slice(r0, r0 + rc)
-                X.view(U, T, rc, L.dx).copy_(self.st_x[:, :, sl])
-                ZG.view(U, T, rc, 4 * L.h).copy_(self.st_g[:, :, sl])
-                Cc.view(U, T, rc, L.h).copy_(self.st_c[:, :, sl])
+                sl, ci = slice(r0, r0 + rc), r0 // self.chunk
+                X.view(U, T, rc, L.dx).copy_(self.st_x[:, ci])
+                ZG.view(U, T, rc, 4 * L.h).copy_(self.st_g[:, ci])
+                Cc.view(U, T, rc, L.h).copy_(self.st_c[:, ci])
                 H4, Hp4 = H.view(U, T, rc, L.h), Hp.view(U, T, rc, L.h)
-                H4.copy_(self.st_h[:, :, sl])
+                H4.copy_(self.st_h[:, ci])
                 Hp4[:, 1:].copy_(H4[:, :-1])
                 Hp4[:, 0].copy_(self.h_bw[:, sl])
                 Hp4.mul_(keep)

@@ -158,9 +158,11 @@ struct StepTC {
   int swap_lbo_sbo;        // debug: exchange the two descriptor strides
   uint32_t seed_lo, seed_hi, step;
   int64_t replica0;
-  // optional activation store for the update (v2 only): bf16 [2A][T][R][w], w = dx / 256 / 64 / 64
+  // optional activation store for the update (v2 only): bf16 [2A][R/rc][T][rc][w], w = dx / 256 / 64 / 64
+  // (replica-chunk major, so that each update chunk is one contiguous block)
   __nv_bfloat16 *st_x, *st_g, *st_c, *st_h;
   int t, T;
+  int64_t rc;
 };
 
 extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -468,7 +470,7 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
   a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done;
   a.swap_lbo_sbo = swap_lbo_sbo; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.step = (uint32_t)step; a.replica0 = replica0;
-  a.st_x = a.st_g = a.st_c = a.st_h = nullptr; a.t = 0; a.T = 1;
+  a.st_x = a.st_g = a.st_c = a.st_h = nullptr; a.t = 0; a.T = 1; a.rc = R;
   policy_step_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
@@ -603,7 +605,9 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
         *reinterpret_cast<uint4*>(sA + (size_t)((c0 >> 3) + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
         if (a.st_x && r0 + row < a.R) {
-          uint4* o = reinterpret_cast<uint4*>(a.st_x + ((((int64_t)u * a.T + a.t) * a.R + r0 + row) * d.dx + c0));
+          const int64_t rr = r0 + row;
+          const int64_t m = (((int64_t)u * (a.R / a.rc) + rr / a.rc) * a.T + a.t) * a.rc + rr % a.rc;
+          uint4* o = reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0));
           o[0] = *reinterpret_cast<const uint4*>(v); o[1] = *reinterpret_cast<const uint4*>(v + 8);
         }
       }
@@ -688,7 +692,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
           for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
         }
         if (valid && a.st_g) {
-          const int64_t m = ((int64_t)u * a.T + a.t) * a.R + r;
+          const int64_t m = (((int64_t)u * (a.R / a.rc) + r / a.rc) * a.T + a.t) * a.rc + r % a.rc;
           const int jo = half * 32 + jb * 16;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -765,8 +769,9 @@ extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const vo
                                    int64_t R, const float* c_in, const float* h_in, float* c_out, float* h_out,
                                    float* pi, float* val, int32_t* act, int32_t done, uint64_t seed, int64_t step,
                                    int64_t replica0, float* zdbg, void* st_x, void* st_g, void* st_c, void* st_h,
-                                   int32_t t, int32_t T, void* stream) {
+                                   int32_t t, int32_t T, int64_t rc, void* stream) {
   if (!h || !params || !wpack_bf16 || !obs || R <= 0) return tsc_set_error("tscl_policy_step_v2: bad argument");
+  if (st_x && (rc <= 0 || R % rc != 0)) return tsc_set_error("tscl_policy_step_v2: store chunk must divide R");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
   const int K = d.dx + TC_H;
@@ -788,7 +793,7 @@ extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const vo
   a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done; a.swap_lbo_sbo = 0;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.step = (uint32_t)step; a.replica0 = replica0;
   a.st_x = (__nv_bfloat16*)st_x; a.st_g = (__nv_bfloat16*)st_g; a.st_c = (__nv_bfloat16*)st_c; a.st_h = (__nv_bfloat16*)st_h;
-  a.t = t; a.T = T > 0 ? T : 1;
+  a.t = t; a.T = T > 0 ? T : 1; a.rc = rc > 0 ? rc : R;
   policy_step_tc2_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;

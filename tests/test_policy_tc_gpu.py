@@ -29,7 +29,7 @@ def _run_tc(m, obs, done, zdbg, swap, v2=False):
     args = (m._h, _p(m.P), _p(m.Wp), _p(obs), C.c_int64(m.R), _p(m.c_fw), _p(m.h_fw), _p(m.c_tmp), _p(m.h_tmp),
             _p(m.pi), _p(m.val), _p(m.act), C.c_int32(int(done)), C.c_uint64(7), C.c_int64(0), C.c_int64(0), _p(zdbg))
     if v2:
-        _lib.check(_lib.lib().tscl_policy_step_v2(*args, None, None, None, None, C.c_int32(0), C.c_int32(1), m._st()))
+        _lib.check(_lib.lib().tscl_policy_step_v2(*args, None, None, None, None, C.c_int32(0), C.c_int32(1), C.c_int64(0), m._st()))
     else:
         _lib.check(_lib.lib().tscl_policy_step(*args, C.c_int32(swap), m._st()))
     torch.cuda.synchronize()
@@ -123,7 +123,7 @@ def test_update_from_stored_activations_matches_recompute():
     from deeprl_signal_control_b200.agents.learner import BatchedA2C
     lay = _layout(64)
     R, T = 200, 6
-    kw = dict(n_step=T, gamma=0.99, v_coef=0.5, max_grad_norm=0.0, seed=9, chunk=128, reward_norm=2.0,
+    kw = dict(n_step=T, gamma=0.99, v_coef=0.5, max_grad_norm=0.0, seed=9, chunk=100, reward_norm=2.0,
               reward_clip=2.0, allow_tf32=False)
     a = BatchedA2C(lay, R, use_tc=True, store_acts=True, **kw)
     b = BatchedA2C(lay, R, use_tc=True, store_acts=False, **kw)
@@ -142,11 +142,17 @@ def test_update_from_stored_activations_matches_recompute():
     a.backward(boot, lr=0.0, beta=0.01); b.backward(boot, lr=0.0, beta=0.01)
     torch.cuda.synchronize()
     ga, gb = lay.views(a.G.cpu().numpy()), lay.views(b.G.cpu().numpy())
+    worst = 1.0
     for k in ga:
-        if gb[k].size == 0:
+        if gb[k].size < 8:
             continue
-        scale = max(np.abs(gb[k]).max(), 1e-8)
-        assert np.abs(ga[k] - gb[k]).max() / scale < 4e-2, (k, np.abs(ga[k] - gb[k]).max() / scale)
-    # and the overall direction is the same
-    va, vb = a.G.flatten(), b.G.flatten()
+        x, y = ga[k].ravel().astype(np.float64), gb[k].ravel().astype(np.float64)
+        if np.linalg.norm(y) < 1e-12:
+            continue
+        cos = float(x @ y / (np.linalg.norm(x) * np.linalg.norm(y) + 1e-30))
+        rel = float(np.linalg.norm(x - y) / np.linalg.norm(y))
+        worst = min(worst, cos)
+        assert cos > 0.99 and rel < 0.12, (k, cos, rel)      # per-tensor: bf16 activations vs fp32 recompute
+    va, vb = a.G.flatten().double(), b.G.flatten().double()
     assert float(torch.dot(va, vb) / (va.norm() * vb.norm())) > 0.999
+    assert float((va - vb).norm() / vb.norm()) < 0.03

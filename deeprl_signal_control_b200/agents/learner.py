@@ -104,11 +104,11 @@ class BatchedA2C:
             store_acts = self.tc_v2 and need < 0.5 * free
         self.store_acts = bool(store_acts) and self.tc_v2 and (R % self.chunk == 0)
         self.st_x = self.st_g = self.st_c = self.st_h = None
-        if self.store_acts:       # [U][R/chunk][T][chunk][w]: every update chunk is one contiguous block
+        if self.store_acts:       # [R/chunk][U][T][chunk][w]: every update chunk is one contiguous block
             bf = dict(dtype=torch.bfloat16, device=self.dev)
             nc, rc_ = R // self.chunk, self.chunk
-            self.st_x = torch.zeros(U, nc, T, rc_, L.dx, **bf); self.st_g = torch.zeros(U, nc, T, rc_, 4 * L.h, **bf)
-            self.st_c = torch.zeros(U, nc, T, rc_, L.h, **bf); self.st_h = torch.zeros(U, nc, T, rc_, L.h, **bf)
+            self.st_x = torch.zeros(nc, U, T, rc_, L.dx, **bf); self.st_g = torch.zeros(nc, U, T, rc_, 4 * L.h, **bf)
+            self.st_c = torch.zeros(nc, U, T, rc_, L.h, **bf); self.st_h = torch.zeros(nc, U, T, rc_, L.h, **bf)
         self._acts_ok = [False] * T      # step t of the current rollout was produced by a storing forward()
 
     def close(self):
@@ -249,11 +249,11 @@ class BatchedA2C:
             if use_store:
                 # activations of the rollout's forward pass (bf16 store -> fp32 chunk buffers, strided copy)
                 sl, ci = slice(r0, r0 + rc), r0 // self.chunk
-                X.view(U, T, rc, L.dx).copy_(self.st_x[:, ci])
-                ZG.view(U, T, rc, 4 * L.h).copy_(self.st_g[:, ci])
-                Cc.view(U, T, rc, L.h).copy_(self.st_c[:, ci])
+                X.view(U, T, rc, L.dx).copy_(self.st_x[ci])
+                ZG.view(U, T, rc, 4 * L.h).copy_(self.st_g[ci])
+                Cc.view(U, T, rc, L.h).copy_(self.st_c[ci])
                 H4, Hp4 = H.view(U, T, rc, L.h), Hp.view(U, T, rc, L.h)
-                H4.copy_(self.st_h[:, ci])
+                H4.copy_(self.st_h[ci])
                 Hp4[:, 1:].copy_(H4[:, :-1])
                 Hp4[:, 0].copy_(self.h_bw[:, sl])
                 Hp4.mul_(keep)

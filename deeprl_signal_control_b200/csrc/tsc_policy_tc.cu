@@ -158,7 +158,7 @@ struct StepTC {
   int swap_lbo_sbo;        // debug: exchange the two descriptor strides
   uint32_t seed_lo, seed_hi, step;
   int64_t replica0;
-  // optional activation store for the update (v2 only): bf16 [2A][R/rc][T][rc][w], w = dx / 256 / 64 / 64
+  // optional activation store for the update (v2 only): bf16 [R/rc][2A][T][rc][w], w = dx / 256 / 64 / 64
   // (replica-chunk major, so that each update chunk is one contiguous block)
   __nv_bfloat16 *st_x, *st_g, *st_c, *st_h;
   int t, T;
@@ -606,7 +606,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         *reinterpret_cast<uint4*>(sA + (size_t)((c0 >> 3) + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
         if (a.st_x && r0 + row < a.R) {
           const int64_t rr = r0 + row;
-          const int64_t m = (((int64_t)u * (a.R / a.rc) + rr / a.rc) * a.T + a.t) * a.rc + rr % a.rc;
+          const int64_t m = (((rr / a.rc) * (2 * d.A) + u) * a.T + a.t) * a.rc + rr % a.rc;
           uint4* o = reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0));
           o[0] = *reinterpret_cast<const uint4*>(v); o[1] = *reinterpret_cast<const uint4*>(v + 8);
         }
@@ -692,7 +692,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
           for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
         }
         if (valid && a.st_g) {
-          const int64_t m = (((int64_t)u * (a.R / a.rc) + r / a.rc) * a.T + a.t) * a.rc + r % a.rc;
+          const int64_t m = (((r / a.rc) * (2 * d.A) + u) * a.T + a.t) * a.rc + r % a.rc;
           const int jo = half * 32 + jb * 16;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {

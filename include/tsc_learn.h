@@ -127,7 +127,7 @@ int tscl_policy_step_v2(tscl_handle* h, const float* params, const void* wpack_b
                         const float* c_in, const float* h_in, float* c_out, float* h_out, float* pi, float* val,
                         int32_t* act, int32_t done, uint64_t seed, int64_t step, int64_t replica0, float* zdbg,
                         void* st_x, void* st_g, void* st_c, void* st_h, int32_t t, int32_t T, int64_t rc, void* stream);
-/* st_x/st_g/st_c/st_h (all or none, may be NULL): bf16 activation store [2A][R/rc][T][rc][dx | 4h | h | h]
+/* st_x/st_g/st_c/st_h (all or none, may be NULL): bf16 activation store [R/rc][2A][T][rc][dx | 4h | h | h]
  * (replica-chunk major; rc must divide R) written at time index t — the relu'd fc outputs, the gate activations i,f,o,u, c_t and h_t — so that the update can
  * back-propagate through the rollout's own forward pass instead of recomputing it.
  * bf16 elements per unit in the packed weight image: ((dx+h)/8)*4h*8 + 8*dx*8 */

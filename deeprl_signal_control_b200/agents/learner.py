@@ -233,7 +233,6 @@ class BatchedA2C:
         self.G.zero_()
         self.stats.zero_()
         scale = 1.0 / (T * self.total_replicas)
-        keep = (1.0 - dpre).view(1, T, 1, 1)
         use_store = self.store_acts and all(self._acts_ok)
         n_obs = L.n_obs
         for r0 in range(0, R, self.chunk):
@@ -248,15 +247,11 @@ class BatchedA2C:
             obs0 = self.obs_hist[0, r0:]
             if use_store:
                 # activations of the rollout's forward pass (bf16 store -> fp32 chunk buffers, strided copy)
-                sl, ci = slice(r0, r0 + rc), r0 // self.chunk
-                X.view(U, T, rc, L.dx).copy_(self.st_x[ci])
-                ZG.view(U, T, rc, 4 * L.h).copy_(self.st_g[ci])
-                Cc.view(U, T, rc, L.h).copy_(self.st_c[ci])
-                H4, Hp4 = H.view(U, T, rc, L.h), Hp.view(U, T, rc, L.h)
-                H4.copy_(self.st_h[ci])
-                Hp4[:, 1:].copy_(H4[:, :-1])
-                Hp4[:, 0].copy_(self.h_bw[:, sl])
-                Hp4.mul_(keep)
+                ci = r0 // self.chunk
+                _lib.check(lib.tscl_unpack_store(self._h, _p(self.st_x[ci]), _p(self.st_g[ci]), _p(self.st_c[ci]),
+                                                 _p(self.st_h[ci]), _p(X), _p(ZG), _p(Cc), _p(H), _p(Hp), _p(self.h_bw),
+                                                 _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0),
+                                                 st()))
             else:
                 _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs0), C.c_int64(M), C.c_int64(rc),
                                              C.c_int64(R * n_obs), _p(X), st()))
@@ -280,7 +275,7 @@ class BatchedA2C:
             torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
             _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
                                        C.c_int64(R * n_obs), _p(self.G), st()))
-            self.kernel_launches += 3 if use_store else 5
+            self.kernel_launches += 4 if use_store else 5
         if self.pg is not None:
             torch.distributed.all_reduce(self.G, op=torch.distributed.ReduceOp.SUM, group=self.pg)
         _lib.check(lib.tscl_clip_rmsprop(self._h, _p(self.P), _p(self.G), _p(self.MS), _p(self.agent_of),

@@ -484,14 +484,18 @@ lstm_seq_bwd_kernel(const DDims d, const float* __restrict__ P, float* __restric
     __syncthreads();
     if (keep != 0.f && t > 0) {
       float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int col = 0; col < G4; ++col) {
-        const float2 w = *reinterpret_cast<const float2*>(&sWT[col * H64 + j0]);
+#pragma unroll 2
+      for (int col = 0; col < G4; col += 4) {
+        float2 w[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) w[cc] = *reinterpret_cast<const float2*>(&sWT[(col + cc) * H64 + j0]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float z = sdz[(ty * 4 + q) * G4 + col];
-          a0[q] = fmaf(z, w.x, a0[q]);
-          a1[q] = fmaf(z, w.y, a1[q]);
+          const float4 z = *reinterpret_cast<const float4*>(&sdz[(ty * 4 + q) * G4 + col]);   // warp-wide broadcast
+          a0[q] = fmaf(z.x, w[0].x, a0[q]); a1[q] = fmaf(z.x, w[0].y, a1[q]);
+          a0[q] = fmaf(z.y, w[1].x, a0[q]); a1[q] = fmaf(z.y, w[1].y, a1[q]);
+          a0[q] = fmaf(z.z, w[2].x, a0[q]); a1[q] = fmaf(z.z, w[2].y, a1[q]);
+          a0[q] = fmaf(z.w, w[3].x, a0[q]); a1[q] = fmaf(z.w, w[3].y, a1[q]);
         }
       }
 #pragma unroll
@@ -578,6 +582,44 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
     for (int k = 0; k < FE_KW; ++k)
       if (k < nk) atomicAdd(&G[wo + (int64_t)k * ld + c], acc[k]);
     atomicAdd(&G[bo + c], accb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Activation-store chunk -> fp32 work buffers in one pass: X, gates, C, H (8 bf16 = 16 B per thread-iteration)
+// and Hp[t] = keep[t] * (t > 0 ? H[t-1] : h0).  All arrays are [2A][T][rc][w] contiguous.
+__global__ void unpack_store_kernel(const uint4* __restrict__ sx, const uint4* __restrict__ sg, const uint4* __restrict__ sc,
+                                    const uint4* __restrict__ shh, float4* __restrict__ X, float4* __restrict__ ZG,
+                                    float4* __restrict__ Cc, float4* __restrict__ H, float4* __restrict__ Hp,
+                                    const float* __restrict__ h0, const float* __restrict__ done, int64_t nx8, int64_t ng8,
+                                    int64_t nh8, int T, int64_t rc, int64_t ld_state, int64_t r0) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto cvt = [](const uint4 v, float4& a, float4& b) {
+    a.x = __uint_as_float(v.x << 16); a.y = __uint_as_float(v.x & 0xffff0000u);
+    a.z = __uint_as_float(v.y << 16); a.w = __uint_as_float(v.y & 0xffff0000u);
+    b.x = __uint_as_float(v.z << 16); b.y = __uint_as_float(v.z & 0xffff0000u);
+    b.z = __uint_as_float(v.w << 16); b.w = __uint_as_float(v.w & 0xffff0000u);
+  };
+  for (int64_t i = i0; i < nx8; i += stride) { float4 a, b; cvt(sx[i], a, b); X[2 * i] = a; X[2 * i + 1] = b; }
+  for (int64_t i = i0; i < ng8; i += stride) { float4 a, b; cvt(sg[i], a, b); ZG[2 * i] = a; ZG[2 * i + 1] = b; }
+  for (int64_t i = i0; i < nh8; i += stride) {
+    float4 a, b;
+    cvt(sc[i], a, b); Cc[2 * i] = a; Cc[2 * i + 1] = b;
+    cvt(shh[i], a, b); H[2 * i] = a; H[2 * i + 1] = b;
+    // element index -> (u, t, r, j8): 8 hidden per item, 8 items per row
+    const int64_t row = i >> 3; const int j8 = (int)(i & 7);
+    const int64_t r = row % rc; const int64_t ut = row / rc; const int t = (int)(ut % T); const int64_t u = ut / T;
+    const float keep = 1.0f - done[t];
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+    if (keep != 0.f) {
+      if (t > 0) { cvt(shh[i - rc * 8], pa, pb); }
+      else {
+        const float4* hp = reinterpret_cast<const float4*>(h0 + ((u * ld_state + r0 + r) * H64 + j8 * 8));
+        pa = hp[0]; pb = hp[1];
+      }
+    }
+    Hp[2 * i] = pa; Hp[2 * i + 1] = pb;
   }
 }
 
@@ -759,6 +801,19 @@ extern "C" int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, con
   if (ng > 24) ng = 24;
   dim3 grid((unsigned)ng, 2 * h->d.A);
   fc_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, obs, X, dX, M, rows_per_t, stride_t, grads);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_unpack_store(tscl_handle* h, const void* st_x, const void* st_g, const void* st_c, const void* st_h,
+                                 float* X, float* ZG, float* Cc, float* H, float* Hp, const float* h0, const float* done,
+                                 int32_t T, int64_t rc, int64_t ld_state, int64_t r0, void* stream) {
+  if (!h || !st_x || T <= 0 || rc <= 0) return tsc_set_error("tscl_unpack_store: bad argument");
+  LCK(cudaSetDevice(h->device));
+  const int64_t rows = (int64_t)2 * h->d.A * T * rc;
+  unpack_store_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)st_x, (const uint4*)st_g, (const uint4*)st_c, (const uint4*)st_h, (float4*)X, (float4*)ZG, (float4*)Cc,
+      (float4*)H, (float4*)Hp, h0, done, rows * h->d.dx / 8, rows * G4 / 8, rows * H64 / 8, T, rc, ld_state, r0);
   LCK(cudaGetLastError());
   return 0;
 }

@@ -101,6 +101,12 @@ int tscl_lstm_seq_bwd(tscl_handle* h, const float* params, float* ZG, const floa
 int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* dX, int64_t M,
                 int64_t rows_per_t, int64_t stride_t, float* grads, void* stream);
 
+/* One replica chunk of the bf16 activation store ([2A][T][rc][w] contiguous) -> fp32 work buffers X, ZG (gates),
+ * C, H and Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0[:, r0 + r]). */
+int tscl_unpack_store(tscl_handle* h, const void* st_x, const void* st_g, const void* st_c, const void* st_h, float* X,
+                      float* ZG, float* C, float* H, float* Hp, const float* h0, const float* done, int32_t T,
+                      int64_t rc, int64_t ld_state, int64_t r0, void* stream);
+
 /* Per-agent clip_by_global_norm(max_norm) + RMSProp step (TF1 semantics).  agent_of [n_params] u8.
  * norms [A] receives the pre-clip global norms. */
 int tscl_clip_rmsprop(tscl_handle* h, float* params, float* grads, float* ms, const uint8_t* agent_of,

@@ -95,6 +95,8 @@ class BatchedA2C:
         self.tc_v2 = self.use_tc and (L.dx % 32 == 0)          # fc front end on the tensor cores too
         self.Wp = torch.zeros(U, ((L.dx + L.h) // 8) * 4 * L.h * 8 + 8 * L.dx * 8, dtype=torch.bfloat16,
                               device=self.dev)
+        self.Wt = torch.zeros(U, 32, L.h, 8, dtype=torch.bfloat16, device=self.dev)    # Wh^T image for the BPTT MMA
+        self.bwd_tc = self.use_tc
         self.pack_weights()
         # bf16 activation store of the rollout's own forward pass (written by the v2 kernel): the update then
         # back-propagates through it instead of recomputing fc + gate GEMM + LSTM forward.
@@ -128,7 +130,8 @@ class BatchedA2C:
     def pack_weights(self):
         if self.use_tc:
             _lib.check(_lib.lib().tscl_pack_weights(self._h, _p(self.P), _p(self.Wp), self._st()))
-            self.kernel_launches += 1
+            _lib.check(_lib.lib().tscl_pack_wht(self._h, _p(self.P), _p(self.Wt), self._st()))
+            self.kernel_launches += 3
 
     def _mm(self):
         # cuBLAS fp32 (or TF32 when allowed) for the plain batched GEMMs
@@ -266,8 +269,12 @@ class BatchedA2C:
             # head weight / bias gradients (plain batched GEMM + column sums)
             self.gv["wo"].baddbmm_(H.transpose(1, 2), dlog)
             self.gv["bo"].add_(dlog.sum(dim=1))
-            _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
-                                             C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
+            if self.bwd_tc:
+                _lib.check(lib.tscl_lstm_seq_bwd_tc(self._h, _p(self.Wt), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
+                                                    C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
+            else:
+                _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
+                                                 C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
             dZ = ZG
             self.gv["wx"].baddbmm_(X.transpose(1, 2), dZ)
             self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)

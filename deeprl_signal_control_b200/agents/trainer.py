@@ -86,8 +86,15 @@ class BatchedTrainer:
         sim, m = self.sim, self.model
         t = m.t
         pi, val, act = m.forward(m.obs_slot(t), self.done)
-        act_h = act.cpu().numpy()
-        fp_h = pi.cpu().numpy() if self.agent == 'ma2c' else None
+        if not hasattr(self, '_pin_act'):       # page-locked staging for the D2H of actions / fingerprints
+            self._pin_act = torch.zeros_like(act, device='cpu').pin_memory()
+            self._pin_pi = torch.zeros_like(pi, device='cpu').pin_memory()
+        self._pin_act.copy_(act, non_blocking=True)
+        if self.agent == 'ma2c':
+            self._pin_pi.copy_(pi, non_blocking=True)
+        torch.cuda.current_stream(sim.device).synchronize()
+        act_h = self._pin_act.numpy()
+        fp_h = self._pin_pi.numpy() if self.agent == 'ma2c' else None
         obs_h, rew_h, grew_h, _ = sim.step_host(act_h, fp_h)
         m.obs_hist[t + 1].copy_(torch.from_numpy(obs_h), non_blocking=True)
         reward = torch.from_numpy(rew_h).to(sim.device, non_blocking=True)

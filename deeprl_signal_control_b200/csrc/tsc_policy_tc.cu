@@ -798,3 +798,206 @@ extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const vo
   PCK(cudaGetLastError());
   return 0;
 }
+
+// ===================================================================================================
+// BPTT through the LSTM on the tensor cores (replaces lstm_seq_bwd_kernel of tsc_learn.cu).
+// One CTA walks (unit, 128-replica tile) items; for t = T-1 .. 0:
+//   thread = (replica row, 32 hidden units): cell backward from gate activations, c_t, c_{t-1} and the
+//   incoming dh / dc  ->  dz (4 x 32) written fp32 in place over the gates (operand of the weight-gradient
+//   GEMMs) and as bf16 into the A tile [128 x 256];  tcgen05.mma  D[128 x 64] = dz . Wh^T  (K = 256, N = 64)
+//   -> TMEM -> the thread's 32 columns = dh_{t-1} carry.  dc / dh carries stay in registers.
+#define BW_KC 32            // 256 / 8 K-chunks
+__global__ void pack_wht_kernel(const DDimsTC d, const float* __restrict__ P, __nv_bfloat16* __restrict__ Wt) {
+  const int u = blockIdx.y;
+  const float* Wh = P + d.off_wh + (int64_t)u * TC_H * TC_N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BW_KC * TC_H; i += gridDim.x * blockDim.x) {
+    const int kc = i / TC_H, n = i - kc * TC_H;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(Wh[(int64_t)n * TC_N + kc * 8 + e]);
+    *reinterpret_cast<uint4*>(Wt + (((int64_t)u * BW_KC + kc) * TC_H + n) * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+struct BwdTC {
+  const __nv_bfloat16* Wt;   // [2A][32][64][8]
+  float* ZG;                 // [2A][T*Rc][256] gates in, dZ out
+  const float* C;            // [2A][T*Rc][64]
+  const float* dH;           // [2A][T*Rc][64]
+  const float* c0;           // [2A][ld_state][64]
+  const float* done;         // [T]
+  int T;
+  int64_t Rc, ld_state, r0;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned char* sB = tc_smem;                       // 32 * 1024  : Wh^T image
+  unsigned char* sA = sB + BW_KC * 1024;             // 32 * 2048  : dz tile
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sA + BW_KC * 2048);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
+  const uint32_t bar = smem_u32(sBar);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_H >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+  const int64_t n_tiles = (a.Rc + TC_M - 1) / TC_M;
+  const int64_t n_items = n_tiles * 2 * d.A;
+  int cur_u = -1;
+  uint32_t parity = 0;
+  const int q = warp & 3, half = warp >> 2;
+  const int row = q * 32 + lane;
+  for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int u = (int)(it / n_tiles);
+    const int64_t r = (it - (int64_t)u * n_tiles) * TC_M + row;
+    const bool valid = r < a.Rc;
+    __syncthreads();
+    if (u != cur_u) {
+      cur_u = u;
+      const uint4* src = reinterpret_cast<const uint4*>(a.Wt + (int64_t)u * BW_KC * TC_H * 8);
+      uint4* dst = reinterpret_cast<uint4*>(sB);
+      for (int i = tid; i < BW_KC * TC_H; i += TC_THREADS) dst[i] = src[i];
+    }
+    float dc[32], dhc[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) { dc[e] = 0.f; dhc[e] = 0.f; }
+    for (int t = a.T - 1; t >= 0; --t) {
+      const float keep = 1.0f - a.done[t];
+      const int64_t m = ((int64_t)u * a.T + t) * a.Rc + (valid ? r : 0);
+#pragma unroll
+      for (int jb = 0; jb < 2; ++jb) {
+        const int jo = half * 32 + jb * 16;
+        float gi[16], gf[16], go[16], gu[16], ct[16], cp[16], dh[16];
+        if (valid) {
+          const float4* z = reinterpret_cast<const float4*>(a.ZG + m * TC_N + jo);
+          const float4* cc = reinterpret_cast<const float4*>(a.C + m * TC_H + jo);
+          const float4* pp = t > 0 ? reinterpret_cast<const float4*>(a.C + (m - a.Rc) * TC_H + jo)
+                                   : reinterpret_cast<const float4*>(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo);
+          const float4* hh = reinterpret_cast<const float4*>(a.dH + m * TC_H + jo);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 x0 = z[e4], x1 = z[16 + e4], x2 = z[32 + e4], x3 = z[48 + e4], x4 = cc[e4], x5 = pp[e4], x6 = hh[e4];
+            gi[4 * e4] = x0.x; gi[4 * e4 + 1] = x0.y; gi[4 * e4 + 2] = x0.z; gi[4 * e4 + 3] = x0.w;
+            gf[4 * e4] = x1.x; gf[4 * e4 + 1] = x1.y; gf[4 * e4 + 2] = x1.z; gf[4 * e4 + 3] = x1.w;
+            go[4 * e4] = x2.x; go[4 * e4 + 1] = x2.y; go[4 * e4 + 2] = x2.z; go[4 * e4 + 3] = x2.w;
+            gu[4 * e4] = x3.x; gu[4 * e4 + 1] = x3.y; gu[4 * e4 + 2] = x3.z; gu[4 * e4 + 3] = x3.w;
+            ct[4 * e4] = x4.x; ct[4 * e4 + 1] = x4.y; ct[4 * e4 + 2] = x4.z; ct[4 * e4 + 3] = x4.w;
+            cp[4 * e4] = x5.x * keep; cp[4 * e4 + 1] = x5.y * keep; cp[4 * e4 + 2] = x5.z * keep; cp[4 * e4 + 3] = x5.w * keep;
+            dh[4 * e4] = x6.x; dh[4 * e4 + 1] = x6.y; dh[4 * e4 + 2] = x6.z; dh[4 * e4 + 3] = x6.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { gi[e] = gf[e] = go[e] = gu[e] = ct[e] = cp[e] = dh[e] = 0.f; }
+        }
+        float dzi[16], dzf[16], dzo[16], dzu[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int k = jb * 16 + e;
+          const float dht = dh[e] + dhc[k];
+          const float tc = tanh_fast(ct[e]);
+          const float dcc = dc[k] + dht * go[e] * (1.0f - tc * tc);
+          dzi[e] = dcc * gu[e] * gi[e] * (1.0f - gi[e]);
+          dzf[e] = dcc * cp[e] * gf[e] * (1.0f - gf[e]);
+          dzo[e] = dht * tc * go[e] * (1.0f - go[e]);
+          dzu[e] = dcc * gi[e] * (1.0f - gu[e] * gu[e]);
+          dc[k] = dcc * gf[e] * keep;
+        }
+        if (valid) {
+          float4* z = reinterpret_cast<float4*>(a.ZG + m * TC_N + jo);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            z[e4] = make_float4(dzi[4 * e4], dzi[4 * e4 + 1], dzi[4 * e4 + 2], dzi[4 * e4 + 3]);
+            z[16 + e4] = make_float4(dzf[4 * e4], dzf[4 * e4 + 1], dzf[4 * e4 + 2], dzf[4 * e4 + 3]);
+            z[32 + e4] = make_float4(dzo[4 * e4], dzo[4 * e4 + 1], dzo[4 * e4 + 2], dzo[4 * e4 + 3]);
+            z[48 + e4] = make_float4(dzu[4 * e4], dzu[4 * e4 + 1], dzu[4 * e4 + 2], dzu[4 * e4 + 3]);
+          }
+        }
+        // bf16 copies into the A tile: column g*64 + jo + e  -> chunk (g*64 + jo)/8 (+1), row `row`
+        __align__(16) __nv_bfloat16 v[16];
+        const float* srcs[4] = {dzi, dzf, dzo, dzu};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __float2bfloat16_rn(srcs[g][e]);
+          const int kc = (g * 64 + jo) >> 3;
+          *reinterpret_cast<uint4*>(sA + (size_t)kc * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+          *reinterpret_cast<uint4*>(sA + (size_t)(kc + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
+        }
+      }
+      if (keep != 0.f && t > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+          if (lane == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int ks = 0; ks < 16; ++ks)
+              umma_bf16(tmem, make_desc(aA + ks * 2 * 2048, 2048, 128), make_desc(aB + ks * 2 * 1024, 1024, 128), idesc,
+                        ks > 0 ? 1u : 0u);
+            umma_commit(bar);
+          }
+          __syncwarp();
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float dhp[32];
+        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+        tmem_ld16(tb, dhp); tmem_ld16(tb + 16, dhp + 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 32; ++e) dhc[e] = dhp[e] * keep;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) dhc[e] = 0.f;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+}
+
+extern "C" int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16, void* stream) {
+  if (!h || !params || !wt_bf16) return tsc_set_error("tscl_pack_wht: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  pack_wht_kernel<<<dim3(2, 2 * d.A), 256, 0, (cudaStream_t)stream>>>(d, params, (__nv_bfloat16*)wt_bf16);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH,
+                                    const float* c0, const float* done, int32_t T, int64_t Rc, int64_t ld_state,
+                                    int64_t r0, void* stream) {
+  if (!h || !wt_bf16 || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_bwd_tc: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  const size_t smem = BW_KC * 1024 + BW_KC * 2048 + 16;
+  static int attr_dev = -1;
+  if (attr_dev != tscl_device_of(h)) {
+    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = tscl_device_of(h);
+  }
+  int n_sm = 0;
+  PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
+  const int64_t n_items = ((Rc + TC_M - 1) / TC_M) * 2 * d.A;
+  const int grid = (int)(n_items < 2 * n_sm ? n_items : 2 * n_sm);   // 96 KB smem, <=255 regs: 1-2 CTAs per SM
+  BwdTC a;
+  a.Wt = (const __nv_bfloat16*)wt_bf16; a.ZG = ZG; a.C = C; a.dH = dH; a.c0 = c0; a.done = done; a.T = T; a.Rc = Rc;
+  a.ld_state = ld_state; a.r0 = r0;
+  lstm_bwd_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  PCK(cudaGetLastError());
+  return 0;
+}

@@ -93,9 +93,12 @@ class BatchedSim:
         n = self.net
         action = np.ascontiguousarray(action, np.int32).reshape(self.R, n.n_nodes)
         fp = None if fp is None else np.ascontiguousarray(fp, np.float32)
-        if not hasattr(self, "_h_out"):
-            self._h_out = (np.zeros((self.R, n.n_obs), np.float32), np.zeros((self.R, n.n_nodes), np.float32),
-                           np.zeros(self.R, np.float32), np.zeros(self.R, np.uint8))
+        if not hasattr(self, "_h_out"):     # page-locked output buffers: D2H copies run at full PCIe/C2C speed
+            self._h_out_t = (torch.zeros(self.R, n.n_obs, dtype=torch.float32).pin_memory(),
+                             torch.zeros(self.R, n.n_nodes, dtype=torch.float32).pin_memory(),
+                             torch.zeros(self.R, dtype=torch.float32).pin_memory(),
+                             torch.zeros(self.R, dtype=torch.uint8).pin_memory())
+            self._h_out = tuple(t.numpy() for t in self._h_out_t)
         obs, reward, greward, done = self._h_out
         _lib.check(_lib.lib().tsc_step_host(self._h, _np(action, C.c_int32), _np(fp, C.c_float),
                                             _np(obs, C.c_float), _np(reward, C.c_float),

@@ -101,6 +101,13 @@ int tscl_lstm_seq_bwd(tscl_handle* h, const float* params, float* ZG, const floa
 int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* dX, int64_t M,
                 int64_t rows_per_t, int64_t stride_t, float* grads, void* stream);
 
+/* BPTT on the tensor cores (tcgen05): same contract as tscl_lstm_seq_bwd, with the recurrent product dz.Wh^T as
+ * a bf16 MMA (M=128, N=64, K=256) per step; wt_bf16 [2A][32][64][8] comes from tscl_pack_wht (refresh after
+ * every optimizer step). */
+int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16, void* stream);
+int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH, const float* c0,
+                         const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0, void* stream);
+
 /* One replica chunk of the bf16 activation store ([2A][T][rc][w] contiguous) -> fp32 work buffers X, ZG (gates),
  * C, H and Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0[:, r0 + r]). */
 int tscl_unpack_store(tscl_handle* h, const void* st_x, const void* st_g, const void* st_c, const void* st_h, float* X,

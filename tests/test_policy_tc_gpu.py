@@ -156,3 +156,36 @@ def test_update_from_stored_activations_matches_recompute():
     va, vb = a.G.flatten().double(), b.G.flatten().double()
     assert float(torch.dot(va, vb) / (va.norm() * vb.norm())) > 0.999
     assert float((va - vb).norm() / vb.norm()) < 0.03
+
+
+def test_bptt_tensor_core_kernel_matches_fp32_kernel():
+    """tscl_lstm_seq_bwd_tc (tcgen05 dz.Wh^T, bf16 operands) vs tscl_lstm_seq_bwd (fp32 SIMT) on the same inputs."""
+    from deeprl_signal_control_b200 import _lib
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C, _p
+    lay = _layout(64)
+    Rc, T, R = 150, 7, 300
+    m = BatchedA2C(lay, R, n_step=T, seed=2)
+    U = lay.U
+    g = torch.Generator(device="cuda").manual_seed(0)
+    gates = torch.rand(U, T * Rc, 256, device="cuda", generator=g)
+    gates[..., 192:] = gates[..., 192:] * 2 - 1                      # u gate in (-1, 1)
+    Cc = torch.randn(U, T * Rc, 64, device="cuda", generator=g) * 0.7
+    dH = torch.randn(U, T * Rc, 64, device="cuda", generator=g) * 1e-3
+    m.c_bw.copy_(torch.randn(U, R, 64, device="cuda", generator=g) * 0.5)
+    done = torch.tensor([0, 0, 0, 1, 0, 0, 0], dtype=torch.float32, device="cuda")
+    r0 = 100
+    z1, z2 = gates.clone(), gates.clone()
+    lib = _lib.lib()
+    _lib.check(lib.tscl_lstm_seq_bwd(m._h, _p(m.P), _p(z1), _p(Cc), _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
+                                     C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), m._st()))
+    _lib.check(lib.tscl_lstm_seq_bwd_tc(m._h, _p(m.Wt), _p(z2), _p(Cc), _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
+                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), m._st()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(z2).all()
+    scale = float(z1.abs().max())
+    err = float((z1 - z2).abs().max()) / scale
+    rel = float((z1 - z2).norm() / z1.norm())
+    assert err < 3e-2 and rel < 1e-2, (err, rel)
+    # the last time step has no recurrent carry: identical up to tanh.approx
+    last = slice((T - 1) * Rc, T * Rc)
+    assert float((z1[:, last] - z2[:, last]).abs().max()) / scale < 2e-3

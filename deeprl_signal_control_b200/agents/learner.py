@@ -251,8 +251,10 @@ class BatchedA2C:
             if use_store:
                 # activations of the rollout's forward pass (bf16 store -> fp32 chunk buffers, strided copy)
                 ci = r0 // self.chunk
+                direct = self.bwd_tc        # the tensor-core BPTT kernel reads gates / c from the store itself
                 _lib.check(lib.tscl_unpack_store(self._h, _p(self.st_x[ci]), _p(self.st_g[ci]), _p(self.st_c[ci]),
-                                                 _p(self.st_h[ci]), _p(X), _p(ZG), _p(Cc), _p(H), _p(Hp), _p(self.h_bw),
+                                                 _p(self.st_h[ci]), _p(X), None if direct else _p(ZG),
+                                                 None if direct else _p(Cc), _p(H), _p(Hp), _p(self.h_bw),
                                                  _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0),
                                                  st()))
             else:
@@ -270,8 +272,9 @@ class BatchedA2C:
             self.gv["wo"].baddbmm_(H.transpose(1, 2), dlog)
             self.gv["bo"].add_(dlog.sum(dim=1))
             if self.bwd_tc:
+                gb = (_p(self.st_g[r0 // self.chunk]), _p(self.st_c[r0 // self.chunk])) if use_store else (None, None)
                 _lib.check(lib.tscl_lstm_seq_bwd_tc(self._h, _p(self.Wt), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
-                                                    C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
+                                                    C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), *gb, st()))
             else:
                 _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
                                                  C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))

@@ -602,10 +602,11 @@ __global__ void unpack_store_kernel(const uint4* __restrict__ sx, const uint4* _
     b.z = __uint_as_float(v.w << 16); b.w = __uint_as_float(v.w & 0xffff0000u);
   };
   for (int64_t i = i0; i < nx8; i += stride) { float4 a, b; cvt(sx[i], a, b); X[2 * i] = a; X[2 * i + 1] = b; }
-  for (int64_t i = i0; i < ng8; i += stride) { float4 a, b; cvt(sg[i], a, b); ZG[2 * i] = a; ZG[2 * i + 1] = b; }
+  if (ZG)
+    for (int64_t i = i0; i < ng8; i += stride) { float4 a, b; cvt(sg[i], a, b); ZG[2 * i] = a; ZG[2 * i + 1] = b; }
   for (int64_t i = i0; i < nh8; i += stride) {
     float4 a, b;
-    cvt(sc[i], a, b); Cc[2 * i] = a; Cc[2 * i + 1] = b;
+    if (Cc) { cvt(sc[i], a, b); Cc[2 * i] = a; Cc[2 * i + 1] = b; }
     cvt(shh[i], a, b); H[2 * i] = a; H[2 * i + 1] = b;
     // element index -> (u, t, r, j8): 8 hidden per item, 8 items per row
     const int64_t row = i >> 3; const int j8 = (int)(i & 7);

@@ -828,6 +828,8 @@ struct BwdTC {
   const float* done;         // [T]
   int T;
   int64_t Rc, ld_state, r0;
+  const __nv_bfloat16* Gb;   // optional: gate activations / c_t straight from the bf16 activation store
+  const __nv_bfloat16* Cb;   //           ([2A][T*Rc][256] / [..][64]); when set, ZG is write-only and C is unused
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -879,7 +881,28 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
       for (int jb = 0; jb < 2; ++jb) {
         const int jo = half * 32 + jb * 16;
         float gi[16], gf[16], go[16], gu[16], ct[16], cp[16], dh[16];
-        if (valid) {
+        if (valid && a.Gb) {
+          auto ld16 = [](const __nv_bfloat16* p, float* o) {
+            const uint4 v0 = reinterpret_cast<const uint4*>(p)[0], v1 = reinterpret_cast<const uint4*>(p)[1];
+            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+          };
+          const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
+          ld16(zb, gi); ld16(zb + 64, gf); ld16(zb + 128, go); ld16(zb + 192, gu);
+          ld16(a.Cb + m * TC_H + jo, ct);
+          if (t > 0) ld16(a.Cb + (m - a.Rc) * TC_H + jo, cp);
+          else {
+            const float4* pp = reinterpret_cast<const float4*>(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo);
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) { const float4 x = pp[e4]; cp[4 * e4] = x.x; cp[4 * e4 + 1] = x.y; cp[4 * e4 + 2] = x.z; cp[4 * e4 + 3] = x.w; }
+          }
+          const float4* hh = reinterpret_cast<const float4*>(a.dH + m * TC_H + jo);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) { const float4 x = hh[e4]; dh[4 * e4] = x.x; dh[4 * e4 + 1] = x.y; dh[4 * e4 + 2] = x.z; dh[4 * e4 + 3] = x.w; }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cp[e] *= keep;
+        } else if (valid) {
           const float4* z = reinterpret_cast<const float4*>(a.ZG + m * TC_N + jo);
           const float4* cc = reinterpret_cast<const float4*>(a.C + m * TC_H + jo);
           const float4* pp = t > 0 ? reinterpret_cast<const float4*>(a.C + (m - a.Rc) * TC_H + jo)
@@ -980,7 +1003,7 @@ extern "C" int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16,
 
 extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH,
                                     const float* c0, const float* done, int32_t T, int64_t Rc, int64_t ld_state,
-                                    int64_t r0, void* stream) {
+                                    int64_t r0, const void* gates_bf16, const void* c_bf16, void* stream) {
   if (!h || !wt_bf16 || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_bwd_tc: bad argument");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
@@ -996,7 +1019,7 @@ extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* 
   const int grid = (int)(n_items < 2 * n_sm ? n_items : 2 * n_sm);   // 96 KB smem, <=255 regs: 1-2 CTAs per SM
   BwdTC a;
   a.Wt = (const __nv_bfloat16*)wt_bf16; a.ZG = ZG; a.C = C; a.dH = dH; a.c0 = c0; a.done = done; a.T = T; a.Rc = Rc;
-  a.ld_state = ld_state; a.r0 = r0;
+  a.ld_state = ld_state; a.r0 = r0; a.Gb = (const __nv_bfloat16*)gates_bf16; a.Cb = (const __nv_bfloat16*)c_bf16;
   lstm_bwd_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;

@@ -106,10 +106,14 @@ int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* d
  * every optimizer step). */
 int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16, void* stream);
 int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH, const float* c0,
-                         const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0, void* stream);
+                         const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
+                         const void* gates_bf16, const void* c_bf16, void* stream);
+/* gates_bf16 / c_bf16 (both or neither): read gate activations and c_t straight from one chunk of the bf16
+ * activation store instead of ZG / C (ZG is then write-only: it receives dZ). */
 
 /* One replica chunk of the bf16 activation store ([2A][T][rc][w] contiguous) -> fp32 work buffers X, ZG (gates),
- * C, H and Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0[:, r0 + r]). */
+ * C, H and Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0[:, r0 + r]).  ZG and C may be NULL (skipped) when the
+ * BPTT kernel reads them from the store itself. */
 int tscl_unpack_store(tscl_handle* h, const void* st_x, const void* st_g, const void* st_c, const void* st_h, float* X,
                       float* ZG, float* C, float* H, float* Hp, const float* h0, const float* done, int32_t T,
                       int64_t rc, int64_t ld_state, int64_t r0, void* stream);

@@ -179,8 +179,14 @@ def test_bptt_tensor_core_kernel_matches_fp32_kernel():
     _lib.check(lib.tscl_lstm_seq_bwd(m._h, _p(m.P), _p(z1), _p(Cc), _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
                                      C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), m._st()))
     _lib.check(lib.tscl_lstm_seq_bwd_tc(m._h, _p(m.Wt), _p(z2), _p(Cc), _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
-                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), m._st()))
+                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), None, None, m._st()))
+    # same again with gates / c read from bf16 copies (the activation-store fast path)
+    z3 = torch.zeros_like(gates)
+    gb, cb = gates.to(torch.bfloat16).contiguous(), Cc.to(torch.bfloat16).contiguous()
+    _lib.check(lib.tscl_lstm_seq_bwd_tc(m._h, _p(m.Wt), _p(z3), None, _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
+                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(gb), _p(cb), m._st()))
     torch.cuda.synchronize()
+    assert float((z3 - z1).norm() / z1.norm()) < 2e-2
     assert torch.isfinite(z2).all()
     scale = float(z1.abs().max())
     err = float((z1 - z2).abs().max()) / scale

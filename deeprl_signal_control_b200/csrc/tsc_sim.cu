@@ -4,7 +4,7 @@
 // (reference envs/env.py:566-631: yellow phase, 2 x 1 s, green phase, 3 x 1 s, detector reads,
 // reward, observation) with the replica's entire vehicle state resident in shared memory:
 //
-//   HBM  (compact, lane-major)  --128-bit coalesced loads-->  per-lane FIFO rings in smem
+//   HBM  (compact, lane-major, SoA 12 B/vehicle)  --coalesced loads-->  per-lane FIFO rings in smem
 //   5 x { A1 lane summaries + scan | A2 junction limits | B per-vehicle Krauss update |
 //         C junction transfers | D pops | E insertion }
 //   detector scan -> reward -> shaping -> observation gather -> compact store back to HBM
@@ -29,7 +29,7 @@
 #define TSC_THREADS 256
 #endif
 #ifndef TSC_MIN_BLOCKS
-#define TSC_MIN_BLOCKS 3   /* 3 CTAs/SM is the shared-memory limit for the 5x5 grid (70.9 KB each) */
+#define TSC_MIN_BLOCKS 4   /* 4 CTAs/SM is the shared-memory limit for the 5x5 grid (54.8 KB each) */
 #endif
 #define INF_SPEED 1.0e9f
 #define F_CROSS 1
@@ -69,7 +69,7 @@ struct StepArgs {
   DevNet net;
   tsc_cfg cfg;
   // state (HBM)
-  uint4* veh;         // [R][n_slots]  compact lane-major records
+  uint32_t* veh;      // [R][3][n_slots]  compact lane-major records, SoA: pos f32 | speed f32 | meta0
   uint8_t* lane_cnt;  // [R][lpad]
   int32_t* ctl;       // [R][ctl_words]
   int32_t* meas;      // [R][3*n_det + n_nodes]  parity taps
@@ -154,6 +154,14 @@ __device__ __forceinline__ float clipf(float x, float hi) {
   return x;
 }
 
+// Vehicle record = 12 bytes {pos f32, speed f32, meta0}; stored SoA both in HBM and in shared memory.
+struct Ring { float* x; float* v; uint32_t* m; };
+__device__ __forceinline__ uint3 ld3(const Ring& r, int i) {
+  return make_uint3(__float_as_uint(r.x[i]), __float_as_uint(r.v[i]), r.m[i]);
+}
+__device__ __forceinline__ void st3(const Ring& r, int i, const uint3 e) {
+  r.x[i] = __uint_as_float(e.x); r.v[i] = __uint_as_float(e.y); r.m[i] = e.z;
+}
 #define M0_WAIT(m) ((m) & 1023u)
 #define M0_HOP(m) (((m) >> 10) & 63u)
 #define M0_ROUTE(m) (((m) >> 16) & 255u)
@@ -269,8 +277,11 @@ tsc_step_kernel(const StepArgs A) {
   const int L = n.n_lanes, N = n.n_nodes;
 
   // ---- shared-memory carve-up ----
-  uint4* ring = reinterpret_cast<uint4*>(smem_raw);
-  int32_t* s_cnt = reinterpret_cast<int32_t*>(ring + n.n_slots);
+  Ring ring;
+  ring.x = reinterpret_cast<float*>(smem_raw);
+  ring.v = ring.x + n.n_slots;
+  ring.m = reinterpret_cast<uint32_t*>(ring.v + n.n_slots);
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(ring.m + n.n_slots);
   int32_t* s_head = s_cnt + L;
   int32_t* s_pre = s_head + L;              // L + 1
   float* s_headlim = reinterpret_cast<float*>(s_pre + L + 1);
@@ -294,7 +305,9 @@ tsc_step_kernel(const StepArgs A) {
   // ---- load replica state -------------------------------------------------------------------
   const uint8_t* g_cnt = A.lane_cnt + (size_t)rep * n.lpad;
   int32_t* g_ctl = A.ctl + (size_t)rep * A.ctl_words;
-  uint4* g_veh = A.veh + (size_t)rep * n.n_slots;
+  uint32_t* g_x = A.veh + (size_t)rep * 3 * n.n_slots;
+  uint32_t* g_v = g_x + n.n_slots;
+  uint32_t* g_m = g_v + n.n_slots;
   for (int l = tid; l < L; l += TSC_THREADS) { s_cnt[l] = g_cnt[l]; s_head[l] = 0; }
   if (tid < CTL_FIXED) s_misc[tid] = g_ctl[tid];
   for (int i = tid; i < N; i += TSC_THREADS) {
@@ -310,7 +323,7 @@ tsc_step_kernel(const StepArgs A) {
     for (int k = tid; k < V; k += TSC_THREADS) {
       int lane = find_lane(s_pre, L, k);
       int rank = k - s_pre[lane];
-      ring[__ldg(&n.lane[lane].slot0) + rank] = g_veh[k];
+      st3(ring, __ldg(&n.lane[lane].slot0) + rank, make_uint3(g_x[k], g_v[k], g_m[k]));
     }
   }
   for (int i = tid; i < N; i += TSC_THREADS)
@@ -334,7 +347,7 @@ tsc_step_kernel(const StepArgs A) {
       s_hflag[l] = 0; s_acc[l] = 0; s_cntadd[l] = 0;
       if (s_cnt[l] > 0) {
         const LaneC lc = n.lane[l];
-        const uint4 h = ring[lc.slot0 + s_head[l]];
+        const uint3 h = ld3(ring, lc.slot0 + s_head[l]);
         int link = __ldg(&n.route_link[M0_ROUTE(h.z) * n.max_hops + M0_HOP(h.z)]);
         if (link >= 0) {
           const LinkC* lk = &n.link[link];
@@ -355,7 +368,7 @@ tsc_step_kernel(const StepArgs A) {
       float lim = INF_SPEED;
       if (s_cnt[l] > 0) {
         const LaneC lc = n.lane[l];
-        const uint4 h = ring[lc.slot0 + s_head[l]];
+        const uint3 h = ld3(ring, lc.slot0 + s_head[l]);
         const uint32_t route = M0_ROUTE(h.z), hop = M0_HOP(h.z);
         const int link = __ldg(&n.route_link[route * n.max_hops + hop]);
         if (link >= 0) {
@@ -385,7 +398,7 @@ tsc_step_kernel(const StepArgs A) {
               const LaneC nlc = n.lane[nl];
               int idx = s_head[nl] + nc - 1;
               if (idx >= nlc.cap) idx -= nlc.cap;
-              const uint4 t = ring[nlc.slot0 + idx];
+              const uint3 t = ld3(ring, nlc.slot0 + idx);
               float gap = d + (__uint_as_float(t.x) - c.veh_len);
               gap = gap - c.min_gap;
               float fs = follow_speed(gap, __uint_as_float(t.y), c.decel, c.tau);
@@ -406,7 +419,7 @@ tsc_step_kernel(const StepArgs A) {
         const int k = it * TSC_THREADS + tid;
         const bool act = k < V;
         int slot = 0, lane = 0, rank = 0;
-        uint4 me = make_uint4(0, 0, 0, 0);
+        uint3 me = make_uint3(0, 0, 0);
         uint8_t f = 0;
         if (act) {
           lane = find_lane(s_pre, L, k);
@@ -415,7 +428,7 @@ tsc_step_kernel(const StepArgs A) {
           int idx = s_head[lane] + rank;
           if (idx >= lc.cap) idx -= lc.cap;
           slot = lc.slot0 + idx;
-          me = ring[slot];
+          me = ld3(ring, slot);
           const float x = __uint_as_float(me.x), v = __uint_as_float(me.y);
           const float sf = 0.5f + (float)M0_SFQ(me.z) * (1.0f / 256.0f);
           const float vmax = lc.vmax * sf;
@@ -427,7 +440,7 @@ tsc_step_kernel(const StepArgs A) {
           } else {
             int lidx = idx - 1;
             if (lidx < 0) lidx += lc.cap;
-            const float2 ld = *reinterpret_cast<const float2*>(&ring[lc.slot0 + lidx]);
+            const float2 ld = make_float2(ring.x[lc.slot0 + lidx], ring.v[lc.slot0 + lidx]);
             float gap = ld.x - c.veh_len;
             gap = gap - x;
             gap = gap - c.min_gap;
@@ -452,22 +465,19 @@ tsc_step_kernel(const StepArgs A) {
               if (vn < 0.0f) { vn = 0.0f; xn = x; }
             }
           }
-          uint32_t w = M0_WAIT(me.z), wt = (me.w >> 12) & 4095u, wc = me.w >> 24;
+          uint32_t w = M0_WAIT(me.z);
           if (vn < 0.1f) {
-            if (w == 0 && wc < 255u) wc++;
             if (w < 1023u) w++;
-            if (wt < 4095u) wt++;
           } else {
             w = 0;
           }
           me.x = __float_as_uint(xn);
           me.y = __float_as_uint(vn);
           me.z = (me.z & ~1023u) | w;
-          me.w = (me.w & 4095u) | (wt << 12) | (wc << 24);
         }
         __syncthreads();
         if (act) {
-          ring[slot] = me;
+          st3(ring, slot, me);
           if (rank == 0) s_hflag[lane] = f;
         }
       }
@@ -485,14 +495,14 @@ tsc_step_kernel(const StepArgs A) {
       if (have_tail) {
         int idx = s_head[t] + cur - 1;
         if (idx >= tc.cap) idx -= tc.cap;
-        tail_x = __uint_as_float(ring[tc.slot0 + idx].x);
+        tail_x = ring.x[tc.slot0 + idx];
       }
       for (int q = q0; q < q1; ++q) {
         const int link = __ldg(&n.lane_inl[q]);
         const int src = __ldg(&n.link[link].from);
         if (s_cnt[src] == 0 || s_hflag[src] != F_CROSS) continue;
         const LaneC sc2 = n.lane[src];
-        const uint4 h = ring[sc2.slot0 + s_head[src]];
+        const uint3 h = ld3(ring, sc2.slot0 + s_head[src]);
         const uint32_t route = M0_ROUTE(h.z), hop = M0_HOP(h.z);
         if (__ldg(&n.route_link[route * n.max_hops + hop]) != link) continue;
         if (__ldg(&n.route_lane[route * n.max_hops + hop + 1]) != t) continue;
@@ -506,10 +516,10 @@ tsc_step_kernel(const StepArgs A) {
         if (x < 0.0f) continue;
         int idx = s_head[t] + cur;
         if (idx >= tc.cap) idx -= tc.cap;
-        uint4 e = h;
+        uint3 e = h;
         e.x = __float_as_uint(x);
         e.z = (h.z & ~(63u << 10)) | ((hop + 1) << 10);
-        ring[tc.slot0 + idx] = e;
+        st3(ring, tc.slot0 + idx, e);
         cur++; tail_x = x; have_tail = true;
         s_acc[src] = 1;
       }
@@ -534,9 +544,8 @@ tsc_step_kernel(const StepArgs A) {
         else if (f == F_CROSS) {
           if (s_acc[l]) pop = true;
           else {
-            uint4* h = &ring[lc.slot0 + s_head[l]];
-            h->x = __float_as_uint(lc.len - 0.01f);
-            h->y = __float_as_uint(0.0f);
+            ring.x[lc.slot0 + s_head[l]] = lc.len - 0.01f;
+            ring.v[lc.slot0 + s_head[l]] = 0.0f;
           }
         }
         if (pop) {
@@ -561,7 +570,7 @@ tsc_step_kernel(const StepArgs A) {
             if (ok && cl > 0) {
               int idx = s_head[l] + cl - 1;
               if (idx >= lc.cap) idx -= lc.cap;
-              free_back = __uint_as_float(ring[lc.slot0 + idx].x) - c.veh_len;
+              free_back = ring.x[lc.slot0 + idx] - c.veh_len;
               free_back = free_back - c.min_gap;
             }
             if (ok && !(free_back < c.veh_len)) {
@@ -576,12 +585,11 @@ tsc_step_kernel(const StepArgs A) {
               if (sfq > 255) sfq = 255;
               int idx = s_head[l] + cl;
               if (idx >= lc.cap) idx -= lc.cap;
-              uint4 e;
+              uint3 e;
               e.x = __float_as_uint(pos);
               e.y = __float_as_uint(0.0f);
               e.z = ((uint32_t)__ldg(&n.src_route[q]) << 16) | ((uint32_t)sfq << 24);
-              e.w = t_abs & 4095u;
-              ring[lc.slot0 + idx] = e;
+              st3(ring, lc.slot0 + idx, e);
               cl++;
               b_new--;
               n_dep_add++;
@@ -605,7 +613,7 @@ tsc_step_kernel(const StepArgs A) {
     const int cl = s_cnt[l];
     int idx = s_head[l];
     for (int k = 0; k < cl; ++k) {
-      const uint4 v = ring[lc.slot0 + idx];
+      const uint3 v = ld3(ring, lc.slot0 + idx);
       const float x = __uint_as_float(v.x);
       if (c.det_len > 0.0f && !(x > lc.len - c.det_len)) break;
       veh++;
@@ -683,7 +691,8 @@ tsc_step_kernel(const StepArgs A) {
       const LaneC lc = n.lane[lane];
       int idx = s_head[lane] + rank;
       if (idx >= lc.cap) idx -= lc.cap;
-      g_veh[k] = ring[lc.slot0 + idx];
+      const uint3 e = ld3(ring, lc.slot0 + idx);
+      g_x[k] = e.x; g_v[k] = e.y; g_m[k] = e.z;
     }
   }
   uint8_t* g_cnt_w = A.lane_cnt + (size_t)rep * n.lpad;
@@ -716,7 +725,7 @@ __global__ void tsc_reset_kernel(uint8_t* lane_cnt, int32_t* ctl, int32_t* meas,
 // _measure_traffic_step (envs/env.py:409-437) for every replica: one CTA per replica over the compact state.
 // stats[r] = {n_live, n_departed_total, n_arrived_total, avg_wait, avg_speed, avg_queue, std_queue, backlog}
 // avg/std_queue: lane halting number (speed < 0.1 m/s, whole lane) over the detector lanes (envs/env.py:422-427).
-__global__ void tsc_stats_kernel(const DevNet n, const uint4* __restrict__ veh, const uint8_t* __restrict__ lane_cnt,
+__global__ void tsc_stats_kernel(const DevNet n, const uint32_t* __restrict__ veh, const uint8_t* __restrict__ lane_cnt,
                                  const int32_t* __restrict__ ctl, int ctl_words, float* __restrict__ stats) {
   extern __shared__ int32_t sh[];
   int32_t* s_pre = sh;                 // [L + 1]
@@ -735,10 +744,10 @@ __global__ void tsc_stats_kernel(const DevNet n, const uint4* __restrict__ veh, 
   const int V = s_pre[L];
   float w = 0.f, sp = 0.f;
   for (int k = tid; k < V; k += blockDim.x) {
-    const uint4 v = veh[(size_t)rep * n.n_slots + k];
-    w += (float)(v.z & 1023u);
-    sp += __uint_as_float(v.y);
-    if (__uint_as_float(v.y) < 0.1f) {
+    const float vy = __uint_as_float(veh[((size_t)rep * 3 + 1) * n.n_slots + k]);
+    w += (float)(veh[((size_t)rep * 3 + 2) * n.n_slots + k] & 1023u);
+    sp += vy;
+    if (vy < 0.1f) {
       int lo = 0, hi = L;
       while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= k) lo = mid; else hi = mid; }
       atomicAdd(&s_halt[lo], 1);
@@ -879,7 +888,7 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   h->args.ctl_words = (CTL_FIXED + N + net->n_src + 3) & ~3;
   h->meas_words = 3 * net->n_det + N;
   h->n_nodes = N; h->n_obs = net->n_obs; h->max_na = net->max_na; h->n_det = net->n_det;
-  rc |= dalloc(h, (size_t)R * net->n_slots, &h->args.veh);
+  rc |= dalloc(h, (size_t)R * 3 * net->n_slots, &h->args.veh);
   rc |= dalloc(h, (size_t)R * d.lpad, &h->args.lane_cnt);
   rc |= dalloc(h, (size_t)R * h->args.ctl_words, &h->args.ctl);
   rc |= dalloc(h, (size_t)R * h->meas_words, &h->args.meas);
@@ -893,7 +902,7 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   if (rc) { tsc_destroy(h); return -1; }
   h->args.train_mode = 1;
   // shared memory: must mirror the carve-up in the kernel
-  size_t sm = (size_t)net->n_slots * 16;
+  size_t sm = (size_t)net->n_slots * 12;
   sm += (size_t)L * 4 * 2 + ((size_t)L + 1) * 4 + (size_t)L * 4 * 2 + (size_t)L * 2;
   sm = (sm + 3) & ~(size_t)3;
   sm += (size_t)N * 4 * 6 + (size_t)net->n_src * 4 + (size_t)net->n_det * 12 + (size_t)N * 4 + (8 + TSC_THREADS / 32) * 4;
@@ -1003,7 +1012,14 @@ extern "C" int tsc_dump_state(tsc_handle* h, int32_t replica, int32_t* lane_cnt_
   CK(cudaMemcpy(cnt.data(), h->args.lane_cnt + (size_t)replica * d.lpad, d.lpad, cudaMemcpyDeviceToHost));
   int V = 0;
   for (int l = 0; l < d.n_lanes; ++l) { lane_cnt_host[l] = cnt[l]; V += cnt[l]; }
-  if (V) CK(cudaMemcpy(veh_host, h->args.veh + (size_t)replica * d.n_slots, (size_t)V * 16, cudaMemcpyDeviceToHost));
+  if (V) {   // SoA on the device -> canonical [V][3] records on the host
+    std::vector<uint32_t> tmp((size_t)3 * V);
+    for (int a = 0; a < 3; ++a)
+      CK(cudaMemcpy(tmp.data() + (size_t)a * V, h->args.veh + ((size_t)replica * 3 + a) * d.n_slots, (size_t)V * 4,
+                    cudaMemcpyDeviceToHost));
+    for (int k = 0; k < V; ++k)
+      for (int a = 0; a < 3; ++a) veh_host[(size_t)k * 3 + a] = tmp[(size_t)a * V + k];
+  }
   *n_veh = V;
   return 0;
 }
@@ -1012,7 +1028,7 @@ extern "C" int tsc_info(tsc_handle* h, int64_t* state_bytes_per_replica, int32_t
   if (!h) return fail("tsc_info: null handle");
   const DevNet& d = h->args.net;
   if (state_bytes_per_replica)
-    *state_bytes_per_replica = (int64_t)d.n_slots * 16 + d.lpad + (int64_t)h->args.ctl_words * 4 + (int64_t)h->meas_words * 4;
+    *state_bytes_per_replica = (int64_t)d.n_slots * 12 + d.lpad + (int64_t)h->args.ctl_words * 4 + (int64_t)h->meas_words * 4;
   if (threads_per_block) *threads_per_block = TSC_THREADS;
   if (smem_bytes) *smem_bytes = h->smem;
   return 0;

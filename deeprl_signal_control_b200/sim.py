@@ -118,7 +118,7 @@ class BatchedSim:
     def dump_state(self, replica: int = 0):
         n = self.net
         cnt = np.zeros(n.n_lanes, np.int32)
-        veh = np.zeros((n.n_slots, 4), np.uint32)
+        veh = np.zeros((n.n_slots, 3), np.uint32)
         nv = C.c_int32(0)
         _lib.check(_lib.lib().tsc_dump_state(self._h, C.c_int32(replica), _np(cnt, C.c_int32),
                                              _np(veh, C.c_uint32), C.byref(nv)))

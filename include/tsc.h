@@ -163,8 +163,8 @@ int tsc_get_counts(tsc_handle* h, int32_t* veh_dev /*[R][n_det]*/, int32_t* halt
 int tsc_get_traffic_stats(tsc_handle* h, float* stats_dev, void* stream);
 
 /* Debug / parity: copy replica r's full vehicle state to the host in canonical form:
- * lane_cnt_host int32[n_lanes], veh_host uint32[4*n_slots] (lane-major, front vehicle first,
- * 16-byte records {pos f32, speed f32, meta0, meta1}); *n_veh = vehicles written.
+ * lane_cnt_host int32[n_lanes], veh_host uint32[3*n_slots] (lane-major, front vehicle first,
+ * 12-byte records {pos f32, speed f32, meta0 = wait:10|hop:6|route:8|speedFactor:8}); *n_veh = vehicles written.
  * Synchronous. */
 int tsc_dump_state(tsc_handle* h, int32_t replica, int32_t* lane_cnt_host, uint32_t* veh_host,
                    int32_t* n_veh);

@@ -90,7 +90,7 @@ class RefSim:
     def dump_state(self, replica: int = 0):
         n = self.net
         cnt = np.zeros(n.n_lanes, np.int32)
-        veh = np.zeros((n.n_slots, 4), np.uint32)
+        veh = np.zeros((n.n_slots, 3), np.uint32)
         nv = C.c_int32(0)
         lib().ref_dump_state(self.h, C.c_int32(replica), _p(cnt, C.c_int32), _p(veh, C.c_uint32),
                              C.byref(nv))

@@ -43,8 +43,7 @@
 typedef struct {
   float pos, spd;
   uint32_t m0; /* wait:10 | hop:6 | route:8 | sfq:8 */
-  uint32_t m1; /* depart:12 | wait_total:12 | wait_count:8 */
-} veh_t;
+} veh_t;   /* 12 bytes; trip statistics (depart, total wait) are not carried on the hot path */
 
 typedef struct {
   veh_t* ring;          /* [n_slots] */
@@ -281,16 +280,13 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       int slot = (int)(v - r->ring);
       v->pos = xnew[slot];
       v->spd = vnew[slot];
-      uint32_t w = M0_WAIT(v->m0), wt = (v->m1 >> 12) & 4095u, wc = v->m1 >> 24;
+      uint32_t w = M0_WAIT(v->m0);
       if (v->spd < 0.1f) {
-        if (w == 0 && wc < 255u) wc++;
         if (w < 1023u) w++;
-        if (wt < 4095u) wt++;
       } else {
         w = 0;
       }
       v->m0 = (v->m0 & ~1023u) | w;
-      v->m1 = (v->m1 & 4095u) | (wt << 12) | (wc << 24);
     }
   }
   /* C: junction transfers, one destination lane at a time, sources in merge-priority order */
@@ -391,7 +387,6 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       veh_t* e = &r->ring[n->lane_slot0[lane] + idx];
       e->pos = pos; e->spd = 0.0f;
       e->m0 = ((uint32_t)n->src_route[q] << 16) | ((uint32_t)sfq << 24);
-      e->m1 = t_abs & 4095u;
       r->cnt[lane] = cnt + 1;
       r->backlog[q]--;
       r->n_departed++;
@@ -642,7 +637,7 @@ void ref_dump_state(ref_sim* s, int32_t replica, int32_t* lane_cnt, uint32_t* ve
     lane_cnt[l] = r->cnt[l];
     for (int k = 0; k < r->cnt[l]; ++k) {
       veh_t* v = veh_at(n, r, l, k);
-      memcpy(veh + 4 * (size_t)w, v, 16);
+      memcpy(veh + 3 * (size_t)w, v, 12);
       w++;
     }
   }

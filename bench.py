@@ -192,6 +192,7 @@ def main():
 
     launches = 0
     trainer = None
+    align_steps = 0
     if mode == "train":
         from deeprl_signal_control_b200.agents.layout import PolicyLayout
         from deeprl_signal_control_b200.agents.learner import BatchedA2C
@@ -229,6 +230,13 @@ def main():
         one_step(i)
     for i in range(max(args.warmup, 3)):
         one_step(i)
+    align_steps = 0
+    if trainer is not None:
+        # the timed region must never skip the learner update: align it so that it ENDS on an update boundary
+        # (ceil(K / n_step) updates inside; for K < n_step this over-counts update work — conservative)
+        while (trainer.model.t + args.steps) % N_STEP != 0:
+            one_step(0)
+            align_steps += 1
     live0 = sim.mean_live()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -335,7 +343,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(R, mode), "replicas_per_gpu": R, "agents": net.n_nodes,
                        "burnin_control_steps": args.burnin, "mode": mode, "n_step": N_STEP,
-                       "updates_in_timed_region": n_updates_timed,
+                       "updates_in_timed_region": n_updates_timed, "untimed_alignment_steps": align_steps,
                        "learner_gemm_library": "cuBLAS %s (3 plain batched GEMMs per update chunk + 1 per step)"
                        % ("fp32" if args.fp32_gemm else "TF32 tensor cores, fp32 accumulate")
                        if mode == "train" else None,

@@ -877,6 +877,26 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
     for (int t = a.T - 1; t >= 0; --t) {
       const float keep = 1.0f - a.done[t];
       const int64_t m = ((int64_t)u * a.T + t) * a.Rc + (valid ? r : 0);
+      if (t > 0 && valid) {      // pull step t-1's operands towards L2 while step t is being processed
+        const int64_t mp = m - a.Rc;
+        const int jo0 = half * 32;
+        if (a.Gb) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Gb + mp * TC_N + g * 64 + jo0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + mp * TC_H + jo0));
+          if (t > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + (mp - a.Rc) * TC_H + jo0));
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + g * 64 + jo0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + g * 64 + jo0 + 16));
+          }
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.C + mp * TC_H + jo0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.C + mp * TC_H + jo0 + 16));
+        }
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + jo0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + jo0 + 16));
+      }
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb) {
         const int jo = half * 32 + jb * 16;

@@ -546,6 +546,19 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         sBias0[i] = b0;
       }
     }
+    // L2 prefetch of the NEXT work item's operands (observation slice, c, h): they are consumed ~one tile later
+    if (it + 1 < it_hi) {
+      const int un = (int)((it + 1) / n_tiles);
+      const int64_t rn = ((it + 1) - (int64_t)un * n_tiles) * TC_M + (tid >> 1);
+      if (rn < a.R) {
+        const int an = un >> 1;
+        const float* op = a.obs + rn * d.n_obs + d.obs_off[an] + (tid & 1) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(op));
+        const int64_t so = ((int64_t)un * a.R + rn) * TC_H + (tid & 1) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.c_in + so));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h_in + so));
+      }
+    }
     // ---- 1a. B0 (fc weights) -> first chunks of the A tile; 1b. observation slice -> last 8 chunks ----
     {
       const uint4* src0 = reinterpret_cast<const uint4*>(Wu + (int64_t)KC * TC_N * 8);

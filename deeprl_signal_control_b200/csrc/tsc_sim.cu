@@ -301,6 +301,8 @@ tsc_step_kernel(const StepArgs A) {
   float* s_loc = reinterpret_cast<float*>(s_det + 3 * n.n_det);  // N
   int32_t* s_misc = reinterpret_cast<int32_t*>(s_loc + N);         // [0..7] ctl fixed, [8..15] wsum
   int32_t* s_wsum = s_misc + 8;
+  int32_t* s_blk = s_wsum + TSC_THREADS / 32;                      // lane of compact vehicle 32*j
+  float* s_obsv = reinterpret_cast<float*>(s_blk + (n.n_slots + 31) / 32 + 1);   // [2*n_det] normalised wave | wait
 
   // ---- load replica state -------------------------------------------------------------------
   const uint8_t* g_cnt = A.lane_cnt + (size_t)rep * n.lpad;
@@ -363,6 +365,10 @@ tsc_step_kernel(const StepArgs A) {
     const ScanCarry sc = scan_part1(s_cnt, s_wsum, L);
     __syncthreads();
     scan_part2(sc, s_pre, s_wsum, L);
+    for (int l = l_lo; l < l_hi; ++l) {      // own lanes: which compact indices 32*j fall into lane l
+      const int p0 = s_pre[l], p1 = p0 + s_cnt[l];
+      for (int j = (p0 + 31) >> 5; (j << 5) < p1; ++j) s_blk[j] = l;
+    }
     // A2: head-vehicle speed limit from the junction ahead (own lanes; reads other lanes' tails)
     for (int l = l_lo; l < l_hi; ++l) {
       float lim = INF_SPEED;
@@ -421,8 +427,21 @@ tsc_step_kernel(const StepArgs A) {
         int slot = 0, lane = 0, rank = 0;
         uint3 me = make_uint3(0, 0, 0);
         uint8_t f = 0;
+        {   // lane of compact index k: warp-cooperative search over the 32 lane boundaries after the warp's first lane
+          const int kk = act ? k : V - 1;
+          const int lane0 = s_blk[(kk & ~31) >> 5];
+          const int bi = lane0 + 1 + (tid & 31);
+          const int bnd = s_pre[bi < L ? bi : L];
+          int lo = 0, hi = 32;
+#pragma unroll
+          for (int itb = 0; itb < 5; ++itb) {
+            const int mid = (lo + hi) >> 1;
+            const int vb = __shfl_sync(0xffffffffu, bnd, mid);
+            if (vb <= kk) lo = mid + 1; else hi = mid;
+          }
+          lane = lo < 32 ? lane0 + lo : find_lane(s_pre, L, kk);
+        }
         if (act) {
-          lane = find_lane(s_pre, L, k);
           rank = k - s_pre[lane];
           const LaneC lc = n.lane[lane];
           int idx = s_head[lane] + rank;
@@ -668,13 +687,18 @@ tsc_step_kernel(const StepArgs A) {
   }
   // observation gather (envs/env.py:163-205), coalesced row write
   if (A.obs) {
+    for (int dd = tid; dd < n.n_det; dd += TSC_THREADS) {
+      s_obsv[dd] = clipf((float)s_det[dd] / c.norm_wave, c.clip_wave);
+      s_obsv[n.n_det + dd] = clipf((float)s_det[2 * n.n_det + dd] / c.norm_wait, c.clip_wait);
+    }
+    __syncthreads();
     const float* fp = A.fp ? A.fp + (size_t)rep * N * n.max_na : nullptr;
     float* o = A.obs + (size_t)rep * n.n_obs;
     for (int k = tid; k < n.n_obs; k += TSC_THREADS) {
       const int kind = __ldg(&n.obs_kind[k]), idx = __ldg(&n.obs_idx[k]);
       float v;
-      if (kind == 0) v = clipf((float)s_det[idx] / c.norm_wave, c.clip_wave);
-      else if (kind == 1) v = clipf((float)s_det[2 * n.n_det + idx] / c.norm_wait, c.clip_wait);
+      if (kind == 0) v = s_obsv[idx];
+      else if (kind == 1) v = s_obsv[n.n_det + idx];
       else v = fp ? fp[idx] : 0.0f;
       o[k] = __ldg(&n.obs_scale[k]) * v;
     }
@@ -905,7 +929,8 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   size_t sm = (size_t)net->n_slots * 12;
   sm += (size_t)L * 4 * 2 + ((size_t)L + 1) * 4 + (size_t)L * 4 * 2 + (size_t)L * 2;
   sm = (sm + 3) & ~(size_t)3;
-  sm += (size_t)N * 4 * 6 + (size_t)net->n_src * 4 + (size_t)net->n_det * 12 + (size_t)N * 4 + (8 + TSC_THREADS / 32) * 4;
+  sm += (size_t)N * 4 * 6 + (size_t)net->n_src * 4 + (size_t)net->n_det * 12 + (size_t)N * 4 + (8 + TSC_THREADS / 32) * 4 +
+        ((size_t)(net->n_slots + 31) / 32 + 1) * 4 + (size_t)net->n_det * 8;
   h->smem = (int)sm;
   if (sm > 227 * 1024) { tsc_destroy(h); return fail("tsc_create: replica state exceeds 227 KB of shared memory"); }
   CK(cudaFuncSetAttribute(tsc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));

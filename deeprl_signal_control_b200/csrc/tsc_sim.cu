@@ -427,17 +427,18 @@ tsc_step_kernel(const StepArgs A) {
         int slot = 0, lane = 0, rank = 0;
         uint3 me = make_uint3(0, 0, 0);
         uint8_t f = 0;
-        {   // lane of compact index k: warp-cooperative search over the 32 lane boundaries after the warp's first lane
+        {   // lane of compact index k: warp-cooperative search over the 32 lane boundaries that follow the lane of
+            // the warp's first vehicle (33 possible outcomes -> 6 halvings); falls back to the block-wide search
           const int kk = act ? k : V - 1;
           const int lane0 = s_blk[(kk & ~31) >> 5];
           const int bi = lane0 + 1 + (tid & 31);
           const int bnd = s_pre[bi < L ? bi : L];
           int lo = 0, hi = 32;
 #pragma unroll
-          for (int itb = 0; itb < 5; ++itb) {
+          for (int itb = 0; itb < 6; ++itb) {
             const int mid = (lo + hi) >> 1;
-            const int vb = __shfl_sync(0xffffffffu, bnd, mid);
-            if (vb <= kk) lo = mid + 1; else hi = mid;
+            const int vb = __shfl_sync(0xffffffffu, bnd, mid & 31);
+            if (lo < hi) { if (vb <= kk) lo = mid + 1; else hi = mid; }
           }
           lane = lo < 32 ? lane0 + lo : find_lane(s_pre, L, kk);
         }

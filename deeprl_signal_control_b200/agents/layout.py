@@ -52,6 +52,11 @@ class PolicyLayout:
         if (self.n_wait == 0).all():
             self.ft = 0                                   # agents/policies.py:107-108 (n_w == 0)
         self.dx = self.fw + self.ff + self.ft
+        # 64-slot input tile of the tensor-core kernels: wave block 32 or 48 wide, then 16 fingerprint slots
+        # (+ 16 wait slots when the wave block is 32); one spare wave slot carries the bias column of tscl_fc_bwd_tc
+        mw = int(self.n_wave.max())
+        self.kw = 32 if mw <= 32 else (48 if (mw <= 48 and self.ft == 0) else 0)
+        self.fc_bwd_tc_ok = self.kw > 0 and mw < self.kw and self.dx % 8 == 0 and self.dx <= 256
         self.max_na = int(max_na or self.n_a.max())
         U, dx, g4 = self.U, self.dx, 4 * self.h
         off = 0

@@ -97,6 +97,7 @@ class BatchedA2C:
                               device=self.dev)
         self.Wt = torch.zeros(U, 32, L.h, 8, dtype=torch.bfloat16, device=self.dev)    # Wh^T image for the BPTT MMA
         self.bwd_tc = self.use_tc
+        self.fc_bwd_tc = self.use_tc and layout.fc_bwd_tc_ok     # front-end weight gradients on the tensor cores
         self.pack_weights()
         # bf16 activation store of the rollout's own forward pass (written by the v2 kernel): the update then
         # back-propagates through it instead of recomputing fc + gate GEMM + LSTM forward.
@@ -283,8 +284,13 @@ class BatchedA2C:
             self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)
             self.gv["bl"].add_(dZ.sum(dim=1))
             torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
-            _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
-                                       C.c_int64(R * n_obs), _p(self.G), st()))
+            if self.fc_bwd_tc:
+                xb = _p(self.st_x[r0 // self.chunk]) if use_store else None
+                _lib.check(lib.tscl_fc_bwd_tc(self._h, _p(obs0), _p(X), xb, _p(dX), C.c_int64(M), C.c_int64(rc),
+                                              C.c_int64(R * n_obs), _p(self.G), C.c_int32(0), st()))
+            else:
+                _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
+                                           C.c_int64(R * n_obs), _p(self.G), st()))
             self.kernel_launches += 4 if use_store else 5
         if self.pg is not None:
             torch.distributed.all_reduce(self.G, op=torch.distributed.ReduceOp.SUM, group=self.pg)

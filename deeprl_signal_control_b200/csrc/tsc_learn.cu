@@ -36,6 +36,7 @@ struct DDims {
   const int32_t *obs_off, *n_wave, *n_wait, *n_fp, *n_a;
   const int64_t *off_fcw_w, *off_fcw_b, *off_fcf_w, *off_fcf_b, *off_fct_w, *off_fct_b;
   int64_t off_wx, off_wh, off_bl, off_wo, off_bo, n_params;
+  int kw, ones_slot;   // ones_slot: spare input slot that carries 1.0 in tscl_fc_bwd_tc (-1: none); kw: width of the wave block in the 64-column tensor-core input tile: 32 (wave|fp16|wait16) or 48 (wave|fp16)
 };
 
 struct tscl_handle {
@@ -56,10 +57,11 @@ __device__ __forceinline__ uint32_t lmix32(uint32_t h) {
 // fc front end.  grid (n_row_groups, 2A), 256 threads.  Thread = output column (dx <= 256): its weight
 // column (<= 32 values) lives in registers, each staged row costs one broadcast LDS.128 per 4 FMAs.
 #define FE_ROWS 64
-#define FE_KW 32   // padded inputs of the wave layer
+#define FE_KW_MAX 48   // padded inputs of the wave layer: template parameter KW = 32 (grid <= 30) or 48 (Monaco <= 34)
 #define FE_KF 16   // fingerprint layer
 #define FE_KT 16   // wait layer
-#define FE_KTOT (FE_KW + FE_KF + FE_KT)
+#define FE_KTOT (KW + FE_KF + FE_KT)
+template <int KW>
 __global__ void __launch_bounds__(256)
 fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ obs, int64_t M,
                 int64_t rows_per_t, int64_t stride_t, float* __restrict__ X) {
@@ -68,22 +70,22 @@ fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restr
   const int nw = d.n_wave[a], nt = d.n_wait[a], nf = d.ff > 0 ? d.n_fp[a] : 0;
   const int dx = d.dx, col = tid;
   // this thread's weight column
-  float w[FE_KW];
+  float w[KW];
   float bias = 0.f;
   int kbase = 0, nk = 0;
 #pragma unroll
-  for (int k = 0; k < FE_KW; ++k) w[k] = 0.f;
+  for (int k = 0; k < KW; ++k) w[k] = 0.f;
   if (col < dx) {
     if (col < d.fw) {
       nk = nw; kbase = 0;
-      for (int k = 0; k < FE_KW; ++k) if (k < nw) w[k] = P[d.off_fcw_w[u] + (int64_t)k * d.fw + col];
+      for (int k = 0; k < KW; ++k) if (k < nw) w[k] = P[d.off_fcw_w[u] + (int64_t)k * d.fw + col];
       bias = P[d.off_fcw_b[u] + col];
     } else if (col < d.fw + d.ff) {
-      nk = nf; kbase = FE_KW;
+      nk = nf; kbase = KW;
       for (int k = 0; k < FE_KF; ++k) if (k < nf) w[k] = P[d.off_fcf_w[u] + (int64_t)k * d.ff + (col - d.fw)];
       bias = P[d.off_fcf_b[u] + (col - d.fw)];
     } else {
-      nk = nt; kbase = FE_KW + FE_KF;
+      nk = nt; kbase = KW + FE_KF;
       for (int k = 0; k < FE_KT; ++k) if (k < nt) w[k] = P[d.off_fct_w[u] + (int64_t)k * d.ft + (col - d.fw - d.ff)];
       bias = P[d.off_fct_b[u] + (col - d.fw - d.ff)];
     }
@@ -103,8 +105,8 @@ fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restr
         const float v = obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k];
         int dst;
         if (k < nw) dst = k;
-        else if (k < nw + nt) dst = FE_KW + FE_KF + (k - nw);
-        else dst = FE_KW + (k - nw - nt);
+        else if (k < nw + nt) dst = KW + FE_KF + (k - nw);
+        else dst = KW + (k - nw - nt);
         sIn[row * FE_KTOT + dst] = v;
       }
     }
@@ -116,7 +118,7 @@ fc_embed_kernel(const DDims d, const float* __restrict__ P, const float* __restr
         const float4* in4 = reinterpret_cast<const float4*>(&sIn[row * FE_KTOT + kbase]);
         float acc = bias;
 #pragma unroll
-        for (int k4 = 0; k4 < FE_KW / 4; ++k4) {
+        for (int k4 = 0; k4 < KW / 4; ++k4) {
           if (k4 < nk4) {
             const float4 x = in4[k4];
             acc = fmaf(x.x, w[4 * k4], acc); acc = fmaf(x.y, w[4 * k4 + 1], acc);
@@ -512,6 +514,7 @@ lstm_seq_bwd_kernel(const DDims d, const float* __restrict__ P, float* __restric
 // fc front-end backward.  grid (n_groups, 2A), 256 threads.  Thread = column c of dX: accumulates
 // dW[k][c] for every input k of its layer (<= 32 registers) + the bias gradient; rows staged 32 at a time.
 #define FB_ROWS 32
+template <int KW>
 __global__ void __launch_bounds__(256)
 fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restrict__ X, const float* __restrict__ dX,
               int64_t M, int64_t rows_per_t, int64_t stride_t, float* __restrict__ G) {
@@ -521,12 +524,12 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
   const int n_in = nw + nt + nf, dx = d.dx, col = tid;
   int kbase = 0, nk = 0;
   if (col < d.fw) { nk = nw; kbase = 0; }
-  else if (col < d.fw + d.ff) { nk = nf; kbase = FE_KW; }
-  else if (col < dx) { nk = nt; kbase = FE_KW + FE_KF; }
+  else if (col < d.fw + d.ff) { nk = nf; kbase = KW; }
+  else if (col < dx) { nk = nt; kbase = KW + FE_KF; }
   const int nk4 = (nk + 3) >> 2;
-  float acc[FE_KW];
+  float acc[KW];
 #pragma unroll
-  for (int k = 0; k < FE_KW; ++k) acc[k] = 0.f;
+  for (int k = 0; k < KW; ++k) acc[k] = 0.f;
   float accb = 0.f;
   const int ooff = d.obs_off[a];
   for (int i = tid; i < FB_ROWS * FE_KTOT; i += 256) sIn[i] = 0.f;
@@ -539,8 +542,8 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
       if (m < M) v = obs[(m / rows_per_t) * stride_t + (m % rows_per_t) * d.n_obs + ooff + k];
       int dst;
       if (k < nw) dst = k;
-      else if (k < nw + nt) dst = FE_KW + FE_KF + (k - nw);
-      else dst = FE_KW + (k - nw - nt);
+      else if (k < nw + nt) dst = KW + FE_KF + (k - nw);
+      else dst = KW + (k - nw - nt);
       sIn[row * FE_KTOT + dst] = v;
     }
     __syncthreads();
@@ -563,7 +566,7 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
           accb += g[j];
           const float4* in4 = reinterpret_cast<const float4*>(&sIn[(r0 + j) * FE_KTOT + kbase]);
 #pragma unroll
-          for (int k4 = 0; k4 < FE_KW / 4; ++k4) {
+          for (int k4 = 0; k4 < KW / 4; ++k4) {
             if (k4 < nk4) {
               const float4 x = in4[k4];
               acc[4 * k4] = fmaf(x.x, g[j], acc[4 * k4]); acc[4 * k4 + 1] = fmaf(x.y, g[j], acc[4 * k4 + 1]);
@@ -580,7 +583,7 @@ fc_bwd_kernel(const DDims d, const float* __restrict__ obs, const float* __restr
     else if (col < d.fw + d.ff) { wo = d.off_fcf_w[u]; bo = d.off_fcf_b[u]; ld = d.ff; c = col - d.fw; }
     else { wo = d.off_fct_w[u]; bo = d.off_fct_b[u]; ld = d.ft; c = col - d.fw - d.ff; }
 #pragma unroll
-    for (int k = 0; k < FE_KW; ++k)
+    for (int k = 0; k < KW; ++k)
       if (k < nk) atomicAdd(&G[wo + (int64_t)k * ld + c], acc[k]);
     atomicAdd(&G[bo + c], accb);
   }
@@ -700,10 +703,17 @@ extern "C" int tscl_create(const tscl_dims* x, int32_t device, tscl_handle** out
     if (w > h->max_fcw) h->max_fcw = w;
   }
   for (size_t a = 0; a < A; ++a)
-    if (x->n_wave[a] > FE_KW || (x->ff > 0 && x->n_fp[a] > FE_KF) || x->n_wait[a] > FE_KT || x->dx > 256) {
+    if (x->n_wave[a] > FE_KW_MAX || (x->ff > 0 && x->n_fp[a] > FE_KF) || x->n_wait[a] > FE_KT || x->dx > 256) {
       tscl_destroy(h);
-      return tsc_set_error("tscl_create: fc input widths exceed the kernel limits (wave 32, fp 16, wait 16, dx 256)");
+      return tsc_set_error("tscl_create: fc input widths exceed the kernel limits (wave 48, fp 16, wait 16, dx 256)");
     }
+  {
+    int mw = 0, mt = 0;
+    for (size_t a = 0; a < A; ++a) { if (x->n_wave[a] > mw) mw = x->n_wave[a]; if (x->n_wait[a] > mt) mt = x->n_wait[a]; }
+    d.kw = mw <= 32 ? 32 : 48;
+    if (d.kw == 48 && mt > 0 && x->ft > 0) d.kw = 0;   // no 64-column packing exists: tensor-core forward unavailable
+    d.ones_slot = (d.kw > 0 && mw < d.kw) ? d.kw - 1 : -1;
+  }
   LCK(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (H64 * G4 + LS_ROWS * H64) * 4));
   LCK(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (G4 * H64 + LS_ROWS * G4) * 4));
   *out = h;
@@ -725,7 +735,7 @@ extern "C" int tscl_fc_embed(tscl_handle* h, const float* params, const float* o
   int64_t ng = (M + FE_ROWS - 1) / FE_ROWS;
   if (ng > 24) ng = 24;                 // 24 x 2A CTAs (~8 per SM): the weight column load is amortised over many rows
   dim3 grid((unsigned)ng, 2 * h->d.A);
-  fc_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  (h->d.kw == 32 ? fc_embed_kernel<32> : fc_embed_kernel<48>)<<<grid, 256, 0, (cudaStream_t)stream>>>(
       h->d, params, obs, M, rows_per_t, stride_t, X);
   LCK(cudaGetLastError());
   return 0;
@@ -802,7 +812,7 @@ extern "C" int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, con
   int64_t ng = (M + FB_ROWS - 1) / FB_ROWS;
   if (ng > 24) ng = 24;
   dim3 grid((unsigned)ng, 2 * h->d.A);
-  fc_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, obs, X, dX, M, rows_per_t, stride_t, grads);
+  (h->d.kw == 32 ? fc_bwd_kernel<32> : fc_bwd_kernel<48>)<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, obs, X, dX, M, rows_per_t, stride_t, grads);
   LCK(cudaGetLastError());
   return 0;
 }

@@ -36,6 +36,7 @@ struct DDimsTC {   // mirror of DDims in tsc_learn.cu (kept in sync by tscl_hand
   const int32_t *obs_off, *n_wave, *n_wait, *n_fp, *n_a;
   const int64_t *off_fcw_w, *off_fcw_b, *off_fcf_w, *off_fcf_b, *off_fct_w, *off_fct_b;
   int64_t off_wx, off_wh, off_bl, off_wo, off_bo, n_params;
+  int kw, ones_slot;
 };
 const DDimsTC* tscl_dims_of(tscl_handle* h);   // defined in tsc_learn.cu
 int tscl_device_of(tscl_handle* h);
@@ -132,9 +133,9 @@ __global__ void pack_fc_kernel(const DDimsTC d, const float* __restrict__ P, __n
     for (int e = 0; e < 8; ++e) {
       const int k = kc * 8 + e;
       float w = 0.f;
-      if (n < d.fw) { if (k < TC_KW && k < nw) w = P[d.off_fcw_w[u] + (int64_t)k * d.fw + n]; }
-      else if (n < d.fw + d.ff) { const int kk = k - TC_KW; if (kk >= 0 && kk < TC_KF && kk < nf) w = P[d.off_fcf_w[u] + (int64_t)kk * d.ff + (n - d.fw)]; }
-      else { const int kk = k - TC_KW - TC_KF; if (kk >= 0 && kk < nt) w = P[d.off_fct_w[u] + (int64_t)kk * d.ft + (n - d.fw - d.ff)]; }
+      if (n < d.fw) { if (k < d.kw && k < nw) w = P[d.off_fcw_w[u] + (int64_t)k * d.fw + n]; }
+      else if (n < d.fw + d.ff) { const int kk = k - d.kw; if (kk >= 0 && kk < TC_KF && kk < nf) w = P[d.off_fcf_w[u] + (int64_t)kk * d.ff + (n - d.fw)]; }
+      else { const int kk = k - d.kw - TC_KF; if (kk >= 0 && kk < nt) w = P[d.off_fct_w[u] + (int64_t)kk * d.ft + (n - d.fw - d.ff)]; }
       v[e] = __float2bfloat16_rn(w);
     }
     *reinterpret_cast<uint4*>(W0 + ((int64_t)kc * d.dx + n) * 8) = *reinterpret_cast<const uint4*>(v);
@@ -454,6 +455,7 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
   const DDimsTC& d = *tscl_dims_of(h);
   const int K = d.dx + TC_H;
   if ((d.dx % 16) != 0 || d.dx > TC_THREADS) return tsc_set_error("tscl_policy_step: unsupported dx");
+  if (d.kw != 32) return tsc_set_error("tscl_policy_step: v1 kernel supports wave widths <= 32 only (use tscl_policy_step_v2)");
   const size_t smem = tc_smem_bytes(K);
   if (smem > 232448) return tsc_set_error("tscl_policy_step: operand tiles exceed shared memory");
   static int attr_dev = -1;
@@ -575,9 +577,9 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         for (int e = 0; e < 8; ++e) {
           const int c = ch * 8 + e;
           int src = -1;
-          if (c < TC_KW) { if (c < nw) src = c; }
-          else if (c < TC_KW + TC_KF) { if (c - TC_KW < nf) src = nw + nt + (c - TC_KW); }
-          else { if (c - TC_KW - TC_KF < nt) src = nw + (c - TC_KW - TC_KF); }
+          if (c < d.kw) { if (c < nw) src = c; }
+          else if (c < d.kw + TC_KF) { if (c - d.kw < nf) src = nw + nt + (c - d.kw); }
+          else { if (c - d.kw - TC_KF < nt) src = nw + (c - d.kw - TC_KF); }
           float x = 0.f;
           if (src >= 0 && r < a.R) x = __ldg(a.obs + r * d.n_obs + ooff + src);
           v[e] = __float2bfloat16_rn(x);
@@ -789,6 +791,7 @@ extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const vo
   const DDimsTC& d = *tscl_dims_of(h);
   const int K = d.dx + TC_H;
   if ((d.dx % 32) != 0 || d.dx > 256) return tsc_set_error("tscl_policy_step_v2: dx must be a multiple of 32, <= 256");
+  if (d.kw == 0) return tsc_set_error("tscl_policy_step_v2: observation slice does not fit the 64-column input tile");
   if (8 * d.dx * 16 > (d.dx / 8) * 2048) return tsc_set_error("tscl_policy_step_v2: fc operand does not fit its staging region");
   const size_t smem = tc2_smem_bytes(K);
   if (smem > 232448) return tsc_set_error("tscl_policy_step_v2: operand tiles exceed shared memory");
@@ -1054,6 +1057,226 @@ extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* 
   a.Wt = (const __nv_bfloat16*)wt_bf16; a.ZG = ZG; a.C = C; a.dH = dH; a.c0 = c0; a.done = done; a.T = T; a.Rc = Rc;
   a.ld_state = ld_state; a.r0 = r0; a.Gb = (const __nv_bfloat16*)gates_bf16; a.Cb = (const __nv_bfloat16*)c_bf16;
   lstm_bwd_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+// ===================================================================================================
+// fc front-end weight gradients on the tensor cores (replaces fc_bwd_kernel of tsc_learn.cu).
+//   dW[k][c] = sum_m In[m][k] * dXm[m][c],   dXm = dX * (X > 0),   m = (t, replica) rows of one chunk
+// is a GEMM whose reduction index is the ROW index, so both operands are staged MN-major: the row-major global
+// data lands as [col/8][128 rows][8 cols] bf16 without a transposition, and
+//   D[dX column (two M = 128 halves)][64 input slots] += A^T B      (tcgen05.mma, a_major = b_major = MN, K = 128 rows)
+// accumulates in TMEM over all tiles of a unit.  A spare input slot holds 1.0: its D column is the bias gradient.
+// Persistent: CTA b owns the tile range [b NT / grid, (b + 1) NT / grid) of the (unit, tile) list and flushes its
+// accumulator with atomics whenever the unit changes (<= 3 flushes per CTA).
+#define FBT_ROWS 128
+#define FBT_SBO 2064                       // chunk stride: 128 rows * 16 B + 16 B pad (conflict-free transposing stores)
+#define FBT_A_BYTES (32 * FBT_SBO)
+#define FBT_B_BYTES (8 * FBT_SBO)
+#define FBT_STAGE (FBT_A_BYTES + FBT_B_BYTES)
+#define FBT_THREADS 512
+struct FcBwdTC {
+  const float* obs;            // rows as tscl_fc_embed
+  const float* X;              // [2A][M][dx] fp32 activations, or
+  const __nv_bfloat16* Xb;     // [2A][M][dx] bf16 activations (one chunk of the activation store)
+  const float* dX;             // [2A][M][dx]
+  float* G;
+  int64_t M, rows_per_t, stride_t;
+  int variant;                 // 1: LBO/SBO swapped (descriptor diagnosis)
+};
+
+__global__ void __launch_bounds__(FBT_THREADS, 1)
+fc_bwd_tc_kernel(const DDimsTC d, const FcBwdTC a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(tc_smem + 2 * FBT_STAGE);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2);
+  const uint32_t bar0 = smem_u32(sBar);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  // bf16 x bf16 -> f32, A and B MN-major, N = 64, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  const uint32_t lbo = a.variant ? FBT_SBO : 128, sbo = a.variant ? 128 : FBT_SBO;
+  const int dx = d.dx, ng = dx >> 3, n_items = FBT_ROWS * ng;
+  const int64_t tpu = (a.M + FBT_ROWS - 1) / FBT_ROWS;
+  const int64_t NT = tpu * 2 * d.A;
+  const int64_t j0 = NT * blockIdx.x / gridDim.x, j1 = NT * (blockIdx.x + 1) / gridDim.x;
+  uint32_t ph0 = 0, ph1 = 0;
+  bool pend0 = false, pend1 = false, first = true;
+  int cur_u = -1, nw = 0, nt = 0, nf = 0, ooff = 0;
+  int src[8];                                  // observation index of each of this thread's 8 input slots (-1 none, -2 one)
+  const int bc = tid & 7;                      // this thread's B chunk (8 input slots)
+
+  auto flush = [&](int u) {
+    if (pend0) { mbar_wait(bar0, ph0); ph0 ^= 1; pend0 = false; }
+    if (pend1) { mbar_wait(bar0 + 8, ph1); ph1 ^= 1; pend1 = false; }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3, cgp = warp >> 2, mh = cgp >> 1, k0 = (cgp & 1) * 32;
+    const int c = mh * 128 + q * 32 + lane;
+    float v[32];
+    const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 64 + k0);
+    tmem_ld16(tb, v); tmem_ld16(tb + 16, v + 16);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (c < dx) {
+      int64_t wo, bo; int ld, cc, s0, n;
+      if (c < d.fw) { wo = d.off_fcw_w[u]; bo = d.off_fcw_b[u]; ld = d.fw; cc = c; s0 = 0; n = nw; }
+      else if (c < d.fw + d.ff) { wo = d.off_fcf_w[u]; bo = d.off_fcf_b[u]; ld = d.ff; cc = c - d.fw; s0 = d.kw; n = nf; }
+      else { wo = d.off_fct_w[u]; bo = d.off_fct_b[u]; ld = d.ft; cc = c - d.fw - d.ff; s0 = d.kw + TC_KF; n = nt; }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int slot = k0 + e, kin = slot - s0;
+        if (kin >= 0 && kin < n) atomicAdd(&a.G[wo + (int64_t)kin * ld + cc], v[e]);
+        if (slot == d.ones_slot) atomicAdd(&a.G[bo + cc], v[e]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  };
+
+  for (int64_t j = j0; j < j1; ++j) {
+    const int u = (int)(j / tpu);
+    const int64_t m0 = (j - (int64_t)u * tpu) * FBT_ROWS;
+    const int s = (int)((j - j0) & 1);
+    if (u != cur_u) {
+      if (cur_u >= 0) flush(cur_u);
+      cur_u = u; first = true;
+      const int ag = u >> 1;
+      nw = d.n_wave[ag]; nt = d.n_wait[ag]; nf = d.ff > 0 ? d.n_fp[ag] : 0; ooff = d.obs_off[ag];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int slot = bc * 8 + e;
+        int sidx = -1;
+        if (slot < d.kw) { if (slot < nw) sidx = slot; }
+        else if (slot < d.kw + TC_KF) { if (slot - d.kw < nf) sidx = nw + nt + (slot - d.kw); }
+        else { if (slot - d.kw - TC_KF < nt) sidx = nw + (slot - d.kw - TC_KF); }
+        if (slot == d.ones_slot) sidx = -2;
+        src[e] = sidx;
+      }
+    }
+    // the MMAs that read stage s two tiles ago must have drained it
+    if (s == 0) { if (pend0) { mbar_wait(bar0, ph0); ph0 ^= 1; pend0 = false; } }
+    else { if (pend1) { mbar_wait(bar0 + 8, ph1); ph1 ^= 1; pend1 = false; } }
+    unsigned char* sA = tc_smem + (size_t)s * FBT_STAGE;
+    unsigned char* sB = sA + FBT_A_BYTES;
+    const int rows_valid = (a.M - m0) < FBT_ROWS ? (int)(a.M - m0) : FBT_ROWS;
+    const int items_valid = rows_valid * ng;
+    const int64_t base = ((int64_t)u * a.M + m0) * dx;
+    // ---- A: masked dX, 8 columns (one 16 B chunk row) per item; items are contiguous in global memory ----
+    for (int ib = 0; ib < n_items; ib += 4 * FBT_THREADS) {
+      float4 g0[4], g1[4];
+      uint4 xb[4];
+      float4 x0[4], x1[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = ib + r * FBT_THREADS + tid;
+        g0[r] = g1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[r] = make_uint4(0, 0, 0, 0);
+        x0[r] = x1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < items_valid) {
+          const float4* gp = reinterpret_cast<const float4*>(a.dX + base) + 2 * (int64_t)i;
+          g0[r] = __ldg(gp); g1[r] = __ldg(gp + 1);
+          if (a.Xb) xb[r] = __ldg(reinterpret_cast<const uint4*>(a.Xb + base) + i);
+          else {
+            const float4* xp = reinterpret_cast<const float4*>(a.X + base) + 2 * (int64_t)i;
+            x0[r] = __ldg(xp); x1[r] = __ldg(xp + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = ib + r * FBT_THREADS + tid;
+        if (i < n_items) {
+          const float gv[8] = {g0[r].x, g0[r].y, g0[r].z, g0[r].w, g1[r].x, g1[r].y, g1[r].z, g1[r].w};
+          bool pos[8];
+          if (a.Xb) {
+            const uint32_t w[4] = {xb[r].x, xb[r].y, xb[r].z, xb[r].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t lo = w[e] & 0xffffu, hi = w[e] >> 16;
+              pos[2 * e] = (lo & 0x8000u) == 0 && (lo & 0x7fffu) != 0;
+              pos[2 * e + 1] = (hi & 0x8000u) == 0 && (hi & 0x7fffu) != 0;
+            }
+          } else {
+            const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pos[e] = xv[e] > 0.f;
+          }
+          __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(pos[e] ? gv[e] : 0.f);
+          const int row = i / ng, cg = i - row * ng;
+          *reinterpret_cast<uint4*>(sA + (size_t)cg * FBT_SBO + row * 16) = *reinterpret_cast<const uint4*>(o);
+        }
+      }
+    }
+    // ---- B: the unit's observation slice scattered into the 64 input slots ----
+#pragma unroll
+    for (int r = 0; r < (FBT_ROWS * 8) / FBT_THREADS; ++r) {
+      const int row = (r * FBT_THREADS + tid) >> 3;
+      __align__(16) __nv_bfloat16 o[8];
+      if (row < rows_valid) {
+        const int64_t m = m0 + row;
+        const float* op = a.obs + (m / a.rows_per_t) * a.stride_t + (m % a.rows_per_t) * d.n_obs + ooff;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(src[e] >= 0 ? __ldg(op + src[e]) : (src[e] == -2 ? 1.0f : 0.f));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(0.f);
+      }
+      *reinterpret_cast<uint4*>(sB + (size_t)bc * FBT_SBO + row * 16) = *reinterpret_cast<const uint4*>(o);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+#pragma unroll
+      for (int mh = 0; mh < 2; ++mh)
+        for (int ks = 0; ks < FBT_ROWS / 16; ++ks)
+          umma_bf16(tmem + mh * 64, make_desc(aA + mh * 16 * FBT_SBO + ks * 256, lbo, sbo),
+                    make_desc(aB + ks * 256, lbo, sbo), idesc, (first && ks == 0) ? 0u : 1u);
+      umma_commit(bar0 + 8 * s);
+    }
+    if (s == 0) pend0 = true; else pend1 = true;
+    first = false;
+  }
+  if (cur_u >= 0) flush(cur_u);
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+extern "C" int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, const void* x_bf16, const float* dX,
+                              int64_t M, int64_t rows_per_t, int64_t stride_t, float* grads, int32_t variant, void* stream) {
+  if (!h || !obs || (!X && !x_bf16) || !dX || !grads || M <= 0) return tsc_set_error("tscl_fc_bwd_tc: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  if ((d.dx % 8) != 0 || d.dx > 256) return tsc_set_error("tscl_fc_bwd_tc: dx must be a multiple of 8, <= 256");
+  if (d.kw == 0 || d.ones_slot < 0) return tsc_set_error("tscl_fc_bwd_tc: no free input slot for the bias column (use tscl_fc_bwd)");
+  const size_t smem = 2 * FBT_STAGE + 32;
+  static int attr_dev = -1;
+  if (attr_dev != tscl_device_of(h)) {
+    PCK(cudaFuncSetAttribute(fc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = tscl_device_of(h);
+  }
+  int n_sm = 0;
+  PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
+  const int64_t NT = ((M + FBT_ROWS - 1) / FBT_ROWS) * 2 * d.A;
+  const int grid = (int)(NT < n_sm ? NT : n_sm);
+  FcBwdTC a;
+  a.obs = obs; a.X = X; a.Xb = (const __nv_bfloat16*)x_bf16; a.dX = dX; a.G = grads; a.M = M; a.rows_per_t = rows_per_t;
+  a.stride_t = stride_t; a.variant = variant;
+  fc_bwd_tc_kernel<<<grid, FBT_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
 }

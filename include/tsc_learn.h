@@ -101,6 +101,12 @@ int tscl_lstm_seq_bwd(tscl_handle* h, const float* params, float* ZG, const floa
 int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* dX, int64_t M,
                 int64_t rows_per_t, int64_t stride_t, float* grads, void* stream);
 
+/* The same contraction on the tensor cores (tcgen05, MN-major bf16 operands, fp32 accumulation in TMEM over
+ * 128-row tiles; replaces the SIMT kernel in the training loop).  Pass the activations either as fp32 `X` or as one
+ * chunk of the bf16 activation store `x_bf16` ([2A][M][dx]); `variant` must be 0. */
+int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, const void* x_bf16, const float* dX, int64_t M,
+                   int64_t rows_per_t, int64_t stride_t, float* grads, int32_t variant, void* stream);
+
 /* BPTT on the tensor cores (tcgen05): same contract as tscl_lstm_seq_bwd, with the recurrent product dz.Wh^T as
  * a bf16 MMA (M=128, N=64, K=256) per step; wt_bf16 [2A][32][64][8] comes from tscl_pack_wht (refresh after
  * every optimizer step). */

@@ -10,6 +10,12 @@ pytestmark = pytest.mark.gpu
 
 def _layout(ff=64):
     from deeprl_signal_control_b200.agents.layout import PolicyLayout
+    if ff == "monaco":
+        # Monaco shapes (real_net): no wait block (ft = 0), up to 34 wave inputs, 6 phases
+        n_w, n_f, n_wave = [0, 0, 0], [16, 4, 9], [34, 5, 33]
+        n_s = [w + f for w, f in zip(n_wave, n_f)]
+        off = np.concatenate([[0], np.cumsum(n_s)]).astype(np.int32)
+        return PolicyLayout(n_s, [6, 2, 4], n_w, n_f, off, int(off[-1]) + 2, fw=128, ft=0, ff=64, h=64, max_na=6)
     # three agents with the three grid shapes: corner / edge / interior (n_s 32 / 42 / 52)
     n_w = [6, 6, 6]
     n_f = [8, 12, 16] if ff else [0, 0, 0]
@@ -23,7 +29,7 @@ def _ref_views(lay, P):
     return lay.views(torch.from_numpy(P.astype(np.float64)))
 
 
-@pytest.mark.parametrize("ff", [64, 0])
+@pytest.mark.parametrize("ff", [64, 0, "monaco"])
 def test_forward_matches_oracle(ff):
     from deeprl_signal_control_b200.agents.learner import BatchedA2C
     from oracle.learner_ref import unit_forward
@@ -78,7 +84,7 @@ def test_sampling_follows_policy():
         assert np.abs(freq - p).max() < 0.03
 
 
-@pytest.mark.parametrize("ff,chunk", [(64, 16), (0, 64)])
+@pytest.mark.parametrize("ff,chunk", [(64, 16), (0, 64), ("monaco", 37)])
 def test_backward_gradients_match_autograd(ff, chunk):
     from deeprl_signal_control_b200.agents.learner import BatchedA2C
     from oracle.learner_ref import a2c_loss, nstep_returns

@@ -15,6 +15,12 @@ pytestmark = pytest.mark.gpu
 
 def _layout(ff):
     from deeprl_signal_control_b200.agents.layout import PolicyLayout
+    if ff == "monaco":
+        # Monaco shapes (real_net): no wait block (ft = 0, dx = 192), up to 34 wave inputs -> 48|16 input tile
+        n_w, n_f, n_wave = [0, 0, 0], [16, 4, 9], [34, 5, 33]
+        n_s = [w + f for w, f in zip(n_wave, n_f)]
+        off = np.concatenate([[0], np.cumsum(n_s)]).astype(np.int32)
+        return PolicyLayout(n_s, [6, 2, 4], n_w, n_f, off, int(off[-1]) + 2, fw=128, ft=0, ff=64, h=64, max_na=6)
     n_w = [6, 6, 6]
     n_f = [8, 12, 16] if ff else [0, 0, 0]
     n_wave = [18, 24, 30]
@@ -35,7 +41,7 @@ def _run_tc(m, obs, done, zdbg, swap, v2=False):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("ff", [64, 0])
+@pytest.mark.parametrize("ff", [64, 0, "monaco"])
 def test_gate_accumulators_match_bf16_matmul(ff):
     from deeprl_signal_control_b200 import _lib
     from deeprl_signal_control_b200.agents.learner import BatchedA2C, _p
@@ -55,6 +61,15 @@ def test_gate_accumulators_match_bf16_matmul(ff):
     torch.backends.cuda.matmul.allow_tf32 = False
     z_ref = torch.bmm(Xb, Wx) + torch.bmm(Hb, Wh)
     zdbg = torch.zeros(lay.U, R, 256, device="cuda")
+    if ff == "monaco":                          # v1 keeps the 32-wide wave block and must say so
+        with pytest.raises(RuntimeError, match="wave widths"):
+            _run_tc(m, obs, False, zdbg, 0)
+    else:
+        _check_v1(m, obs, zdbg, z_ref, Xb, Wx)
+    _check_v2(m, lay, obs, zdbg, Hb, Wx, Wh)
+
+
+def _check_v1(m, obs, zdbg, z_ref, Xb, Wx):
     _run_tc(m, obs, False, zdbg, 0)
     err0 = float((zdbg - z_ref).abs().max())
     if err0 > 5e-2:                             # diagnose a descriptor-stride mix-up in one GPU run
@@ -66,6 +81,9 @@ def test_gate_accumulators_match_bf16_matmul(ff):
     # done flag zeroes h and c inside the cell (agents/utils.py:104-105)
     _run_tc(m, obs, True, zdbg, 0)
     torch.testing.assert_close(zdbg, torch.bmm(Xb, Wx), rtol=1e-3, atol=2e-3)
+
+
+def _check_v2(m, lay, obs, zdbg, Hb, Wx, Wh):
     # v2 (fc front end on the tensor cores): reference with bf16-rounded observations and fc weights
     v = lay.views(m.P)
     Xs = []
@@ -76,7 +94,8 @@ def test_gate_accumulators_match_bf16_matmul(ff):
         parts = [torch.relu(ob[:, o0:o0 + nw] @ v["fcw_w%d" % u].to(torch.bfloat16).float() + v["fcw_b%d" % u])]
         if lay.ff > 0:
             parts.append(torch.relu(ob[:, o0 + nw + nt:o0 + nw + nt + nf] @ v["fcf_w%d" % u].to(torch.bfloat16).float() + v["fcf_b%d" % u]))
-        parts.append(torch.relu(ob[:, o0 + nw:o0 + nw + nt] @ v["fct_w%d" % u].to(torch.bfloat16).float() + v["fct_b%d" % u]))
+        if lay.ft > 0:
+            parts.append(torch.relu(ob[:, o0 + nw:o0 + nw + nt] @ v["fct_w%d" % u].to(torch.bfloat16).float() + v["fct_b%d" % u]))
         Xs.append(torch.cat(parts, 1))
     X2 = torch.stack(Xs).to(torch.bfloat16).float()
     z2_ref = torch.bmm(X2, Wx) + torch.bmm(Hb, Wh)
@@ -87,7 +106,7 @@ def test_gate_accumulators_match_bf16_matmul(ff):
     assert float((z2 - z2_ref).abs().mean()) < 2e-3
 
 
-@pytest.mark.parametrize("ff", [64, 0])
+@pytest.mark.parametrize("ff", [64, 0, "monaco"])
 def test_fused_forward_matches_fp32_path(ff):
     from deeprl_signal_control_b200.agents.learner import BatchedA2C
     lay = _layout(ff)
@@ -195,3 +214,68 @@ def test_bptt_tensor_core_kernel_matches_fp32_kernel():
     # the last time step has no recurrent carry: identical up to tanh.approx
     last = slice((T - 1) * Rc, T * Rc)
     assert float((z1[:, last] - z2[:, last]).abs().max()) / scale < 2e-3
+
+
+@pytest.mark.parametrize("ff,use_bf16_x", [(64, True), (0, False), ("monaco", True)])
+def test_fc_weight_gradients_tensor_core_kernel(ff, use_bf16_x):
+    """tscl_fc_bwd_tc (tcgen05, MN-major bf16 operands, reduction over rows) vs
+      * a float64 contraction of the SAME bf16-rounded operands (rtol 2e-3: only summation order differs), and
+      * tscl_fc_bwd (fp32 SIMT kernel) within the bf16 operand rounding."""
+    from deeprl_signal_control_b200 import _lib
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C, _p
+    lay = _layout(ff)
+    assert lay.fc_bwd_tc_ok
+    T, Rc, R = 5, 333, 400                        # M = 1665 rows: 13 full tiles + a ragged one, chunk at r0 = 40
+    m = BatchedA2C(lay, R, n_step=T, seed=4)
+    U, M, dx = lay.U, T * Rc, lay.dx
+    g = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.rand(T, R, lay.n_obs, device="cuda", generator=g) * 2
+    X = torch.relu(torch.randn(U, M, dx, device="cuda", generator=g))
+    Xb = X.to(torch.bfloat16).contiguous()
+    X = Xb.float()                                 # same mask on both paths
+    dX = torch.randn(U, M, dx, device="cuda", generator=g) * 1e-2
+    r0 = 40
+    obs0 = obs[0, r0:]
+    lib = _lib.lib()
+    G1, G2 = torch.zeros_like(m.G), torch.zeros_like(m.G)
+    _lib.check(lib.tscl_fc_bwd(m._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(Rc), C.c_int64(R * lay.n_obs),
+                               _p(G1), m._st()))
+
+    def run(variant, out):
+        _lib.check(lib.tscl_fc_bwd_tc(m._h, _p(obs0), None if use_bf16_x else _p(X), _p(Xb) if use_bf16_x else None,
+                                      _p(dX), C.c_int64(M), C.c_int64(Rc), C.c_int64(R * lay.n_obs), _p(out),
+                                      C.c_int32(variant), m._st()))
+        torch.cuda.synchronize()
+    run(0, G2)
+    g1, g2 = lay.views(G1.cpu().numpy()), lay.views(G2.cpu().numpy())
+    # float64 reference from bf16-rounded operands
+    ob = obs[:, r0:r0 + Rc].reshape(M, lay.n_obs).to(torch.bfloat16).double()
+    dXm = (dX * (X > 0)).to(torch.bfloat16).double()
+    worst = 0.0
+    for u in range(U):
+        a = u // 2
+        o0, nw, nt, nf = int(lay.obs_off[a]), int(lay.n_wave[a]), int(lay.n_wait[a]), int(lay.n_fp[a])
+        blocks = [("fcw", ob[:, o0:o0 + nw], dXm[u][:, :lay.fw])]
+        c0 = lay.fw
+        if lay.ff > 0:
+            blocks.append(("fcf", ob[:, o0 + nw + nt:o0 + nw + nt + nf], dXm[u][:, c0:c0 + lay.ff])); c0 += lay.ff
+        if lay.ft > 0:
+            blocks.append(("fct", ob[:, o0 + nw:o0 + nw + nt], dXm[u][:, c0:c0 + lay.ft]))
+        for name, inp, dd in blocks:
+            w_ref = (inp.T @ dd).cpu().numpy()
+            b_ref = dd.sum(0).cpu().numpy()
+            w_tc, b_tc = g2["%s_w%d" % (name, u)], g2["%s_b%d" % (name, u)]
+            e = max(np.abs(w_tc - w_ref).max() / max(np.abs(w_ref).max(), 1e-12),
+                    np.abs(b_tc - b_ref).max() / max(np.abs(b_ref).max(), 1e-12))
+            worst = max(worst, e)
+    if worst > 2e-3:                               # diagnose a descriptor-stride mix-up in one GPU run
+        G3 = torch.zeros_like(m.G)
+        run(1, G3)
+        raise AssertionError("tcgen05 MN-major fc_bwd mismatch: worst rel err %.4f (LBO/SBO swapped: rel-L2 vs fp32 %.4f)"
+                             % (worst, float((G3 - G1).norm() / G1.norm())))
+    # untouched parameter ranges stay zero, and the fp32 kernel agrees within bf16 operand rounding
+    for k in g1:
+        if not k.startswith("fc"):
+            assert not g2[k].any()
+    rel = float((G2 - G1).norm() / G1.norm())
+    assert rel < 1e-2, rel

@@ -98,6 +98,8 @@ class BatchedA2C:
         self.Wt = torch.zeros(U, 32, L.h, 8, dtype=torch.bfloat16, device=self.dev)    # Wh^T image for the BPTT MMA
         self.bwd_tc = self.use_tc
         self.fc_bwd_tc = self.use_tc and layout.fc_bwd_tc_ok     # front-end weight gradients on the tensor cores
+        self.wgrad_tc = self.use_tc and L.dx % 8 == 0 and L.dx <= 240   # LSTM weight gradients on the tensor cores
+        self.fused_heads = True                                  # head weight gradients inside tscl_heads_loss
         self.pack_weights()
         # bf16 activation store of the rollout's own forward pass (written by the v2 kernel): the update then
         # back-propagates through it instead of recomputing fc + gate GEMM + LSTM forward.
@@ -207,16 +209,21 @@ class BatchedA2C:
         self.done_post[t] = 1.0 if done_post else 0.0
         self.t += 1
 
-    def _bufs(self, rc):
+    def _bufs(self, rc, lean=False):
+        """fp32 work buffers of one update chunk.  `lean`: every consumer reads the bf16 activation store itself,
+        so only ZG (dZ out), dH and dX exist; the others are allocated the first time a fallback path needs them."""
         L, T, U = self.lay, self.T, self.lay.U
+        f32 = dict(dtype=torch.float32, device=self.dev)
         if self._upd_bufs is None or self._upd_bufs["rc"] < rc:
             M = T * rc
-            f32 = dict(dtype=torch.float32, device=self.dev)
-            self._upd_bufs = dict(rc=rc, X=torch.empty(U, M, L.dx, **f32), ZG=torch.empty(U, M, 4 * L.h, **f32),
-                                  C=torch.empty(U, M, L.h, **f32), H=torch.empty(U, M, L.h, **f32),
-                                  Hp=torch.empty(U, M, L.h, **f32), dH=torch.empty(U, M, L.h, **f32),
-                                  dX=torch.empty(U, M, L.dx, **f32), dlog=torch.empty(U, M, L.max_na, **f32))
-        return self._upd_bufs
+            self._upd_bufs = dict(rc=rc, ZG=torch.empty(U, M, 4 * L.h, **f32), dH=torch.empty(U, M, L.h, **f32),
+                                  dX=torch.empty(U, M, L.dx, **f32))
+        b = self._upd_bufs
+        if not lean and "X" not in b:
+            M = T * b["rc"]
+            b.update(X=torch.empty(U, M, L.dx, **f32), C=torch.empty(U, M, L.h, **f32), H=torch.empty(U, M, L.h, **f32),
+                     Hp=torch.empty(U, M, L.h, **f32), dlog=torch.empty(U, M, L.max_na, **f32))
+        return b
 
     def backward(self, boot: Optional[torch.Tensor], lr: float, beta: float):
         """One A2C update from the stored n_step rollout (agents/models.py:174-183).  `boot` is the
@@ -242,16 +249,23 @@ class BatchedA2C:
         for r0 in range(0, R, self.chunk):
             rc = min(self.chunk, R - r0)
             M = T * rc
-            b = self._bufs(rc)
+            ci = r0 // self.chunk
+            all_tc = use_store and self.bwd_tc and self.fc_bwd_tc and self.wgrad_tc and self.fused_heads
+            b = self._bufs(rc, lean=all_tc)
+            X = Cc = H = Hp = dlog = None
             if b["rc"] == rc:
-                X, ZG, Cc, H, Hp, dH, dX, dlog = (b[k] for k in ("X", "ZG", "C", "H", "Hp", "dH", "dX", "dlog"))
+                ZG, dH, dX = b["ZG"], b["dH"], b["dX"]
+                if not all_tc:
+                    X, Cc, H, Hp, dlog = (b[k] for k in ("X", "C", "H", "Hp", "dlog"))
             else:               # tail chunk: dense temporaries of the right shape
-                X, ZG, Cc, H, Hp, dH, dX, dlog = (torch.empty(U, M, s_, **f32) for s_ in
-                                                  (L.dx, 4 * L.h, L.h, L.h, L.h, L.h, L.dx, L.max_na))
+                ZG, dH, dX = (torch.empty(U, M, s_, **f32) for s_ in (4 * L.h, L.h, L.dx))
+                if not all_tc:
+                    X, Cc, H, Hp, dlog = (torch.empty(U, M, s_, **f32) for s_ in (L.dx, L.h, L.h, L.h, L.max_na))
             obs0 = self.obs_hist[0, r0:]
-            if use_store:
-                # activations of the rollout's forward pass (bf16 store -> fp32 chunk buffers, strided copy)
-                ci = r0 // self.chunk
+            if all_tc:
+                pass        # every consumer reads the bf16 activation store itself
+            elif use_store:
+                # activations of the rollout's forward pass (bf16 store -> fp32 chunk buffers)
                 direct = self.bwd_tc        # the tensor-core BPTT kernel reads gates / c from the store itself
                 _lib.check(lib.tscl_unpack_store(self._h, _p(self.st_x[ci]), _p(self.st_g[ci]), _p(self.st_c[ci]),
                                                  _p(self.st_h[ci]), _p(X), None if direct else _p(ZG),
@@ -265,29 +279,41 @@ class BatchedA2C:
                 _lib.check(lib.tscl_lstm_seq_fwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(H), _p(Hp), _p(self.c_bw),
                                                  _p(self.h_bw), None, None, _p(dpre), C.c_int32(T), C.c_int64(rc),
                                                  C.c_int64(R), C.c_int64(r0), st()))
-            _lib.check(lib.tscl_heads_loss(self._h, _p(self.P), _p(H), _p(self.act_hist[0, r0:]), _p(self.Rs[0, r0:]),
-                                           _p(self.Adv[0, r0:]), C.c_int64(M), C.c_int64(rc), C.c_int64(R * A),
-                                           C.c_float(self.v_coef), C.c_float(beta), C.c_float(scale), _p(dlog),
-                                           _p(dH), _p(self.stats), st()))
-            # head weight / bias gradients (plain batched GEMM + column sums)
-            self.gv["wo"].baddbmm_(H.transpose(1, 2), dlog)
-            self.gv["bo"].add_(dlog.sum(dim=1))
+            hb = _p(self.st_h[ci]) if use_store else None
+            _lib.check(lib.tscl_heads_loss(self._h, _p(self.P), None if all_tc else _p(H), _p(self.act_hist[0, r0:]),
+                                           _p(self.Rs[0, r0:]), _p(self.Adv[0, r0:]), C.c_int64(M), C.c_int64(rc),
+                                           C.c_int64(R * A), C.c_float(self.v_coef), C.c_float(beta), C.c_float(scale),
+                                           None if self.fused_heads else _p(dlog), _p(dH), _p(self.stats),
+                                           hb if all_tc else None, _p(self.G) if self.fused_heads else None, st()))
+            if not self.fused_heads:
+                # head weight / bias gradients (plain batched GEMM + column sums)
+                self.gv["wo"].baddbmm_(H.transpose(1, 2), dlog)
+                self.gv["bo"].add_(dlog.sum(dim=1))
             if self.bwd_tc:
-                gb = (_p(self.st_g[r0 // self.chunk]), _p(self.st_c[r0 // self.chunk])) if use_store else (None, None)
+                gb = (_p(self.st_g[ci]), _p(self.st_c[ci])) if use_store else (None, None)
                 _lib.check(lib.tscl_lstm_seq_bwd_tc(self._h, _p(self.Wt), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
                                                     C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), *gb, st()))
             else:
                 _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
                                                  C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
             dZ = ZG
-            self.gv["wx"].baddbmm_(X.transpose(1, 2), dZ)
-            self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)
-            self.gv["bl"].add_(dZ.sum(dim=1))
+            if self.wgrad_tc:
+                if use_store:
+                    _lib.check(lib.tscl_wgrad_tc(self._h, _p(dZ), None, _p(self.st_x[ci]), None, _p(self.st_h[ci]),
+                                                 _p(self.h_bw), _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R),
+                                                 C.c_int64(r0), _p(self.G), C.c_int32(0), st()))
+                else:
+                    _lib.check(lib.tscl_wgrad_tc(self._h, _p(dZ), _p(X), None, _p(Hp), None, None, None, C.c_int32(T),
+                                                 C.c_int64(rc), C.c_int64(R), C.c_int64(r0), _p(self.G), C.c_int32(0), st()))
+            else:
+                self.gv["wx"].baddbmm_(X.transpose(1, 2), dZ)
+                self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)
+                self.gv["bl"].add_(dZ.sum(dim=1))
             torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
             if self.fc_bwd_tc:
-                xb = _p(self.st_x[r0 // self.chunk]) if use_store else None
-                _lib.check(lib.tscl_fc_bwd_tc(self._h, _p(obs0), _p(X), xb, _p(dX), C.c_int64(M), C.c_int64(rc),
-                                              C.c_int64(R * n_obs), _p(self.G), C.c_int32(0), st()))
+                xb = _p(self.st_x[ci]) if use_store else None
+                _lib.check(lib.tscl_fc_bwd_tc(self._h, _p(obs0), None if all_tc else _p(X), xb, _p(dX), C.c_int64(M),
+                                              C.c_int64(rc), C.c_int64(R * n_obs), _p(self.G), C.c_int32(0), st()))
             else:
                 _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
                                            C.c_int64(R * n_obs), _p(self.G), st()))

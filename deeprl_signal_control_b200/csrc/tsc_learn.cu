@@ -11,6 +11,7 @@
 //   norm2_kernel / rmsprop_kernel   per-agent global-norm clip + TF1 RMSProp   agents/policies.py:54-61
 //
 // Layout conventions: unit u = 2*agent + net (0 = pi, 1 = V); time-major rows m = t*Rc + r.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -323,17 +324,25 @@ __global__ void returns_kernel(const float* __restrict__ rew, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Loss gradients at the heads.  grid (ceil(M/128), A), 128 threads, thread = row m.
+// Loss gradients at the heads.  grid (<= HL_GX row-tile walkers, A), 128 threads, thread = row m of a 128-row tile.
+// With `G` the head weight / bias gradients  dWo += H^T dlog,  dbo += sum dlog  are accumulated here too
+// (rows staged in smem, thread = (hidden unit k, 4 logits); one atomic per output per CTA), and `dlog` may be null.
+// `Hb`: read H from one chunk of the bf16 activation store instead of the fp32 buffer.
+#define HL_GX 96
+#define HL_LD 65
 __global__ void __launch_bounds__(128)
 heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ Hm,
-                  const int32_t* __restrict__ act, const float* __restrict__ Rs, const float* __restrict__ Adv,
-                  int64_t M, int64_t Rc, int64_t stride_t, float v_coef, float beta, float scale,
-                  float* __restrict__ dlog, float* __restrict__ dH, float* __restrict__ stats) {
+                  const __nv_bfloat16* __restrict__ Hb, const int32_t* __restrict__ act, const float* __restrict__ Rs,
+                  const float* __restrict__ Adv, int64_t M, int64_t Rc, int64_t stride_t, float v_coef, float beta,
+                  float scale, float* __restrict__ dlog, float* __restrict__ dH, float* __restrict__ stats,
+                  float* __restrict__ G) {
   extern __shared__ float sm[];
   const int a = blockIdx.y, tid = threadIdx.x, na = d.n_a[a], mna = d.max_na;
   float* sWp = sm;
   float* sWv = sWp + H64 * mna;
   float* sb = sWv + H64;
+  float* sH = sb + 16;                 // [128][HL_LD] rows of H (policy unit, then value unit)
+  float* sdl = sH + 128 * HL_LD;       // [128][9] dlog (8) + dv
   const float* Wp = P + d.off_wo + (int64_t)(2 * a) * H64 * mna;
   const float* Wv = P + d.off_wo + (int64_t)(2 * a + 1) * H64 * mna;
   for (int i = tid; i < H64 * mna; i += 128) sWp[i] = Wp[i];
@@ -341,77 +350,148 @@ heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __res
   for (int i = tid; i < mna; i += 128) sb[i] = P[d.off_bo + (int64_t)(2 * a) * mna + i];
   if (tid == 0) sb[mna] = P[d.off_bo + (int64_t)(2 * a + 1) * mna];
   __syncthreads();
-  const int64_t m = (int64_t)blockIdx.x * 128 + tid;
   float pl = 0.f, vl = 0.f, el = 0.f;
-  if (m < M) {
-    const float4* hp = reinterpret_cast<const float4*>(Hm + ((int64_t)(2 * a) * M + m) * H64);
-    const float4* hv = reinterpret_cast<const float4*>(Hm + ((int64_t)(2 * a + 1) * M + m) * H64);
-    float lg[8];
+  float accp[4] = {0.f, 0.f, 0.f, 0.f}, accv = 0.f, accb = 0.f;
+  const int kk = tid & 63, hh = tid >> 6;
+  const int64_t n_tiles = (M + 127) / 128;
+  float* myH = sH + tid * HL_LD;
+  auto load_row = [&](int64_t off) {       // one row of H (64 values) -> this thread's smem row
+    if (Hb) {
+      const uint4* p4 = reinterpret_cast<const uint4*>(Hb + off);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) lg[j] = j < mna ? sb[j] : 0.f;
-    float v = sb[mna];
-    for (int k4 = 0; k4 < H64 / 4; ++k4) {
-      const float4 x = hp[k4], y = hv[k4];
-      const float xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+      for (int k8 = 0; k8 < H64 / 8; ++k8) {
+        const uint4 x = __ldg(p4 + k8);
+        const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = k4 * 4 + e;
+        for (int e = 0; e < 4; ++e) {
+          myH[k8 * 8 + 2 * e] = __uint_as_float(xw[e] << 16); myH[k8 * 8 + 2 * e + 1] = __uint_as_float(xw[e] & 0xffff0000u);
+        }
+      }
+    } else {
+      const float4* p4 = reinterpret_cast<const float4*>(Hm + off);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < mna) lg[j] = fmaf(xs[e], sWp[k * mna + j], lg[j]);
-        v = fmaf(ys[e], sWv[k], v);
+      for (int k4 = 0; k4 < H64 / 4; ++k4) {
+        const float4 x = __ldg(p4 + k4);
+        myH[4 * k4] = x.x; myH[4 * k4 + 1] = x.y; myH[4 * k4 + 2] = x.z; myH[4 * k4 + 3] = x.w;
       }
     }
-    float mx = -1e30f;
+  };
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t m = tile * 128 + tid;
+    const bool valid = m < M;
+    const int64_t op = ((int64_t)(2 * a) * M + (valid ? m : 0)) * H64, ov = ((int64_t)(2 * a + 1) * M + (valid ? m : 0)) * H64;
+    const int64_t io = valid ? (m / Rc) * stride_t + (m % Rc) * d.A + a : 0;
+    // ---- value unit ----
+    __syncthreads();                       // previous tile's readers of sH / sdl are done
+    float dv = 0.f, v = 0.f, ret = 0.f;
+    if (valid) {
+      load_row(ov);
+      v = sb[mna]; ret = Rs[io];
+#pragma unroll 16
+      for (int k = 0; k < H64; ++k) v = fmaf(myH[k], sWv[k], v);
+      dv = scale * v_coef * (v - ret);
+      float4* dhv = reinterpret_cast<float4*>(dH + ov);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (j < na) mx = fmaxf(mx, lg[j]);
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { lg[j] = j < na ? __expf(lg[j] - mx) : 0.f; s += lg[j]; }
-    const float inv = 1.0f / s;
-    const int64_t io = (m / Rc) * stride_t + (m % Rc) * d.A + a;
-    const int at = act[io];
-    const float adv = Adv[io], ret = Rs[io];
-    float lp[8], ent = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      lg[j] *= inv;                                             // pi_j
-      lp[j] = j < na ? __logf(fminf(fmaxf(lg[j], 1e-10f), 1.0f)) : 0.f;   // agents/policies.py:47
-      ent -= lg[j] * lp[j];
+      for (int k4 = 0; k4 < H64 / 4; ++k4)
+        dhv[k4] = make_float4(dv * sWv[4 * k4], dv * sWv[4 * k4 + 1], dv * sWv[4 * k4 + 2], dv * sWv[4 * k4 + 3]);
+    } else {
+      for (int k = 0; k < H64; ++k) myH[k] = 0.f;
     }
+    sdl[tid * 9 + 8] = dv;
+    if (G) {
+      __syncthreads();
+      if (hh == 0) for (int row = 0; row < 128; ++row) accv = fmaf(sH[row * HL_LD + kk], sdl[row * 9 + 8], accv);
+      __syncthreads();
+    }
+    // ---- policy unit ----
     float dl[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float g = 0.f;
-      if (j < na) g = scale * (-adv * ((j == at ? 1.f : 0.f) - lg[j]) + beta * lg[j] * (lp[j] + ent));
-      dl[j] = g;
-    }
-    const float dv = scale * v_coef * (v - ret);
-    float* dlp = dlog + ((int64_t)(2 * a) * M + m) * mna;
-    float* dlv = dlog + ((int64_t)(2 * a + 1) * M + m) * mna;
+    for (int j = 0; j < 8; ++j) dl[j] = 0.f;
+    if (valid) {
+      load_row(op);
+      float lg[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (j < mna) { dlp[j] = dl[j]; dlv[j] = j == 0 ? dv : 0.f; }
-    float4* dhp = reinterpret_cast<float4*>(dH + ((int64_t)(2 * a) * M + m) * H64);
-    float4* dhv = reinterpret_cast<float4*>(dH + ((int64_t)(2 * a + 1) * M + m) * H64);
-    for (int k4 = 0; k4 < H64 / 4; ++k4) {
-      float o[4], w[4];
+      for (int j = 0; j < 8; ++j) lg[j] = j < mna ? sb[j] : 0.f;
+#pragma unroll 8
+      for (int k = 0; k < H64; ++k) {
+        const float x = myH[k];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = k4 * 4 + e;
-        float t = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) if (j < mna) t = fmaf(dl[j], sWp[k * mna + j], t);
-        o[e] = t; w[e] = dv * sWv[k];
+        for (int j = 0; j < 8; ++j)
+          if (j < mna) lg[j] = fmaf(x, sWp[k * mna + j], lg[j]);
       }
-      dhp[k4] = make_float4(o[0], o[1], o[2], o[3]);
-      dhv[k4] = make_float4(w[0], w[1], w[2], w[3]);
-    }
-    if (a == 0) {
+      float mx = -1e30f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (j == at) pl = -lp[j] * adv;
-      vl = 0.5f * v_coef * (ret - v) * (ret - v);
-      el = -beta * ent;
+      for (int j = 0; j < 8; ++j) if (j < na) mx = fmaxf(mx, lg[j]);
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { lg[j] = j < na ? __expf(lg[j] - mx) : 0.f; s += lg[j]; }
+      const float inv = 1.0f / s;
+      const int at = act[io];
+      const float adv = Adv[io];
+      float lp[8], ent = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        lg[j] *= inv;                                             // pi_j
+        lp[j] = j < na ? __logf(fminf(fmaxf(lg[j], 1e-10f), 1.0f)) : 0.f;   // agents/policies.py:47
+        ent -= lg[j] * lp[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = 0.f;
+        if (j < na) g = scale * (-adv * ((j == at ? 1.f : 0.f) - lg[j]) + beta * lg[j] * (lp[j] + ent));
+        dl[j] = g;
+      }
+      if (dlog) {
+        float* dlp = dlog + ((int64_t)(2 * a) * M + m) * mna;
+        float* dlv = dlog + ((int64_t)(2 * a + 1) * M + m) * mna;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < mna) { dlp[j] = dl[j]; dlv[j] = j == 0 ? dv : 0.f; }
+      }
+      float4* dhp = reinterpret_cast<float4*>(dH + op);
+#pragma unroll 4
+      for (int k4 = 0; k4 < H64 / 4; ++k4) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = k4 * 4 + e;
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < mna) t = fmaf(dl[j], sWp[k * mna + j], t);
+          o[e] = t;
+        }
+        dhp[k4] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      if (a == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j == at) pl += -lp[j] * adv;
+        vl += 0.5f * v_coef * (ret - v) * (ret - v);
+        el += -beta * ent;
+      }
+    } else {
+      for (int k = 0; k < H64; ++k) myH[k] = 0.f;
     }
+    if (G) {      // head weight gradients of this tile: thread = (hidden unit kk, 4 logits)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sdl[tid * 9 + j] = dl[j];
+      __syncthreads();
+      for (int row = 0; row < 128; ++row) {
+        const float x = sH[row * HL_LD + kk];
+        const float* q = sdl + row * 9 + hh * 4;
+        accp[0] = fmaf(x, q[0], accp[0]); accp[1] = fmaf(x, q[1], accp[1]);
+        accp[2] = fmaf(x, q[2], accp[2]); accp[3] = fmaf(x, q[3], accp[3]);
+      }
+      if (tid < 9) for (int row = 0; row < 128; ++row) accb += sdl[row * 9 + tid];
+    }
+  }
+  if (G) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = hh * 4 + jj;
+      if (j < mna) atomicAdd(&G[d.off_wo + ((int64_t)(2 * a) * H64 + kk) * mna + j], accp[jj]);
+    }
+    if (hh == 0) atomicAdd(&G[d.off_wo + ((int64_t)(2 * a + 1) * H64 + kk) * mna], accv);
+    if (tid < mna) atomicAdd(&G[d.off_bo + (int64_t)(2 * a) * mna + tid], accb);
+    if (tid == 8) atomicAdd(&G[d.off_bo + (int64_t)(2 * a + 1) * mna], accb);
   }
   if (a == 0 && stats) {
     for (int o = 16; o; o >>= 1) {
@@ -605,13 +685,16 @@ __global__ void unpack_store_kernel(const uint4* __restrict__ sx, const uint4* _
     b.x = __uint_as_float(v.z << 16); b.y = __uint_as_float(v.z & 0xffff0000u);
     b.z = __uint_as_float(v.w << 16); b.w = __uint_as_float(v.w & 0xffff0000u);
   };
-  for (int64_t i = i0; i < nx8; i += stride) { float4 a, b; cvt(sx[i], a, b); X[2 * i] = a; X[2 * i + 1] = b; }
+  if (X)
+    for (int64_t i = i0; i < nx8; i += stride) { float4 a, b; cvt(sx[i], a, b); X[2 * i] = a; X[2 * i + 1] = b; }
   if (ZG)
     for (int64_t i = i0; i < ng8; i += stride) { float4 a, b; cvt(sg[i], a, b); ZG[2 * i] = a; ZG[2 * i + 1] = b; }
+  if (!Cc && !H && !Hp) return;
   for (int64_t i = i0; i < nh8; i += stride) {
     float4 a, b;
     if (Cc) { cvt(sc[i], a, b); Cc[2 * i] = a; Cc[2 * i + 1] = b; }
-    cvt(shh[i], a, b); H[2 * i] = a; H[2 * i + 1] = b;
+    if (H) { cvt(shh[i], a, b); H[2 * i] = a; H[2 * i + 1] = b; }
+    if (!Hp) continue;
     // element index -> (u, t, r, j8): 8 hidden per item, 8 items per row
     const int64_t row = i >> 3; const int j8 = (int)(i & 7);
     const int64_t r = row % rc; const int64_t ut = row / rc; const int t = (int)(ut % T); const int64_t u = ut / T;
@@ -782,13 +865,15 @@ extern "C" int tscl_returns(tscl_handle* h, const float* rew, const float* val, 
 extern "C" int tscl_heads_loss(tscl_handle* h, const float* params, const float* H, const int32_t* act,
                                const float* Rs, const float* Adv, int64_t M, int64_t Rc, int64_t stride_t,
                                float v_coef, float beta, float scale, float* dlog, float* dH, float* stats,
-                               void* stream) {
-  if (!h || M <= 0) return tsc_set_error("tscl_heads_loss: bad argument");
+                               const void* h_bf16, float* grads, void* stream) {
+  if (!h || M <= 0 || (!H && !h_bf16) || !dH) return tsc_set_error("tscl_heads_loss: bad argument");
+  if (h->d.max_na > 8) return tsc_set_error("tscl_heads_loss: more than 8 actions");
   LCK(cudaSetDevice(h->device));
-  dim3 grid((unsigned)((M + 127) / 128), h->d.A);
-  const int smem = (H64 * h->d.max_na + H64 + h->d.max_na + 1) * 4;
-  heads_loss_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(h->d, params, H, act, Rs, Adv, M, Rc, stride_t, v_coef,
-                                                               beta, scale, dlog, dH, stats);
+  const int64_t n_tiles = (M + 127) / 128;
+  dim3 grid((unsigned)(grads ? (n_tiles < HL_GX ? n_tiles : HL_GX) : n_tiles), h->d.A);
+  const int smem = (H64 * h->d.max_na + H64 + 16 + 128 * HL_LD + 128 * 9) * 4;
+  heads_loss_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(h->d, params, H, (const __nv_bfloat16*)h_bf16, act, Rs, Adv,
+                                                               M, Rc, stride_t, v_coef, beta, scale, dlog, dH, stats, grads);
   LCK(cudaGetLastError());
   return 0;
 }

@@ -1280,3 +1280,234 @@ extern "C" int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, 
   PCK(cudaGetLastError());
   return 0;
 }
+
+// ===================================================================================================
+// LSTM weight gradients on the tensor cores (replaces two cuBLAS GEMMs, a column reduction and the fp32 unpacking of
+// X / Hp):   dWx += X^T dZ,   dWh += Hp^T dZ,   dbl += 1^T dZ      over the rows m = (t, replica) of one chunk.
+// Same MN-major staging as fc_bwd_tc_kernel.  A = [X | Hp | 1] (dx + 64 + 1 columns = up to three M = 128 blocks),
+// B = one 128-column half of dZ; D[block][128 gate columns] accumulates in TMEM (384 columns).  A CTA owns a
+// contiguous tile range of the (unit, half, tile) list and flushes with atomics when (unit, half) changes.
+// Hp is rebuilt from the bf16 activation store: Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0).
+#define WG_A_CHUNKS 40
+#define WG_Z_CHUNKS 16
+#define WG_STAGE ((WG_A_CHUNKS + WG_Z_CHUNKS) * FBT_SBO)
+struct WGradTC {
+  const float* dZ;             // [2A][M][256]
+  const float* X;              // [2A][M][dx] fp32, or
+  const __nv_bfloat16* Xb;     // [2A][M][dx] bf16
+  const float* Hp;             // [2A][M][64] fp32, or
+  const __nv_bfloat16* Hb;     // [2A][T][rc][64] bf16 with h0 / done / T / rc / ld_state / r0
+  const float* h0;
+  const float* done;
+  float* G;
+  int64_t M, rc, ld_state, r0;
+  int T, variant;
+};
+
+__global__ void __launch_bounds__(FBT_THREADS, 1)
+wgrad_tc_kernel(const DDimsTC d, const WGradTC a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(tc_smem + 2 * WG_STAGE);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2);
+  const uint32_t bar0 = smem_u32(sBar);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // never-written A chunks are read by the last M block: keep them finite
+  for (int i = tid; i < 2 * WG_STAGE / 16; i += FBT_THREADS) reinterpret_cast<uint4*>(tc_smem)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  const uint32_t lbo = a.variant ? FBT_SBO : 128, sbo = a.variant ? 128 : FBT_SBO;
+  const int dx = d.dx, ng = dx >> 3, n_xitems = FBT_ROWS * ng;
+  const int nb = (dx + TC_H + 1 + 127) >> 7;        // M blocks
+  const int64_t tpu = (a.M + FBT_ROWS - 1) / FBT_ROWS;
+  const int64_t NT = tpu * 4 * d.A;
+  const int64_t j0 = NT * blockIdx.x / gridDim.x, j1 = NT * (blockIdx.x + 1) / gridDim.x;
+  uint32_t ph0 = 0, ph1 = 0;
+  bool pend0 = false, pend1 = false, first = true;
+  int cur_pu = -1;
+
+  auto flush = [&](int pu) {
+    if (pend0) { mbar_wait(bar0, ph0); ph0 ^= 1; pend0 = false; }
+    if (pend1) { mbar_wait(bar0 + 8, ph1); ph1 ^= 1; pend1 = false; }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int u = pu >> 1, nh = pu & 1;
+    const int q = warp & 3, cq = warp >> 2;
+    const int g0 = nh * 128 + cq * 32;
+    for (int b = 0; b < nb; ++b) {
+      const int ci = b * 128 + q * 32 + lane;
+      float v[32];
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 128 + cq * 32);
+      tmem_ld16(tb, v); tmem_ld16(tb + 16, v + 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* dst = nullptr;
+      if (ci < dx) dst = a.G + d.off_wx + ((int64_t)u * dx + ci) * TC_N + g0;
+      else if (ci < dx + TC_H) dst = a.G + d.off_wh + ((int64_t)u * TC_H + (ci - dx)) * TC_N + g0;
+      else if (ci == dx + TC_H) dst = a.G + d.off_bl + (int64_t)u * TC_N + g0;
+      if (dst) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(dst + e, v[e]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  };
+
+  for (int64_t j = j0; j < j1; ++j) {
+    const int pu = (int)(j / tpu), u = pu >> 1, nh = pu & 1;
+    const int64_t m0 = (j - (int64_t)pu * tpu) * FBT_ROWS;
+    const int s = (int)((j - j0) & 1);
+    if (pu != cur_pu) {
+      if (cur_pu >= 0) flush(cur_pu);
+      cur_pu = pu; first = true;
+    }
+    if (s == 0) { if (pend0) { mbar_wait(bar0, ph0); ph0 ^= 1; pend0 = false; } }
+    else { if (pend1) { mbar_wait(bar0 + 8, ph1); ph1 ^= 1; pend1 = false; } }
+    unsigned char* sA = tc_smem + (size_t)s * WG_STAGE;
+    unsigned char* sZ = sA + (size_t)WG_A_CHUNKS * FBT_SBO;
+    const int rows_valid = (a.M - m0) < FBT_ROWS ? (int)(a.M - m0) : FBT_ROWS;
+    const int64_t rowbase = (int64_t)u * a.M + m0;
+    // ---- B: this half of dZ (fp32 -> bf16), 8 gate columns per item ----
+    {
+      float4 z0[4], z1[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = r * FBT_THREADS + tid, row = i >> 4, g = i & 15;
+        z0[r] = z1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows_valid) {
+          const float4* zp = reinterpret_cast<const float4*>(a.dZ + (rowbase + row) * TC_N + nh * 128 + g * 8);
+          z0[r] = __ldg(zp); z1[r] = __ldg(zp + 1);
+        }
+      }
+      // ---- A: X, 8 columns per item; items are contiguous in global memory ----
+      for (int ib = 0; ib < n_xitems; ib += 4 * FBT_THREADS) {
+        uint4 xb[4];
+        float4 x0[4], x1[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = ib + r * FBT_THREADS + tid;
+          xb[r] = make_uint4(0, 0, 0, 0);
+          x0[r] = x1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < rows_valid * ng) {
+            if (a.Xb) xb[r] = __ldg(reinterpret_cast<const uint4*>(a.Xb + rowbase * dx) + i);
+            else {
+              const float4* xp = reinterpret_cast<const float4*>(a.X + rowbase * dx) + 2 * (int64_t)i;
+              x0[r] = __ldg(xp); x1[r] = __ldg(xp + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = ib + r * FBT_THREADS + tid;
+          if (i < n_xitems) {
+            uint4 o = xb[r];
+            if (!a.Xb) {
+              __align__(16) __nv_bfloat16 t[8] = {__float2bfloat16_rn(x0[r].x), __float2bfloat16_rn(x0[r].y),
+                                                  __float2bfloat16_rn(x0[r].z), __float2bfloat16_rn(x0[r].w),
+                                                  __float2bfloat16_rn(x1[r].x), __float2bfloat16_rn(x1[r].y),
+                                                  __float2bfloat16_rn(x1[r].z), __float2bfloat16_rn(x1[r].w)};
+              o = *reinterpret_cast<const uint4*>(t);
+            }
+            const int row = i / ng, cg = i - row * ng;
+            *reinterpret_cast<uint4*>(sA + (size_t)cg * FBT_SBO + row * 16) = o;
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = r * FBT_THREADS + tid, row = i >> 4, g = i & 15;
+        __align__(16) __nv_bfloat16 t[8] = {__float2bfloat16_rn(z0[r].x), __float2bfloat16_rn(z0[r].y),
+                                            __float2bfloat16_rn(z0[r].z), __float2bfloat16_rn(z0[r].w),
+                                            __float2bfloat16_rn(z1[r].x), __float2bfloat16_rn(z1[r].y),
+                                            __float2bfloat16_rn(z1[r].z), __float2bfloat16_rn(z1[r].w)};
+        *reinterpret_cast<uint4*>(sZ + (size_t)g * FBT_SBO + row * 16) = *reinterpret_cast<const uint4*>(t);
+      }
+    }
+    // ---- A: Hp (8 hidden units per item) and the ones column ----
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = r * FBT_THREADS + tid, row = i >> 3, c = i & 7;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (row < rows_valid) {
+        if (a.Hb) {
+          const int64_t m = m0 + row;
+          const int t = (int)(m / a.rc);
+          if (a.done[t] == 0.f) {
+            if (t > 0) o = __ldg(reinterpret_cast<const uint4*>(a.Hb + (rowbase + row - a.rc) * TC_H + c * 8));
+            else {
+              const float4* hp = reinterpret_cast<const float4*>(a.h0 + ((int64_t)u * a.ld_state + a.r0 + m) * TC_H + c * 8);
+              const float4 p = __ldg(hp), qv = __ldg(hp + 1);
+              __align__(16) __nv_bfloat16 tt[8] = {__float2bfloat16_rn(p.x), __float2bfloat16_rn(p.y), __float2bfloat16_rn(p.z),
+                                                   __float2bfloat16_rn(p.w), __float2bfloat16_rn(qv.x), __float2bfloat16_rn(qv.y),
+                                                   __float2bfloat16_rn(qv.z), __float2bfloat16_rn(qv.w)};
+              o = *reinterpret_cast<const uint4*>(tt);
+            }
+          }
+        } else {
+          const float4* hp = reinterpret_cast<const float4*>(a.Hp + (rowbase + row) * TC_H + c * 8);
+          const float4 p = __ldg(hp), qv = __ldg(hp + 1);
+          __align__(16) __nv_bfloat16 tt[8] = {__float2bfloat16_rn(p.x), __float2bfloat16_rn(p.y), __float2bfloat16_rn(p.z),
+                                               __float2bfloat16_rn(p.w), __float2bfloat16_rn(qv.x), __float2bfloat16_rn(qv.y),
+                                               __float2bfloat16_rn(qv.z), __float2bfloat16_rn(qv.w)};
+          o = *reinterpret_cast<const uint4*>(tt);
+        }
+      }
+      *reinterpret_cast<uint4*>(sA + (size_t)(ng + c) * FBT_SBO + row * 16) = o;
+    }
+    if (tid < FBT_ROWS)
+      *reinterpret_cast<uint4*>(sA + (size_t)(ng + 8) * FBT_SBO + tid * 16) = make_uint4(tid < rows_valid ? 0x3f80u : 0u, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aA = smem_u32(sA), aZ = smem_u32(sZ);
+      for (int b = 0; b < nb; ++b)
+        for (int ks = 0; ks < FBT_ROWS / 16; ++ks)
+          umma_bf16(tmem + b * 128, make_desc(aA + b * 16 * FBT_SBO + ks * 256, lbo, sbo),
+                    make_desc(aZ + ks * 256, lbo, sbo), idesc, (first && ks == 0) ? 0u : 1u);
+      umma_commit(bar0 + 8 * s);
+    }
+    if (s == 0) pend0 = true; else pend1 = true;
+    first = false;
+  }
+  if (cur_pu >= 0) flush(cur_pu);
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+extern "C" int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const float* X, const void* x_bf16, const float* Hp,
+                             const void* h_bf16, const float* h0, const float* done, int32_t T, int64_t rc,
+                             int64_t ld_state, int64_t r0, float* grads, int32_t variant, void* stream) {
+  if (!h || !dZ || (!X && !x_bf16) || (!Hp && !h_bf16) || !grads || T <= 0 || rc <= 0)
+    return tsc_set_error("tscl_wgrad_tc: bad argument");
+  if (h_bf16 && (!h0 || !done)) return tsc_set_error("tscl_wgrad_tc: h_bf16 needs h0 and done");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  if ((d.dx % 8) != 0 || d.dx / 8 + 9 > WG_A_CHUNKS) return tsc_set_error("tscl_wgrad_tc: dx must be a multiple of 8, <= 240");
+  const size_t smem = 2 * (size_t)WG_STAGE + 32;
+  static int attr_dev = -1;
+  if (attr_dev != tscl_device_of(h)) {
+    PCK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = tscl_device_of(h);
+  }
+  int n_sm = 0;
+  PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
+  const int64_t M = (int64_t)T * rc;
+  const int64_t NT = ((M + FBT_ROWS - 1) / FBT_ROWS) * 4 * d.A;
+  const int grid = (int)(NT < n_sm ? NT : n_sm);
+  WGradTC a;
+  a.dZ = dZ; a.X = X; a.Xb = (const __nv_bfloat16*)x_bf16; a.Hp = Hp; a.Hb = (const __nv_bfloat16*)h_bf16; a.h0 = h0;
+  a.done = done; a.G = grads; a.M = M; a.rc = rc; a.ld_state = ld_state; a.r0 = r0; a.T = T; a.variant = variant;
+  wgrad_tc_kernel<<<grid, FBT_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  PCK(cudaGetLastError());
+  return 0;
+}

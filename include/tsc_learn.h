@@ -86,10 +86,14 @@ int tscl_returns(tscl_handle* h, const float* rew, const float* val, const float
  *   H [2A][M][h], act/Rs/Adv rows m -> base + (m / Rc)*stride_t + (m % Rc)*A
  *   dlog [2A][M][max_na] (out; V units use column 0), dH [2A][M][h] (out)
  *   stats [4] += {policy_loss, value_loss, entropy_loss, count} of agent 0 (agents/policies.py:63-72)
- *   scale = 1 / (n_step * total replicas): mean over the batch and over replicas */
+ *   scale = 1 / (n_step * total replicas): mean over the batch and over replicas
+ *   h_bf16 (optional): read H from one chunk of the bf16 activation store ([2A][M][h]) instead of `H`
+ *   grads (optional): also accumulate the head gradients  dWo += H^T dlog, dbo += sum dlog  into the flat
+ *                     gradient vector; `dlog` may then be NULL */
 int tscl_heads_loss(tscl_handle* h, const float* params, const float* H, const int32_t* act, const float* Rs,
                     const float* Adv, int64_t M, int64_t Rc, int64_t stride_t, float v_coef, float beta,
-                    float scale, float* dlog, float* dH, float* stats, void* stream);
+                    float scale, float* dlog, float* dH, float* stats, const void* h_bf16, float* grads,
+                    void* stream);
 
 /* BPTT through the LSTM (reverse of tscl_lstm_seq_fwd).  ZG holds gate activations on entry and
  * dZ (pre-activation gate gradients) on exit; dH holds head gradients on entry. */
@@ -107,6 +111,14 @@ int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* d
 int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, const void* x_bf16, const float* dX, int64_t M,
                    int64_t rows_per_t, int64_t stride_t, float* grads, int32_t variant, void* stream);
 
+/* LSTM weight gradients of one chunk on the tensor cores:  grads.wx += X^T dZ, grads.wh += Hp^T dZ, grads.bl += 1^T dZ
+ * (rows m = t * rc + r, M = T * rc; bf16 operands, fp32 accumulation in TMEM).  X as fp32 `X` or bf16 `x_bf16`
+ * ([2A][M][dx]); Hp as fp32 `Hp` ([2A][M][h]) or rebuilt from the bf16 store chunk `h_bf16` ([2A][T][rc][h]) as
+ * (1 - done[t]) * (t > 0 ? H[t-1] : h0[u][r0 + r]).  `variant` must be 0. */
+int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const float* X, const void* x_bf16, const float* Hp,
+                  const void* h_bf16, const float* h0, const float* done, int32_t T, int64_t rc, int64_t ld_state,
+                  int64_t r0, float* grads, int32_t variant, void* stream);
+
 /* BPTT on the tensor cores (tcgen05): same contract as tscl_lstm_seq_bwd, with the recurrent product dz.Wh^T as
  * a bf16 MMA (M=128, N=64, K=256) per step; wt_bf16 [2A][32][64][8] comes from tscl_pack_wht (refresh after
  * every optimizer step). */
@@ -118,8 +130,8 @@ int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const f
  * activation store instead of ZG / C (ZG is then write-only: it receives dZ). */
 
 /* One replica chunk of the bf16 activation store ([2A][T][rc][w] contiguous) -> fp32 work buffers X, ZG (gates),
- * C, H and Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0[:, r0 + r]).  ZG and C may be NULL (skipped) when the
- * BPTT kernel reads them from the store itself. */
+ * C, H and Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0[:, r0 + r]).  Every output may be NULL (skipped): the
+ * tensor-core kernels read the store themselves. */
 int tscl_unpack_store(tscl_handle* h, const void* st_x, const void* st_g, const void* st_c, const void* st_h, float* X,
                       float* ZG, float* C, float* H, float* Hp, const float* h0, const float* done, int32_t T,
                       int64_t rc, int64_t ld_state, int64_t r0, void* stream);

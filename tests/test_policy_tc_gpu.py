@@ -279,3 +279,56 @@ def test_fc_weight_gradients_tensor_core_kernel(ff, use_bf16_x):
             assert not g2[k].any()
     rel = float((G2 - G1).norm() / G1.norm())
     assert rel < 1e-2, rel
+
+
+@pytest.mark.parametrize("ff,from_store", [(64, True), (0, False), ("monaco", True)])
+def test_lstm_weight_gradients_tensor_core_kernel(ff, from_store):
+    """tscl_wgrad_tc: dWx = X^T dZ, dWh = Hp^T dZ, dbl = 1^T dZ (tcgen05, MN-major bf16 operands) vs a float64
+    contraction of the same bf16-rounded operands (rtol 2e-3); Hp rebuilt from the bf16 store with the done mask."""
+    from deeprl_signal_control_b200 import _lib
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C, _p
+    lay = _layout(ff)
+    T, Rc, R, r0 = 5, 333, 400, 40
+    m = BatchedA2C(lay, R, n_step=T, seed=4)
+    U, M, dx = lay.U, T * Rc, lay.dx
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Xb = torch.relu(torch.randn(U, M, dx, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    Hb = torch.tanh(torch.randn(U, T, Rc, 64, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    h0 = torch.tanh(torch.randn(U, R, 64, device="cuda", generator=g))
+    done = torch.tensor([0, 0, 1, 0, 0], dtype=torch.float32, device="cuda")
+    dZ = torch.randn(U, M, 256, device="cuda", generator=g) * 1e-2
+    # reference Hp (fp32 values of the bf16 operands)
+    Hp = torch.empty(U, T, Rc, 64, device="cuda")
+    Hp[:, 0] = h0[:, r0:r0 + Rc].to(torch.bfloat16).float()
+    Hp[:, 1:] = Hb[:, :-1].float()
+    Hp = (Hp * (1 - done)[None, :, None, None]).reshape(U, M, 64).contiguous()
+    G = torch.zeros_like(m.G)
+    lib = _lib.lib()
+
+    def run(variant, out):
+        if from_store:
+            _lib.check(lib.tscl_wgrad_tc(m._h, _p(dZ), None, _p(Xb), None, _p(Hb), _p(h0), _p(done), C.c_int32(T),
+                                         C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(out), C.c_int32(variant), m._st()))
+        else:
+            Xf = Xb.float().contiguous()
+            _lib.check(lib.tscl_wgrad_tc(m._h, _p(dZ), _p(Xf), None, _p(Hp), None, None, None, C.c_int32(T),
+                                         C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(out), C.c_int32(variant), m._st()))
+        torch.cuda.synchronize()
+    run(0, G)
+    gv = lay.views(G)
+    Zb = dZ.to(torch.bfloat16).double()
+    wx_ref = torch.bmm(Xb.double().transpose(1, 2), Zb)
+    wh_ref = torch.bmm(Hp.double().transpose(1, 2), Zb)
+    bl_ref = Zb.sum(1)
+    errs = [float((gv["wx"].double() - wx_ref).abs().max() / wx_ref.abs().max()),
+            float((gv["wh"].double() - wh_ref).abs().max() / wh_ref.abs().max()),
+            float((gv["bl"].double() - bl_ref).abs().max() / bl_ref.abs().max())]
+    if max(errs) > 2e-3:
+        G3 = torch.zeros_like(m.G)
+        run(1, G3)
+        e3 = float((lay.views(G3)["wx"].double() - wx_ref).abs().max() / wx_ref.abs().max())
+        raise AssertionError("tcgen05 wgrad mismatch: rel errs wx/wh/bl %s (LBO/SBO swapped: wx %.4f)" % (errs, e3))
+    # nothing outside wx / wh / bl is touched
+    for k, v in gv.items():
+        if k not in ("wx", "wh", "bl"):
+            assert not bool(v.any()), k

@@ -134,6 +134,7 @@ class BatchedA2C:
         if self.use_tc:
             _lib.check(_lib.lib().tscl_pack_weights(self._h, _p(self.P), _p(self.Wp), self._st()))
             _lib.check(_lib.lib().tscl_pack_wht(self._h, _p(self.P), _p(self.Wt), self._st()))
+            self.wx_b = self.pv["wx"].to(torch.bfloat16)       # operand of the bf16 library GEMM dX = dZ . Wx^T
             self.kernel_launches += 3
 
     def _mm(self):
@@ -210,18 +211,22 @@ class BatchedA2C:
         self.t += 1
 
     def _bufs(self, rc, lean=False):
-        """fp32 work buffers of one update chunk.  `lean`: every consumer reads the bf16 activation store itself,
-        so only ZG (dZ out), dH and dX exist; the others are allocated the first time a fallback path needs them."""
+        """Work buffers of one update chunk.  `lean`: every consumer reads the bf16 activation store itself and dZ / dX
+        travel as bf16 between the tensor-core kernels, so only dH (fp32), dZb and dXb (bf16) exist; the fp32 set is
+        allocated the first time a fallback path needs it."""
         L, T, U = self.lay, self.T, self.lay.U
         f32 = dict(dtype=torch.float32, device=self.dev)
         if self._upd_bufs is None or self._upd_bufs["rc"] < rc:
             M = T * rc
-            self._upd_bufs = dict(rc=rc, ZG=torch.empty(U, M, 4 * L.h, **f32), dH=torch.empty(U, M, L.h, **f32),
-                                  dX=torch.empty(U, M, L.dx, **f32))
+            self._upd_bufs = dict(rc=rc, dH=torch.empty(U, M, L.h, **f32))
         b = self._upd_bufs
+        M = T * b["rc"]
+        if lean and "dZb" not in b:
+            b.update(dZb=torch.empty(U, M, 4 * L.h, dtype=torch.bfloat16, device=self.dev),
+                     dXb=torch.empty(U, M, L.dx, dtype=torch.bfloat16, device=self.dev))
         if not lean and "X" not in b:
-            M = T * b["rc"]
-            b.update(X=torch.empty(U, M, L.dx, **f32), C=torch.empty(U, M, L.h, **f32), H=torch.empty(U, M, L.h, **f32),
+            b.update(ZG=torch.empty(U, M, 4 * L.h, **f32), dX=torch.empty(U, M, L.dx, **f32),
+                     X=torch.empty(U, M, L.dx, **f32), C=torch.empty(U, M, L.h, **f32), H=torch.empty(U, M, L.h, **f32),
                      Hp=torch.empty(U, M, L.h, **f32), dlog=torch.empty(U, M, L.max_na, **f32))
         return b
 
@@ -252,15 +257,21 @@ class BatchedA2C:
             ci = r0 // self.chunk
             all_tc = use_store and self.bwd_tc and self.fc_bwd_tc and self.wgrad_tc and self.fused_heads
             b = self._bufs(rc, lean=all_tc)
-            X = Cc = H = Hp = dlog = None
+            X = Cc = H = Hp = dlog = ZG = dX = dZb = dXb = None
+            bf16 = dict(dtype=torch.bfloat16, device=self.dev)
             if b["rc"] == rc:
-                ZG, dH, dX = b["ZG"], b["dH"], b["dX"]
-                if not all_tc:
-                    X, Cc, H, Hp, dlog = (b[k] for k in ("X", "C", "H", "Hp", "dlog"))
+                dH = b["dH"]
+                if all_tc:
+                    dZb, dXb = b["dZb"], b["dXb"]
+                else:
+                    ZG, dX, X, Cc, H, Hp, dlog = (b[k] for k in ("ZG", "dX", "X", "C", "H", "Hp", "dlog"))
             else:               # tail chunk: dense temporaries of the right shape
-                ZG, dH, dX = (torch.empty(U, M, s_, **f32) for s_ in (4 * L.h, L.h, L.dx))
-                if not all_tc:
-                    X, Cc, H, Hp, dlog = (torch.empty(U, M, s_, **f32) for s_ in (L.dx, L.h, L.h, L.h, L.max_na))
+                dH = torch.empty(U, M, L.h, **f32)
+                if all_tc:
+                    dZb, dXb = torch.empty(U, M, 4 * L.h, **bf16), torch.empty(U, M, L.dx, **bf16)
+                else:
+                    ZG, dX, X, Cc, H, Hp, dlog = (torch.empty(U, M, s_, **f32) for s_ in
+                                                  (4 * L.h, L.dx, L.dx, L.h, L.h, L.h, L.max_na))
             obs0 = self.obs_hist[0, r0:]
             if all_tc:
                 pass        # every consumer reads the bf16 activation store itself
@@ -292,28 +303,34 @@ class BatchedA2C:
             if self.bwd_tc:
                 gb = (_p(self.st_g[ci]), _p(self.st_c[ci])) if use_store else (None, None)
                 _lib.check(lib.tscl_lstm_seq_bwd_tc(self._h, _p(self.Wt), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
-                                                    C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), *gb, st()))
+                                                    C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), *gb,
+                                                    _p(dZb), st()))
             else:
                 _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
                                                  C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
             dZ = ZG
             if self.wgrad_tc:
                 if use_store:
-                    _lib.check(lib.tscl_wgrad_tc(self._h, _p(dZ), None, _p(self.st_x[ci]), None, _p(self.st_h[ci]),
+                    _lib.check(lib.tscl_wgrad_tc(self._h, _p(dZ), _p(dZb), None, _p(self.st_x[ci]), None, _p(self.st_h[ci]),
                                                  _p(self.h_bw), _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R),
                                                  C.c_int64(r0), _p(self.G), C.c_int32(0), st()))
                 else:
-                    _lib.check(lib.tscl_wgrad_tc(self._h, _p(dZ), _p(X), None, _p(Hp), None, None, None, C.c_int32(T),
+                    _lib.check(lib.tscl_wgrad_tc(self._h, _p(dZ), None, _p(X), None, _p(Hp), None, None, None, C.c_int32(T),
                                                  C.c_int64(rc), C.c_int64(R), C.c_int64(r0), _p(self.G), C.c_int32(0), st()))
             else:
                 self.gv["wx"].baddbmm_(X.transpose(1, 2), dZ)
                 self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)
                 self.gv["bl"].add_(dZ.sum(dim=1))
-            torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
+            # dX = dZ . Wx^T: plain library GEMM (bf16 operands when dZ travels as bf16, else fp32 / TF32)
+            if all_tc:
+                torch.bmm(dZb, self.wx_b.transpose(1, 2), out=dXb)
+            else:
+                torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
             if self.fc_bwd_tc:
                 xb = _p(self.st_x[ci]) if use_store else None
-                _lib.check(lib.tscl_fc_bwd_tc(self._h, _p(obs0), None if all_tc else _p(X), xb, _p(dX), C.c_int64(M),
-                                              C.c_int64(rc), C.c_int64(R * n_obs), _p(self.G), C.c_int32(0), st()))
+                _lib.check(lib.tscl_fc_bwd_tc(self._h, _p(obs0), None if all_tc else _p(X), xb, _p(dX), _p(dXb),
+                                              C.c_int64(M), C.c_int64(rc), C.c_int64(R * n_obs), _p(self.G), C.c_int32(0),
+                                              st()))
             else:
                 _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
                                            C.c_int64(R * n_obs), _p(self.G), st()))

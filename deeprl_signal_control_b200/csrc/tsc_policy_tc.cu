@@ -525,6 +525,13 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     const int u = (int)(it / n_tiles);
     const int64_t r0 = (it - (int64_t)u * n_tiles) * TC_M;
     const int ag = u >> 1;
+    // row of the activation store (chunk-outermost [R/rc][2A][T][rc][w]) for tile row `row`: one division per item
+    const int64_t st_c0 = r0 / a.rc, st_rin0 = r0 - st_c0 * a.rc;
+    auto store_row = [&](int row) -> int64_t {
+      int64_t c = st_c0, rin = st_rin0 + row;
+      while (rin >= a.rc) { rin -= a.rc; ++c; }
+      return ((c * (2 * d.A) + u) * a.T + a.t) * a.rc + rin;
+    };
     const __nv_bfloat16* Wu = a.Wp + (int64_t)u * wp_stride(d.dx);
     __syncthreads();      // previous tile fully retired (sRed, sA, TMEM readers)
     if (u != cur_u) {
@@ -620,8 +627,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
         *reinterpret_cast<uint4*>(sA + (size_t)((c0 >> 3) + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
         if (a.st_x && r0 + row < a.R) {
-          const int64_t rr = r0 + row;
-          const int64_t m = (((rr / a.rc) * (2 * d.A) + u) * a.T + a.t) * a.rc + rr % a.rc;
+          const int64_t m = store_row(row);
           uint4* o = reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0));
           o[0] = *reinterpret_cast<const uint4*>(v); o[1] = *reinterpret_cast<const uint4*>(v + 8);
         }
@@ -707,7 +713,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
           for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
         }
         if (valid && a.st_g) {
-          const int64_t m = (((r / a.rc) * (2 * d.A) + u) * a.T + a.t) * a.rc + r % a.rc;
+          const int64_t m = store_row((int)(r - r0));
           const int jo = half * 32 + jb * 16;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -846,9 +852,12 @@ struct BwdTC {
   int64_t Rc, ld_state, r0;
   const __nv_bfloat16* Gb;   // optional: gate activations / c_t straight from the bf16 activation store
   const __nv_bfloat16* Cb;   //           ([2A][T*Rc][256] / [..][64]); when set, ZG is write-only and C is unused
+  __nv_bfloat16* dZb;        // optional: dZ as bf16 [2A][T*Rc][256] (operand of the tensor-core weight-gradient kernels);
+                             //           ZG may then be null (needs Gb / Cb)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+#define BW_THREADS 512      // thread = (replica row, 16 hidden units): 16 warps keep the issue slots busy between the per-step MMAs
+__global__ void __launch_bounds__(BW_THREADS, 1)
 lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* sB = tc_smem;                       // 32 * 1024  : Wh^T image
@@ -874,8 +883,17 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
   const int64_t n_items = n_tiles * 2 * d.A;
   int cur_u = -1;
   uint32_t parity = 0;
-  const int q = warp & 3, half = warp >> 2;
-  const int row = q * 32 + lane;
+  const int q = warp & 3, qt = warp >> 2;            // TMEM lane quadrant, hidden-unit quarter
+  const int row = q * 32 + lane, jq = qt * 16;
+  auto bf8 = [](const uint4 v, float* o) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  };
+  auto f8 = [](const float* p, float* o) {
+    const float4 x = reinterpret_cast<const float4*>(p)[0], y = reinterpret_cast<const float4*>(p)[1];
+    o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
+  };
   for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int u = (int)(it / n_tiles);
     const int64_t r = (it - (int64_t)u * n_tiles) * TC_M + row;
@@ -885,84 +903,56 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
       cur_u = u;
       const uint4* src = reinterpret_cast<const uint4*>(a.Wt + (int64_t)u * BW_KC * TC_H * 8);
       uint4* dst = reinterpret_cast<uint4*>(sB);
-      for (int i = tid; i < BW_KC * TC_H; i += TC_THREADS) dst[i] = src[i];
+      for (int i = tid; i < BW_KC * TC_H; i += BW_THREADS) dst[i] = src[i];
     }
-    float dc[32], dhc[32];
+    float dc[16], dhc[16];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) { dc[e] = 0.f; dhc[e] = 0.f; }
+    for (int e = 0; e < 16; ++e) { dc[e] = 0.f; dhc[e] = 0.f; }
     for (int t = a.T - 1; t >= 0; --t) {
       const float keep = 1.0f - a.done[t];
       const int64_t m = ((int64_t)u * a.T + t) * a.Rc + (valid ? r : 0);
       if (t > 0 && valid) {      // pull step t-1's operands towards L2 while step t is being processed
         const int64_t mp = m - a.Rc;
-        const int jo0 = half * 32;
         if (a.Gb) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Gb + mp * TC_N + g * 64 + jo0));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + mp * TC_H + jo0));
-          if (t > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + (mp - a.Rc) * TC_H + jo0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Gb + mp * TC_N + qt * 64));
+          if (qt == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + mp * TC_H));
+          if (qt == 1 && t > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + (mp - a.Rc) * TC_H));
         } else {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + g * 64 + jo0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + g * 64 + jo0 + 16));
-          }
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.C + mp * TC_H + jo0));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.C + mp * TC_H + jo0 + 16));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + qt * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + qt * 64 + 32));
+          if (qt < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.C + mp * TC_H + qt * 32));
         }
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + jo0));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + jo0 + 16));
+        if (qt >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + (qt - 2) * 32));
       }
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb) {
-        const int jo = half * 32 + jb * 16;
-        float gi[16], gf[16], go[16], gu[16], ct[16], cp[16], dh[16];
-        if (valid && a.Gb) {
-          auto ld16 = [](const __nv_bfloat16* p, float* o) {
-            const uint4 v0 = reinterpret_cast<const uint4*>(p)[0], v1 = reinterpret_cast<const uint4*>(p)[1];
-            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-          };
-          const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
-          ld16(zb, gi); ld16(zb + 64, gf); ld16(zb + 128, go); ld16(zb + 192, gu);
-          ld16(a.Cb + m * TC_H + jo, ct);
-          if (t > 0) ld16(a.Cb + (m - a.Rc) * TC_H + jo, cp);
-          else {
-            const float4* pp = reinterpret_cast<const float4*>(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo);
-#pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) { const float4 x = pp[e4]; cp[4 * e4] = x.x; cp[4 * e4 + 1] = x.y; cp[4 * e4 + 2] = x.z; cp[4 * e4 + 3] = x.w; }
+        const int jo = jq + jb * 8;
+        float gi[8], gf[8], go[8], gu[8], ct[8], cp[8], dh[8];
+        if (valid) {
+          if (a.Gb) {
+            const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
+            bf8(*reinterpret_cast<const uint4*>(zb), gi); bf8(*reinterpret_cast<const uint4*>(zb + 64), gf);
+            bf8(*reinterpret_cast<const uint4*>(zb + 128), go); bf8(*reinterpret_cast<const uint4*>(zb + 192), gu);
+            bf8(*reinterpret_cast<const uint4*>(a.Cb + m * TC_H + jo), ct);
+            if (t > 0) bf8(*reinterpret_cast<const uint4*>(a.Cb + (m - a.Rc) * TC_H + jo), cp);
+            else f8(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo, cp);
+          } else {
+            const float* z = a.ZG + m * TC_N + jo;
+            f8(z, gi); f8(z + 64, gf); f8(z + 128, go); f8(z + 192, gu);
+            f8(a.C + m * TC_H + jo, ct);
+            f8(t > 0 ? a.C + (m - a.Rc) * TC_H + jo : a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo, cp);
           }
-          const float4* hh = reinterpret_cast<const float4*>(a.dH + m * TC_H + jo);
+          f8(a.dH + m * TC_H + jo, dh);
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) { const float4 x = hh[e4]; dh[4 * e4] = x.x; dh[4 * e4 + 1] = x.y; dh[4 * e4 + 2] = x.z; dh[4 * e4 + 3] = x.w; }
-#pragma unroll
-          for (int e = 0; e < 16; ++e) cp[e] *= keep;
-        } else if (valid) {
-          const float4* z = reinterpret_cast<const float4*>(a.ZG + m * TC_N + jo);
-          const float4* cc = reinterpret_cast<const float4*>(a.C + m * TC_H + jo);
-          const float4* pp = t > 0 ? reinterpret_cast<const float4*>(a.C + (m - a.Rc) * TC_H + jo)
-                                   : reinterpret_cast<const float4*>(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo);
-          const float4* hh = reinterpret_cast<const float4*>(a.dH + m * TC_H + jo);
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 x0 = z[e4], x1 = z[16 + e4], x2 = z[32 + e4], x3 = z[48 + e4], x4 = cc[e4], x5 = pp[e4], x6 = hh[e4];
-            gi[4 * e4] = x0.x; gi[4 * e4 + 1] = x0.y; gi[4 * e4 + 2] = x0.z; gi[4 * e4 + 3] = x0.w;
-            gf[4 * e4] = x1.x; gf[4 * e4 + 1] = x1.y; gf[4 * e4 + 2] = x1.z; gf[4 * e4 + 3] = x1.w;
-            go[4 * e4] = x2.x; go[4 * e4 + 1] = x2.y; go[4 * e4 + 2] = x2.z; go[4 * e4 + 3] = x2.w;
-            gu[4 * e4] = x3.x; gu[4 * e4 + 1] = x3.y; gu[4 * e4 + 2] = x3.z; gu[4 * e4 + 3] = x3.w;
-            ct[4 * e4] = x4.x; ct[4 * e4 + 1] = x4.y; ct[4 * e4 + 2] = x4.z; ct[4 * e4 + 3] = x4.w;
-            cp[4 * e4] = x5.x * keep; cp[4 * e4 + 1] = x5.y * keep; cp[4 * e4 + 2] = x5.z * keep; cp[4 * e4 + 3] = x5.w * keep;
-            dh[4 * e4] = x6.x; dh[4 * e4 + 1] = x6.y; dh[4 * e4 + 2] = x6.z; dh[4 * e4 + 3] = x6.w;
-          }
+          for (int e = 0; e < 8; ++e) cp[e] *= keep;
         } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) { gi[e] = gf[e] = go[e] = gu[e] = ct[e] = cp[e] = dh[e] = 0.f; }
+          for (int e = 0; e < 8; ++e) { gi[e] = gf[e] = go[e] = gu[e] = ct[e] = cp[e] = dh[e] = 0.f; }
         }
-        float dzi[16], dzf[16], dzo[16], dzu[16];
+        float dzi[8], dzf[8], dzo[8], dzu[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int k = jb * 16 + e;
+        for (int e = 0; e < 8; ++e) {
+          const int k = jb * 8 + e;
           const float dht = dh[e] + dhc[k];
           const float tc = tanh_fast(ct[e]);
           const float dcc = dc[k] + dht * go[e] * (1.0f - tc * tc);
@@ -972,26 +962,23 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
           dzu[e] = dcc * gi[e] * (1.0f - gu[e] * gu[e]);
           dc[k] = dcc * gf[e] * keep;
         }
-        if (valid) {
+        const float* srcs[4] = {dzi, dzf, dzo, dzu};
+        if (valid && a.ZG) {
           float4* z = reinterpret_cast<float4*>(a.ZG + m * TC_N + jo);
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            z[e4] = make_float4(dzi[4 * e4], dzi[4 * e4 + 1], dzi[4 * e4 + 2], dzi[4 * e4 + 3]);
-            z[16 + e4] = make_float4(dzf[4 * e4], dzf[4 * e4 + 1], dzf[4 * e4 + 2], dzf[4 * e4 + 3]);
-            z[32 + e4] = make_float4(dzo[4 * e4], dzo[4 * e4 + 1], dzo[4 * e4 + 2], dzo[4 * e4 + 3]);
-            z[48 + e4] = make_float4(dzu[4 * e4], dzu[4 * e4 + 1], dzu[4 * e4 + 2], dzu[4 * e4 + 3]);
+          for (int g = 0; g < 4; ++g) {
+            z[g * 16] = make_float4(srcs[g][0], srcs[g][1], srcs[g][2], srcs[g][3]);
+            z[g * 16 + 1] = make_float4(srcs[g][4], srcs[g][5], srcs[g][6], srcs[g][7]);
           }
         }
-        // bf16 copies into the A tile: column g*64 + jo + e  -> chunk (g*64 + jo)/8 (+1), row `row`
-        __align__(16) __nv_bfloat16 v[16];
-        const float* srcs[4] = {dzi, dzf, dzo, dzu};
+        // bf16 copies into the A tile: columns g*64 + jo .. +8  ->  chunk (g*64 + jo)/8, row `row`
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __float2bfloat16_rn(srcs[g][e]);
-          const int kc = (g * 64 + jo) >> 3;
-          *reinterpret_cast<uint4*>(sA + (size_t)kc * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
-          *reinterpret_cast<uint4*>(sA + (size_t)(kc + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
+          for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(srcs[g][e]);
+          *reinterpret_cast<uint4*>(sA + (size_t)((g * 64 + jo) >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+          if (valid && a.dZb) *reinterpret_cast<uint4*>(a.dZb + m * TC_N + g * 64 + jo) = *reinterpret_cast<const uint4*>(v);
         }
       }
       if (keep != 0.f && t > 0) {
@@ -1011,15 +998,14 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
         mbar_wait(bar, parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float dhp[32];
-        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
-        tmem_ld16(tb, dhp); tmem_ld16(tb + 16, dhp + 16);
+        float dhp[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)jq, dhp);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int e = 0; e < 32; ++e) dhc[e] = dhp[e] * keep;
+        for (int e = 0; e < 16; ++e) dhc[e] = dhp[e] * keep;
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) dhc[e] = 0.f;
+        for (int e = 0; e < 16; ++e) dhc[e] = 0.f;
       }
     }
   }
@@ -1039,8 +1025,10 @@ extern "C" int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16,
 
 extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH,
                                     const float* c0, const float* done, int32_t T, int64_t Rc, int64_t ld_state,
-                                    int64_t r0, const void* gates_bf16, const void* c_bf16, void* stream) {
+                                    int64_t r0, const void* gates_bf16, const void* c_bf16, void* dz_bf16, void* stream) {
   if (!h || !wt_bf16 || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_bwd_tc: bad argument");
+  if (!ZG && !(gates_bf16 && c_bf16 && dz_bf16)) return tsc_set_error("tscl_lstm_seq_bwd_tc: ZG may be null only with gates_bf16, c_bf16 and dz_bf16");
+  if ((gates_bf16 == nullptr) != (c_bf16 == nullptr)) return tsc_set_error("tscl_lstm_seq_bwd_tc: gates_bf16 and c_bf16 go together");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
   const size_t smem = BW_KC * 1024 + BW_KC * 2048 + 16;
@@ -1052,11 +1040,11 @@ extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* 
   int n_sm = 0;
   PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
   const int64_t n_items = ((Rc + TC_M - 1) / TC_M) * 2 * d.A;
-  const int grid = (int)(n_items < 2 * n_sm ? n_items : 2 * n_sm);   // 96 KB smem, <=255 regs: 1-2 CTAs per SM
+  const int grid = (int)(n_items < 2 * n_sm ? n_items : 2 * n_sm);   // 96 KB smem: two 512-thread CTAs per SM when registers allow
   BwdTC a;
   a.Wt = (const __nv_bfloat16*)wt_bf16; a.ZG = ZG; a.C = C; a.dH = dH; a.c0 = c0; a.done = done; a.T = T; a.Rc = Rc;
-  a.ld_state = ld_state; a.r0 = r0; a.Gb = (const __nv_bfloat16*)gates_bf16; a.Cb = (const __nv_bfloat16*)c_bf16;
-  lstm_bwd_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  a.ld_state = ld_state; a.r0 = r0; a.Gb = (const __nv_bfloat16*)gates_bf16; a.Cb = (const __nv_bfloat16*)c_bf16; a.dZb = (__nv_bfloat16*)dz_bf16;
+  lstm_bwd_tc_kernel<<<grid, BW_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
 }
@@ -1080,7 +1068,8 @@ struct FcBwdTC {
   const float* obs;            // rows as tscl_fc_embed
   const float* X;              // [2A][M][dx] fp32 activations, or
   const __nv_bfloat16* Xb;     // [2A][M][dx] bf16 activations (one chunk of the activation store)
-  const float* dX;             // [2A][M][dx]
+  const float* dX;             // [2A][M][dx] fp32, or
+  const __nv_bfloat16* dXb;    // [2A][M][dx] bf16
   float* G;
   int64_t M, rows_per_t, stride_t;
   int variant;                 // 1: LBO/SBO swapped (descriptor diagnosis)
@@ -1109,6 +1098,7 @@ fc_bwd_tc_kernel(const DDimsTC d, const FcBwdTC a) {
                          ((uint32_t)(128 >> 4) << 24);
   const uint32_t lbo = a.variant ? FBT_SBO : 128, sbo = a.variant ? 128 : FBT_SBO;
   const int dx = d.dx, ng = dx >> 3, n_items = FBT_ROWS * ng;
+  const uint32_t ng_magic = (1u << 20) / (uint32_t)ng + 1u;      // i / ng == (i * magic) >> 20 for i < 4096, ng <= 32
   const int64_t tpu = (a.M + FBT_ROWS - 1) / FBT_ROWS;
   const int64_t NT = tpu * 2 * d.A;
   const int64_t j0 = NT * blockIdx.x / gridDim.x, j1 = NT * (blockIdx.x + 1) / gridDim.x;
@@ -1172,51 +1162,130 @@ fc_bwd_tc_kernel(const DDimsTC d, const FcBwdTC a) {
     const int rows_valid = (a.M - m0) < FBT_ROWS ? (int)(a.M - m0) : FBT_ROWS;
     const int items_valid = rows_valid * ng;
     const int64_t base = ((int64_t)u * a.M + m0) * dx;
-    // ---- A: masked dX, 8 columns (one 16 B chunk row) per item; items are contiguous in global memory ----
-    for (int ib = 0; ib < n_items; ib += 4 * FBT_THREADS) {
-      float4 g0[4], g1[4];
-      uint4 xb[4];
-      float4 x0[4], x1[4];
+    if (j + 1 < j1) {      // pull the next tile towards L2 while this one is converted and multiplied
+      const int un = (int)((j + 1) / tpu);
+      const int64_t m0n = (j + 1 - (int64_t)un * tpu) * FBT_ROWS;
+      const int rvn = (a.M - m0n) < FBT_ROWS ? (int)(a.M - m0n) : FBT_ROWS;
+      const int64_t basen = ((int64_t)un * a.M + m0n) * dx;
+      const int64_t nbytes = (int64_t)rvn * dx * 4;
+      if (a.dXb) {
+        const char* pd = reinterpret_cast<const char*>(a.dXb + basen);
+        for (int64_t o = (int64_t)tid * 128; o < nbytes / 2; o += FBT_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + o));
+      } else {
+        const char* pd = reinterpret_cast<const char*>(a.dX + basen);
+        for (int64_t o = (int64_t)tid * 128; o < nbytes; o += FBT_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + o));
+      }
+      if (a.Xb) {
+        const char* px = reinterpret_cast<const char*>(a.Xb + basen);
+        for (int64_t o = (int64_t)tid * 128; o < nbytes / 2; o += FBT_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+      }
+      if (tid < rvn) {
+        const int64_t m = m0n + tid;
+        const float* op = a.obs + (m / a.rows_per_t) * a.stride_t + (m % a.rows_per_t) * d.n_obs + d.obs_off[un >> 1];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(op));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(op + 32));
+      }
+    }
+    // ---- B loads first (observation slice of this thread's 8 input slots, 2 rows): their latency overlaps the A staging ----
+    float ov[(FBT_ROWS * 8) / FBT_THREADS][8];
+    {
+      const int64_t tq = m0 / a.rows_per_t, rem0 = m0 - tq * a.rows_per_t;      // one division per tile
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = ib + r * FBT_THREADS + tid;
-        g0[r] = g1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        xb[r] = make_uint4(0, 0, 0, 0);
-        x0[r] = x1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < items_valid) {
-          const float4* gp = reinterpret_cast<const float4*>(a.dX + base) + 2 * (int64_t)i;
-          g0[r] = __ldg(gp); g1[r] = __ldg(gp + 1);
-          if (a.Xb) xb[r] = __ldg(reinterpret_cast<const uint4*>(a.Xb + base) + i);
-          else {
-            const float4* xp = reinterpret_cast<const float4*>(a.X + base) + 2 * (int64_t)i;
-            x0[r] = __ldg(xp); x1[r] = __ldg(xp + 1);
-          }
+      for (int r = 0; r < (FBT_ROWS * 8) / FBT_THREADS; ++r) {
+        const int row = (r * FBT_THREADS + tid) >> 3;
+        if (row < rows_valid) {
+          int64_t tt = tq, rem = rem0 + row;
+          while (rem >= a.rows_per_t) { rem -= a.rows_per_t; ++tt; }
+          const float* op = a.obs + tt * a.stride_t + rem * d.n_obs + ooff;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ov[r][e] = src[e] >= 0 ? __ldg(op + src[e]) : (src[e] == -2 ? 1.0f : 0.f);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ov[r][e] = 0.f;
         }
       }
+    }
+    if (a.dXb && a.Xb) {
+      // ---- A, bf16 in / bf16 out: all loads of the tile in flight at once, relu mask as packed 16-bit integer ops ----
+      uint4 gb[8], xm[8];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = ib + r * FBT_THREADS + tid;
+      for (int k = 0; k < 8; ++k) {
+        const int i = k * FBT_THREADS + tid;
+        gb[k] = make_uint4(0, 0, 0, 0); xm[k] = make_uint4(0, 0, 0, 0);
+        if (i < items_valid) {
+          gb[k] = __ldg(reinterpret_cast<const uint4*>(a.dXb + base) + i);
+          xm[k] = __ldg(reinterpret_cast<const uint4*>(a.Xb + base) + i);
+        }
+      }
+      auto keep2 = [](uint32_t x) -> uint32_t {      // 0xFFFF per 16-bit half where the bf16 value is > 0
+        const uint32_t nz = ((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) & ~x & 0x80008000u;
+        return (nz >> 15) * 0xFFFFu;
+      };
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = k * FBT_THREADS + tid;
         if (i < n_items) {
-          const float gv[8] = {g0[r].x, g0[r].y, g0[r].z, g0[r].w, g1[r].x, g1[r].y, g1[r].z, g1[r].w};
-          bool pos[8];
-          if (a.Xb) {
-            const uint32_t w[4] = {xb[r].x, xb[r].y, xb[r].z, xb[r].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t lo = w[e] & 0xffffu, hi = w[e] >> 16;
-              pos[2 * e] = (lo & 0x8000u) == 0 && (lo & 0x7fffu) != 0;
-              pos[2 * e + 1] = (hi & 0x8000u) == 0 && (hi & 0x7fffu) != 0;
+          const uint4 o = make_uint4(gb[k].x & keep2(xm[k].x), gb[k].y & keep2(xm[k].y), gb[k].z & keep2(xm[k].z),
+                                     gb[k].w & keep2(xm[k].w));
+          const int row = (int)(((uint32_t)i * ng_magic) >> 20), cg = i - row * ng;
+          *reinterpret_cast<uint4*>(sA + (size_t)cg * FBT_SBO + row * 16) = o;
+        }
+      }
+    } else {
+      // ---- A: masked dX, 8 columns (one 16 B chunk row) per item; items are contiguous in global memory ----
+      for (int ib = 0; ib < n_items; ib += 4 * FBT_THREADS) {
+        float4 g0[4], g1[4];
+        uint4 xb[4];
+        float4 x0[4], x1[4];
+  #pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = ib + r * FBT_THREADS + tid;
+          g0[r] = g1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          xb[r] = make_uint4(0, 0, 0, 0);
+          x0[r] = x1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < items_valid) {
+            if (a.dXb) {
+              const uint4 gb = __ldg(reinterpret_cast<const uint4*>(a.dXb + base) + i);
+              g0[r] = make_float4(__uint_as_float(gb.x << 16), __uint_as_float(gb.x & 0xffff0000u), __uint_as_float(gb.y << 16),
+                                  __uint_as_float(gb.y & 0xffff0000u));
+              g1[r] = make_float4(__uint_as_float(gb.z << 16), __uint_as_float(gb.z & 0xffff0000u), __uint_as_float(gb.w << 16),
+                                  __uint_as_float(gb.w & 0xffff0000u));
+            } else {
+              const float4* gp = reinterpret_cast<const float4*>(a.dX + base) + 2 * (int64_t)i;
+              g0[r] = __ldg(gp); g1[r] = __ldg(gp + 1);
             }
-          } else {
-            const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pos[e] = xv[e] > 0.f;
+            if (a.Xb) xb[r] = __ldg(reinterpret_cast<const uint4*>(a.Xb + base) + i);
+            else {
+              const float4* xp = reinterpret_cast<const float4*>(a.X + base) + 2 * (int64_t)i;
+              x0[r] = __ldg(xp); x1[r] = __ldg(xp + 1);
+            }
           }
-          __align__(16) __nv_bfloat16 o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(pos[e] ? gv[e] : 0.f);
-          const int row = i / ng, cg = i - row * ng;
-          *reinterpret_cast<uint4*>(sA + (size_t)cg * FBT_SBO + row * 16) = *reinterpret_cast<const uint4*>(o);
+        }
+  #pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = ib + r * FBT_THREADS + tid;
+          if (i < n_items) {
+            const float gv[8] = {g0[r].x, g0[r].y, g0[r].z, g0[r].w, g1[r].x, g1[r].y, g1[r].z, g1[r].w};
+            bool pos[8];
+            if (a.Xb) {
+              const uint32_t w[4] = {xb[r].x, xb[r].y, xb[r].z, xb[r].w};
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t lo = w[e] & 0xffffu, hi = w[e] >> 16;
+                pos[2 * e] = (lo & 0x8000u) == 0 && (lo & 0x7fffu) != 0;
+                pos[2 * e + 1] = (hi & 0x8000u) == 0 && (hi & 0x7fffu) != 0;
+              }
+            } else {
+              const float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+  #pragma unroll
+              for (int e = 0; e < 8; ++e) pos[e] = xv[e] > 0.f;
+            }
+            __align__(16) __nv_bfloat16 o[8];
+  #pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(pos[e] ? gv[e] : 0.f);
+            const int row = i / ng, cg = i - row * ng;
+            *reinterpret_cast<uint4*>(sA + (size_t)cg * FBT_SBO + row * 16) = *reinterpret_cast<const uint4*>(o);
+          }
         }
       }
     }
@@ -1225,15 +1294,8 @@ fc_bwd_tc_kernel(const DDimsTC d, const FcBwdTC a) {
     for (int r = 0; r < (FBT_ROWS * 8) / FBT_THREADS; ++r) {
       const int row = (r * FBT_THREADS + tid) >> 3;
       __align__(16) __nv_bfloat16 o[8];
-      if (row < rows_valid) {
-        const int64_t m = m0 + row;
-        const float* op = a.obs + (m / a.rows_per_t) * a.stride_t + (m % a.rows_per_t) * d.n_obs + ooff;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(src[e] >= 0 ? __ldg(op + src[e]) : (src[e] == -2 ? 1.0f : 0.f));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(0.f);
-      }
+      for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(ov[r][e]);
       *reinterpret_cast<uint4*>(sB + (size_t)bc * FBT_SBO + row * 16) = *reinterpret_cast<const uint4*>(o);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1257,8 +1319,9 @@ fc_bwd_tc_kernel(const DDimsTC d, const FcBwdTC a) {
 }
 
 extern "C" int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, const void* x_bf16, const float* dX,
-                              int64_t M, int64_t rows_per_t, int64_t stride_t, float* grads, int32_t variant, void* stream) {
-  if (!h || !obs || (!X && !x_bf16) || !dX || !grads || M <= 0) return tsc_set_error("tscl_fc_bwd_tc: bad argument");
+                              const void* dx_bf16, int64_t M, int64_t rows_per_t, int64_t stride_t, float* grads,
+                              int32_t variant, void* stream) {
+  if (!h || !obs || (!X && !x_bf16) || (!dX && !dx_bf16) || !grads || M <= 0) return tsc_set_error("tscl_fc_bwd_tc: bad argument");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
   if ((d.dx % 8) != 0 || d.dx > 256) return tsc_set_error("tscl_fc_bwd_tc: dx must be a multiple of 8, <= 256");
@@ -1274,7 +1337,8 @@ extern "C" int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, 
   const int64_t NT = ((M + FBT_ROWS - 1) / FBT_ROWS) * 2 * d.A;
   const int grid = (int)(NT < n_sm ? NT : n_sm);
   FcBwdTC a;
-  a.obs = obs; a.X = X; a.Xb = (const __nv_bfloat16*)x_bf16; a.dX = dX; a.G = grads; a.M = M; a.rows_per_t = rows_per_t;
+  a.obs = obs; a.X = X; a.Xb = (const __nv_bfloat16*)x_bf16; a.dX = dX; a.dXb = (const __nv_bfloat16*)dx_bf16; a.G = grads; a.M = M;
+  a.rows_per_t = rows_per_t;
   a.stride_t = stride_t; a.variant = variant;
   fc_bwd_tc_kernel<<<grid, FBT_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
@@ -1292,7 +1356,8 @@ extern "C" int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, 
 #define WG_Z_CHUNKS 16
 #define WG_STAGE ((WG_A_CHUNKS + WG_Z_CHUNKS) * FBT_SBO)
 struct WGradTC {
-  const float* dZ;             // [2A][M][256]
+  const float* dZ;             // [2A][M][256] fp32, or
+  const __nv_bfloat16* dZb;    // [2A][M][256] bf16
   const float* X;              // [2A][M][dx] fp32, or
   const __nv_bfloat16* Xb;     // [2A][M][dx] bf16
   const float* Hp;             // [2A][M][64] fp32, or
@@ -1376,6 +1441,22 @@ wgrad_tc_kernel(const DDimsTC d, const WGradTC a) {
     unsigned char* sZ = sA + (size_t)WG_A_CHUNKS * FBT_SBO;
     const int rows_valid = (a.M - m0) < FBT_ROWS ? (int)(a.M - m0) : FBT_ROWS;
     const int64_t rowbase = (int64_t)u * a.M + m0;
+    if (j + 1 < j1) {      // pull the next tile towards L2 while this one is converted and multiplied
+      const int pun = (int)((j + 1) / tpu), un = pun >> 1, nhn = pun & 1;
+      const int64_t m0n = (j + 1 - (int64_t)pun * tpu) * FBT_ROWS;
+      const int rvn = (a.M - m0n) < FBT_ROWS ? (int)(a.M - m0n) : FBT_ROWS;
+      const int64_t rbn = (int64_t)un * a.M + m0n;
+      if ((tid >> 2) < rvn) {
+        if (a.dZb) { if ((tid & 3) < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dZb + (rbn + (tid >> 2)) * TC_N + nhn * 128 + (tid & 3) * 64)); }
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dZ + (rbn + (tid >> 2)) * TC_N + nhn * 128 + (tid & 3) * 32));
+      }
+      if (a.Xb) {
+        const char* px = reinterpret_cast<const char*>(a.Xb + rbn * dx);
+        const int64_t nbytes = (int64_t)rvn * dx * 2;
+        for (int64_t o = (int64_t)tid * 128; o < nbytes; o += FBT_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+      }
+      if (a.Hb && tid < rvn && m0n + tid >= a.rc) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Hb + (rbn + tid - a.rc) * TC_H));
+    }
     // ---- B: this half of dZ (fp32 -> bf16), 8 gate columns per item ----
     {
       float4 z0[4], z1[4];
@@ -1384,8 +1465,13 @@ wgrad_tc_kernel(const DDimsTC d, const WGradTC a) {
         const int i = r * FBT_THREADS + tid, row = i >> 4, g = i & 15;
         z0[r] = z1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < rows_valid) {
-          const float4* zp = reinterpret_cast<const float4*>(a.dZ + (rowbase + row) * TC_N + nh * 128 + g * 8);
-          z0[r] = __ldg(zp); z1[r] = __ldg(zp + 1);
+          if (a.dZb) {       // already bf16: carried bit-for-bit in z0
+            const uint4 zb = __ldg(reinterpret_cast<const uint4*>(a.dZb + (rowbase + row) * TC_N + nh * 128 + g * 8));
+            z0[r] = make_float4(__uint_as_float(zb.x), __uint_as_float(zb.y), __uint_as_float(zb.z), __uint_as_float(zb.w));
+          } else {
+            const float4* zp = reinterpret_cast<const float4*>(a.dZ + (rowbase + row) * TC_N + nh * 128 + g * 8);
+            z0[r] = __ldg(zp); z1[r] = __ldg(zp + 1);
+          }
         }
       }
       // ---- A: X, 8 columns per item; items are contiguous in global memory ----
@@ -1429,7 +1515,9 @@ wgrad_tc_kernel(const DDimsTC d, const WGradTC a) {
                                             __float2bfloat16_rn(z0[r].z), __float2bfloat16_rn(z0[r].w),
                                             __float2bfloat16_rn(z1[r].x), __float2bfloat16_rn(z1[r].y),
                                             __float2bfloat16_rn(z1[r].z), __float2bfloat16_rn(z1[r].w)};
-        *reinterpret_cast<uint4*>(sZ + (size_t)g * FBT_SBO + row * 16) = *reinterpret_cast<const uint4*>(t);
+        uint4 zo = *reinterpret_cast<const uint4*>(t);
+        if (a.dZb) zo = make_uint4(__float_as_uint(z0[r].x), __float_as_uint(z0[r].y), __float_as_uint(z0[r].z), __float_as_uint(z0[r].w));
+        *reinterpret_cast<uint4*>(sZ + (size_t)g * FBT_SBO + row * 16) = zo;
       }
     }
     // ---- A: Hp (8 hidden units per item) and the ones column ----
@@ -1484,19 +1572,202 @@ wgrad_tc_kernel(const DDimsTC d, const WGradTC a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-extern "C" int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const float* X, const void* x_bf16, const float* Hp,
-                             const void* h_bf16, const float* h0, const float* done, int32_t T, int64_t rc,
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// All-bf16 variant (the training loop's): 64-row tiles, three stages, every 16 B piece goes global -> shared with
+// cp.async (no registers) two tiles ahead of the MMAs.  Rows with done[t] (Hp = 0) and the t = 0 rows (Hp = h0, fp32)
+// take the register path.  CTAs 2p and 2p+1 walk the same (unit, tile) range, one per 128-column half of dZ.
+#define WGA_ROWS 64
+#define WGA_SBO (WGA_ROWS * 16 + 16)
+#define WGA_STAGE ((WG_A_CHUNKS + WG_Z_CHUNKS) * WGA_SBO)
+#define WGA_STAGES 2
+#define WGA_MAXT 256
+__global__ void __launch_bounds__(FBT_THREADS, 1)
+wgrad_tc_async_kernel(const DDimsTC d, const WGradTC a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(tc_smem + WGA_STAGES * WGA_STAGE);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + WGA_STAGES);
+  float* sDone = reinterpret_cast<float*>(sTmem + 2);
+  const uint32_t scratch = smem_u32(sDone + WGA_MAXT);      // 16 B sink for pieces that fall outside the tile
+  const uint32_t bar0 = smem_u32(sBar);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < WGA_STAGES; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // never-written A chunks are read by the last M block: keep them finite
+  for (int i = tid; i < WGA_STAGES * WGA_STAGE / 16; i += FBT_THREADS) reinterpret_cast<uint4*>(tc_smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < a.T; i += FBT_THREADS) sDone[i] = a.done[i];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  const uint32_t lbo = a.variant ? WGA_SBO : 128, sbo = a.variant ? 128 : WGA_SBO;
+  const int dx = d.dx, ng = dx >> 3, n_xitems = WGA_ROWS * ng;
+  const uint32_t ng_magic = (1u << 20) / (uint32_t)ng + 1u;      // i / ng == (i * magic) >> 20 for i < 4096, ng <= 32
+  const int nb = (dx + TC_H + 1 + 127) >> 7;        // M blocks
+  const int64_t tpu = (a.M + WGA_ROWS - 1) / WGA_ROWS;
+  const int64_t NT = tpu * 2 * d.A;
+  const int npairs = gridDim.x >> 1, pb = blockIdx.x >> 1, nh = blockIdx.x & 1;
+  const int64_t j0 = NT * pb / npairs, j1 = NT * (pb + 1) / npairs;
+  uint32_t pend = 0, phase = 0;                      // bit s: a commit is outstanding on / the wait parity of stage s
+  bool first = true;
+  int cur_u = -1;
+  auto wait_stage = [&](int s) {
+    if (pend & (1u << s)) { mbar_wait(bar0 + 8 * s, (phase >> s) & 1u); phase ^= 1u << s; pend &= ~(1u << s); }
+  };
+  auto flush = [&](int u) {
+    for (int s = 0; s < WGA_STAGES; ++s) wait_stage(s);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3, cq = warp >> 2;
+    const int g0 = nh * 128 + cq * 32;
+    for (int b = 0; b < nb; ++b) {
+      const int ci = b * 128 + q * 32 + lane;
+      float v[32];
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 128 + cq * 32);
+      tmem_ld16(tb, v); tmem_ld16(tb + 16, v + 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* dst = nullptr;
+      if (ci < dx) dst = a.G + d.off_wx + ((int64_t)u * dx + ci) * TC_N + g0;
+      else if (ci < dx + TC_H) dst = a.G + d.off_wh + ((int64_t)u * TC_H + (ci - dx)) * TC_N + g0;
+      else if (ci == dx + TC_H) dst = a.G + d.off_bl + (int64_t)u * TC_N + g0;
+      if (dst) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(dst + e, v[e]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  };
+
+  // running position of the NEXT tile to issue: unit, first row, and (t, row within t) of that row
+  int iu = (int)(j0 / tpu);
+  int64_t im0 = (j0 - (int64_t)iu * tpu) * WGA_ROWS;
+  int64_t it_t = im0 / a.rc, it_rem = im0 - it_t * a.rc;
+  // Register-staged pipeline: the 7 pieces (16 B each: 2 of dZ, <= 4 of X, 1 of Hp) of tile j + 2 are loaded into
+  // registers while tile j is multiplied and tile j + 1 sits in the other smem stage; they are stored one iteration
+  // later, when their latency has passed.  (cp.async was measured slower here: LDGSTS keeps its address registers
+  // reserved until the copy completes, and the allocator's reuse of them stalls the warp for a memory latency.)
+  uint4 pv[7];
+  int prv = 0;                                   // rows_valid of the tile held in pv
+  auto load_tile = [&]() {
+    const int u = iu;
+    const int64_t m0 = im0;
+    const int rows_valid = (a.M - m0) < WGA_ROWS ? (int)(a.M - m0) : WGA_ROWS;
+    const int64_t rowbase = (int64_t)u * a.M + m0;
+    prv = rows_valid;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = r * FBT_THREADS + tid, row = i >> 4, g = i & 15;
+      pv[r] = make_uint4(0, 0, 0, 0);
+      if (row < rows_valid) pv[r] = __ldg(reinterpret_cast<const uint4*>(a.dZb + (rowbase + row) * TC_N + nh * 128 + g * 8));
+    }
+    const uint4* xsrc = reinterpret_cast<const uint4*>(a.Xb + rowbase * dx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = k * FBT_THREADS + tid;
+      pv[2 + k] = make_uint4(0, 0, 0, 0);
+      if (i < rows_valid * ng) pv[2 + k] = __ldg(xsrc + i);
+    }
+    {
+      const int hrow = tid >> 3, hc = tid & 7;
+      pv[6] = make_uint4(0, 0, 0, 0);
+      if (hrow < rows_valid) {
+        int64_t t = it_t, rem = it_rem + hrow;
+        while (rem >= a.rc) { rem -= a.rc; ++t; }
+        if (sDone[t] == 0.f) {
+          if (t > 0) pv[6] = __ldg(reinterpret_cast<const uint4*>(a.Hb + (rowbase + hrow - a.rc) * TC_H + hc * 8));
+          else {       // first step of the rollout: Hp = h0 (fp32 state)
+            const float4* hp = reinterpret_cast<const float4*>(a.h0 + ((int64_t)u * a.ld_state + a.r0 + rem) * TC_H + hc * 8);
+            const float4 p = __ldg(hp), qv = __ldg(hp + 1);
+            __align__(16) __nv_bfloat16 tt[8] = {__float2bfloat16_rn(p.x), __float2bfloat16_rn(p.y), __float2bfloat16_rn(p.z),
+                                                 __float2bfloat16_rn(p.w), __float2bfloat16_rn(qv.x), __float2bfloat16_rn(qv.y),
+                                                 __float2bfloat16_rn(qv.z), __float2bfloat16_rn(qv.w)};
+            pv[6] = *reinterpret_cast<const uint4*>(tt);
+          }
+        }
+      }
+    }
+    // advance the running position
+    im0 += WGA_ROWS; it_rem += WGA_ROWS;
+    while (it_rem >= a.rc) { it_rem -= a.rc; ++it_t; }
+    if (im0 >= a.M) { ++iu; im0 = 0; it_t = 0; it_rem = 0; }
+  };
+  auto store_tile = [&](int s) {
+    unsigned char* sA = tc_smem + (size_t)s * WGA_STAGE;
+    unsigned char* sZ = sA + (size_t)WG_A_CHUNKS * WGA_SBO;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = r * FBT_THREADS + tid, row = i >> 4, g = i & 15;
+      *reinterpret_cast<uint4*>(sZ + (size_t)g * WGA_SBO + row * 16) = pv[r];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = k * FBT_THREADS + tid;
+      if (i < n_xitems) {
+        const int row = (int)(((uint32_t)i * ng_magic) >> 20), cg = i - row * ng;
+        *reinterpret_cast<uint4*>(sA + (size_t)cg * WGA_SBO + row * 16) = pv[2 + k];
+      }
+    }
+    *reinterpret_cast<uint4*>(sA + (size_t)(ng + (tid & 7)) * WGA_SBO + (tid >> 3) * 16) = pv[6];
+    if (tid < WGA_ROWS)
+      *reinterpret_cast<uint4*>(sA + (size_t)(ng + 8) * WGA_SBO + tid * 16) = make_uint4(tid < prv ? 0x3f80u : 0u, 0, 0, 0);
+  };
+
+  if (j0 < j1) { load_tile(); store_tile(0); }
+  if (j0 + 1 < j1) load_tile();
+  for (int64_t j = j0; j < j1; ++j) {
+    const int u = (int)(j / tpu);
+    const int s = (int)((j - j0) & 1);
+    if (u != cur_u) {
+      if (cur_u >= 0) flush(cur_u);
+      cur_u = u; first = true;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aA = smem_u32(tc_smem + (size_t)s * WGA_STAGE), aZ = aA + WG_A_CHUNKS * WGA_SBO;
+      for (int b = 0; b < nb; ++b)
+        for (int ks = 0; ks < WGA_ROWS / 16; ++ks)
+          umma_bf16(tmem + b * 128, make_desc(aA + b * 16 * WGA_SBO + ks * 256, lbo, sbo),
+                    make_desc(aZ + ks * 256, lbo, sbo), idesc, (first && ks == 0) ? 0u : 1u);
+      umma_commit(bar0 + 8 * s);
+    }
+    pend |= 1u << s;
+    first = false;
+    if (j + 1 < j1) {
+      wait_stage(s ^ 1);            // MMAs of tile j - 1 (issued one iteration ago) have drained the other stage
+      store_tile(s ^ 1);            // tile j + 1, loaded one iteration ago
+      if (j + 2 < j1) load_tile();
+    }
+  }
+  if (cur_u >= 0) flush(cur_u);
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+extern "C" int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const void* dz_bf16, const float* X, const void* x_bf16,
+                             const float* Hp, const void* h_bf16, const float* h0, const float* done, int32_t T, int64_t rc,
                              int64_t ld_state, int64_t r0, float* grads, int32_t variant, void* stream) {
-  if (!h || !dZ || (!X && !x_bf16) || (!Hp && !h_bf16) || !grads || T <= 0 || rc <= 0)
+  if (!h || (!dZ && !dz_bf16) || (!X && !x_bf16) || (!Hp && !h_bf16) || !grads || T <= 0 || rc <= 0)
     return tsc_set_error("tscl_wgrad_tc: bad argument");
   if (h_bf16 && (!h0 || !done)) return tsc_set_error("tscl_wgrad_tc: h_bf16 needs h0 and done");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
   if ((d.dx % 8) != 0 || d.dx / 8 + 9 > WG_A_CHUNKS) return tsc_set_error("tscl_wgrad_tc: dx must be a multiple of 8, <= 240");
   const size_t smem = 2 * (size_t)WG_STAGE + 32;
+  const size_t smem_async = (size_t)WGA_STAGES * WGA_STAGE + 8 * WGA_STAGES + 8 + 4 * WGA_MAXT + 16;
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {
     PCK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(wgrad_tc_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_async));
     attr_dev = tscl_device_of(h);
   }
   int n_sm = 0;
@@ -1505,9 +1776,15 @@ extern "C" int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const float* X, co
   const int64_t NT = ((M + FBT_ROWS - 1) / FBT_ROWS) * 4 * d.A;
   const int grid = (int)(NT < n_sm ? NT : n_sm);
   WGradTC a;
-  a.dZ = dZ; a.X = X; a.Xb = (const __nv_bfloat16*)x_bf16; a.Hp = Hp; a.Hb = (const __nv_bfloat16*)h_bf16; a.h0 = h0;
+  a.dZ = dZ; a.dZb = (const __nv_bfloat16*)dz_bf16; a.X = X; a.Xb = (const __nv_bfloat16*)x_bf16; a.Hp = Hp; a.Hb = (const __nv_bfloat16*)h_bf16; a.h0 = h0;
   a.done = done; a.G = grads; a.M = M; a.rc = rc; a.ld_state = ld_state; a.r0 = r0; a.T = T; a.variant = variant;
-  wgrad_tc_kernel<<<grid, FBT_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  if (a.dZb && a.Xb && a.Hb && T <= WGA_MAXT) {
+    const int64_t nt2 = ((M + WGA_ROWS - 1) / WGA_ROWS) * 2 * d.A;
+    int g2 = (int)(nt2 < n_sm / 2 ? nt2 : n_sm / 2) * 2;      // CTA pairs
+    if (g2 < 2) g2 = 2;
+    wgrad_tc_async_kernel<<<g2, FBT_THREADS, smem_async, (cudaStream_t)stream>>>(d, a);
+  }
+  else wgrad_tc_kernel<<<grid, FBT_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
 }

@@ -108,16 +108,19 @@ int tscl_fc_bwd(tscl_handle* h, const float* obs, const float* X, const float* d
 /* The same contraction on the tensor cores (tcgen05, MN-major bf16 operands, fp32 accumulation in TMEM over
  * 128-row tiles; replaces the SIMT kernel in the training loop).  Pass the activations either as fp32 `X` or as one
  * chunk of the bf16 activation store `x_bf16` ([2A][M][dx]); `variant` must be 0. */
-int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, const void* x_bf16, const float* dX, int64_t M,
-                   int64_t rows_per_t, int64_t stride_t, float* grads, int32_t variant, void* stream);
+int tscl_fc_bwd_tc(tscl_handle* h, const float* obs, const float* X, const void* x_bf16, const float* dX,
+                   const void* dx_bf16, int64_t M, int64_t rows_per_t, int64_t stride_t, float* grads, int32_t variant,
+                   void* stream);
+/* dX likewise as fp32 `dX` or bf16 `dx_bf16` ([2A][M][dx]). */
 
 /* LSTM weight gradients of one chunk on the tensor cores:  grads.wx += X^T dZ, grads.wh += Hp^T dZ, grads.bl += 1^T dZ
  * (rows m = t * rc + r, M = T * rc; bf16 operands, fp32 accumulation in TMEM).  X as fp32 `X` or bf16 `x_bf16`
  * ([2A][M][dx]); Hp as fp32 `Hp` ([2A][M][h]) or rebuilt from the bf16 store chunk `h_bf16` ([2A][T][rc][h]) as
  * (1 - done[t]) * (t > 0 ? H[t-1] : h0[u][r0 + r]).  `variant` must be 0. */
-int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const float* X, const void* x_bf16, const float* Hp,
-                  const void* h_bf16, const float* h0, const float* done, int32_t T, int64_t rc, int64_t ld_state,
-                  int64_t r0, float* grads, int32_t variant, void* stream);
+int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const void* dz_bf16, const float* X, const void* x_bf16,
+                  const float* Hp, const void* h_bf16, const float* h0, const float* done, int32_t T, int64_t rc,
+                  int64_t ld_state, int64_t r0, float* grads, int32_t variant, void* stream);
+/* dZ likewise as fp32 `dZ` or bf16 `dz_bf16` ([2A][M][256], written by tscl_lstm_seq_bwd_tc). */
 
 /* BPTT on the tensor cores (tcgen05): same contract as tscl_lstm_seq_bwd, with the recurrent product dz.Wh^T as
  * a bf16 MMA (M=128, N=64, K=256) per step; wt_bf16 [2A][32][64][8] comes from tscl_pack_wht (refresh after
@@ -125,9 +128,10 @@ int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const float* X, const void* x
 int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16, void* stream);
 int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH, const float* c0,
                          const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
-                         const void* gates_bf16, const void* c_bf16, void* stream);
+                         const void* gates_bf16, const void* c_bf16, void* dz_bf16, void* stream);
 /* gates_bf16 / c_bf16 (both or neither): read gate activations and c_t straight from one chunk of the bf16
- * activation store instead of ZG / C (ZG is then write-only: it receives dZ). */
+ * activation store instead of ZG / C (ZG is then write-only: it receives dZ).
+ * dz_bf16 (optional): also write dZ as bf16 [2A][T*Rc][256]; with all three bf16 pointers ZG may be NULL. */
 
 /* One replica chunk of the bf16 activation store ([2A][T][rc][w] contiguous) -> fp32 work buffers X, ZG (gates),
  * C, H and Hp[t] = (1 - done[t]) * (t > 0 ? H[t-1] : h0[:, r0 + r]).  Every output may be NULL (skipped): the

@@ -198,13 +198,18 @@ def test_bptt_tensor_core_kernel_matches_fp32_kernel():
     _lib.check(lib.tscl_lstm_seq_bwd(m._h, _p(m.P), _p(z1), _p(Cc), _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
                                      C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), m._st()))
     _lib.check(lib.tscl_lstm_seq_bwd_tc(m._h, _p(m.Wt), _p(z2), _p(Cc), _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
-                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), None, None, m._st()))
+                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), None, None, None, m._st()))
     # same again with gates / c read from bf16 copies (the activation-store fast path)
     z3 = torch.zeros_like(gates)
     gb, cb = gates.to(torch.bfloat16).contiguous(), Cc.to(torch.bfloat16).contiguous()
     _lib.check(lib.tscl_lstm_seq_bwd_tc(m._h, _p(m.Wt), _p(z3), None, _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
-                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(gb), _p(cb), m._st()))
+                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(gb), _p(cb), None, m._st()))
+    # ... and with dZ written as bf16 only (no fp32 output at all)
+    z4 = torch.zeros(U, T * Rc, 256, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.tscl_lstm_seq_bwd_tc(m._h, _p(m.Wt), None, None, _p(dH), _p(m.c_bw), _p(done), C.c_int32(T),
+                                        C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(gb), _p(cb), _p(z4), m._st()))
     torch.cuda.synchronize()
+    assert torch.equal(z4, z3.to(torch.bfloat16))
     assert float((z3 - z1).norm() / z1.norm()) < 2e-2
     assert torch.isfinite(z2).all()
     scale = float(z1.abs().max())
@@ -233,7 +238,8 @@ def test_fc_weight_gradients_tensor_core_kernel(ff, use_bf16_x):
     X = torch.relu(torch.randn(U, M, dx, device="cuda", generator=g))
     Xb = X.to(torch.bfloat16).contiguous()
     X = Xb.float()                                 # same mask on both paths
-    dX = torch.randn(U, M, dx, device="cuda", generator=g) * 1e-2
+    dXb = (torch.randn(U, M, dx, device="cuda", generator=g) * 1e-2).to(torch.bfloat16).contiguous()
+    dX = dXb.float()                               # bf16-representable, so the bf16 and fp32 inputs are the same numbers
     r0 = 40
     obs0 = obs[0, r0:]
     lib = _lib.lib()
@@ -243,8 +249,8 @@ def test_fc_weight_gradients_tensor_core_kernel(ff, use_bf16_x):
 
     def run(variant, out):
         _lib.check(lib.tscl_fc_bwd_tc(m._h, _p(obs0), None if use_bf16_x else _p(X), _p(Xb) if use_bf16_x else None,
-                                      _p(dX), C.c_int64(M), C.c_int64(Rc), C.c_int64(R * lay.n_obs), _p(out),
-                                      C.c_int32(variant), m._st()))
+                                      None if use_bf16_x else _p(dX), _p(dXb) if use_bf16_x else None, C.c_int64(M),
+                                      C.c_int64(Rc), C.c_int64(R * lay.n_obs), _p(out), C.c_int32(variant), m._st()))
         torch.cuda.synchronize()
     run(0, G2)
     g1, g2 = lay.views(G1.cpu().numpy()), lay.views(G2.cpu().numpy())
@@ -296,7 +302,8 @@ def test_lstm_weight_gradients_tensor_core_kernel(ff, from_store):
     Hb = torch.tanh(torch.randn(U, T, Rc, 64, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
     h0 = torch.tanh(torch.randn(U, R, 64, device="cuda", generator=g))
     done = torch.tensor([0, 0, 1, 0, 0], dtype=torch.float32, device="cuda")
-    dZ = torch.randn(U, M, 256, device="cuda", generator=g) * 1e-2
+    dZb = (torch.randn(U, M, 256, device="cuda", generator=g) * 1e-2).to(torch.bfloat16).contiguous()
+    dZ = dZb.float()
     # reference Hp (fp32 values of the bf16 operands)
     Hp = torch.empty(U, T, Rc, 64, device="cuda")
     Hp[:, 0] = h0[:, r0:r0 + Rc].to(torch.bfloat16).float()
@@ -307,11 +314,11 @@ def test_lstm_weight_gradients_tensor_core_kernel(ff, from_store):
 
     def run(variant, out):
         if from_store:
-            _lib.check(lib.tscl_wgrad_tc(m._h, _p(dZ), None, _p(Xb), None, _p(Hb), _p(h0), _p(done), C.c_int32(T),
+            _lib.check(lib.tscl_wgrad_tc(m._h, None, _p(dZb), None, _p(Xb), None, _p(Hb), _p(h0), _p(done), C.c_int32(T),
                                          C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(out), C.c_int32(variant), m._st()))
         else:
             Xf = Xb.float().contiguous()
-            _lib.check(lib.tscl_wgrad_tc(m._h, _p(dZ), _p(Xf), None, _p(Hp), None, None, None, C.c_int32(T),
+            _lib.check(lib.tscl_wgrad_tc(m._h, _p(dZ), None, _p(Xf), None, _p(Hp), None, None, None, C.c_int32(T),
                                          C.c_int64(Rc), C.c_int64(R), C.c_int64(r0), _p(out), C.c_int32(variant), m._st()))
         torch.cuda.synchronize()
     run(0, G)

@@ -924,25 +924,42 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
         }
         if (qt >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + (qt - 2) * 32));
       }
+      // the second half's loads are issued before the first half is consumed (their latencies overlap)
+      uint4 rg[4], rc, rp;
+      if (valid && a.Gb) {
+        const int jo = jq + 8;
+        const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rg[g] = *reinterpret_cast<const uint4*>(zb + g * 64);
+        rc = *reinterpret_cast<const uint4*>(a.Cb + m * TC_H + jo);
+        if (t > 0) rp = *reinterpret_cast<const uint4*>(a.Cb + (m - a.Rc) * TC_H + jo);
+      }
 #pragma unroll
       for (int jb = 0; jb < 2; ++jb) {
         const int jo = jq + jb * 8;
         float gi[8], gf[8], go[8], gu[8], ct[8], cp[8], dh[8];
         if (valid) {
           if (a.Gb) {
-            const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
-            bf8(*reinterpret_cast<const uint4*>(zb), gi); bf8(*reinterpret_cast<const uint4*>(zb + 64), gf);
-            bf8(*reinterpret_cast<const uint4*>(zb + 128), go); bf8(*reinterpret_cast<const uint4*>(zb + 192), gu);
-            bf8(*reinterpret_cast<const uint4*>(a.Cb + m * TC_H + jo), ct);
-            if (t > 0) bf8(*reinterpret_cast<const uint4*>(a.Cb + (m - a.Rc) * TC_H + jo), cp);
-            else f8(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo, cp);
+            if (jb == 0) {
+              const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
+              bf8(*reinterpret_cast<const uint4*>(zb), gi); bf8(*reinterpret_cast<const uint4*>(zb + 64), gf);
+              bf8(*reinterpret_cast<const uint4*>(zb + 128), go); bf8(*reinterpret_cast<const uint4*>(zb + 192), gu);
+              bf8(*reinterpret_cast<const uint4*>(a.Cb + m * TC_H + jo), ct);
+              if (t > 0) bf8(*reinterpret_cast<const uint4*>(a.Cb + (m - a.Rc) * TC_H + jo), cp);
+            } else {
+              bf8(rg[0], gi); bf8(rg[1], gf); bf8(rg[2], go); bf8(rg[3], gu);
+              bf8(rc, ct);
+              if (t > 0) bf8(rp, cp);
+            }
+            if (t == 0) f8(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo, cp);
+            f8(a.dH + m * TC_H + jo, dh);
           } else {
             const float* z = a.ZG + m * TC_N + jo;
             f8(z, gi); f8(z + 64, gf); f8(z + 128, go); f8(z + 192, gu);
             f8(a.C + m * TC_H + jo, ct);
             f8(t > 0 ? a.C + (m - a.Rc) * TC_H + jo : a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo, cp);
+            f8(a.dH + m * TC_H + jo, dh);
           }
-          f8(a.dH + m * TC_H + jo, dh);
 #pragma unroll
           for (int e = 0; e < 8; ++e) cp[e] *= keep;
         } else {

@@ -55,6 +55,8 @@ def parse():
     p.add_argument("--fp32-gemm", action="store_true", help="plain fp32 (no TF32 tensor cores) in the learner GEMMs")
     p.add_argument("--seed", type=int, default=12)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--e2e-parts", type=int, default=2,
+                   help="replica ranges of the host-buffer (e2e) loop, one stream each (1: single blocking tsc_step_host)")
     return p.parse_args()
 
 
@@ -276,18 +278,27 @@ def main():
     # ---------------- e2e: the environment driven through the host-buffer C-ABI call ------------
     if trainer is not None:
         e2e_steps = N_STEP                     # one full rollout + one update
+        if args.e2e_parts > 1:
+            host_step = lambda: trainer.control_step_host_pipelined(n_parts=args.e2e_parts)
+        else:
+            host_step = trainer.control_step_host
         for i in range(3):
-            trainer.control_step_host()
+            host_step()
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            trainer.control_step_host()
+            host_step()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4
         d2h = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
         e2e_api = ("BatchedTrainer.control_step_host: policy forward on device, actions+fingerprints D2H, "
                    "tsc_step_host (H2D, kernel, D2H), obs+reward H2D, update every 120 steps")
+        if args.e2e_parts > 1:
+            e2e_api = ("BatchedTrainer.control_step_host_pipelined: %d replica ranges, one stream each; per range: policy "
+                       "forward (tscl_policy_step_v2r), actions+fingerprints D2H to pinned host buffers, "
+                       "tsc_step_host_range (H2D, kernel, D2H, host sync), obs+reward H2D into the learner; update "
+                       "every 120 steps" % args.e2e_parts)
     else:
         e2e_steps = max(3, min(args.steps, 20))
         h_act = [torch.randint(0, 5, (R, net.n_nodes), dtype=torch.int32).pin_memory().numpy() for _ in range(4)]

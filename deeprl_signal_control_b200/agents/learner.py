@@ -189,6 +189,51 @@ class BatchedA2C:
             self.n_forward += 1
         return self.pi, self.val, (self.act if want_act else None)
 
+    def forward_range(self, r0: int, n: int, done: bool, t: int, n_forward: int):
+        """forward() for the replica range [r0, r0 + n) only, on the current stream, for rollout slot `t` and decision
+        counter `n_forward` (the caller may run ranges one step apart): reads obs_slot(t)[r0:r0+n], advances that
+        range's recurrent state and writes its slices of pi / val / act (and of the activation store).  Ranges are
+        independent.  Tensor-core path only; bookkeeping of the step: end_forward_ranges()."""
+        assert self.use_tc and self.tc_v2, "forward_range needs the fused tensor-core forward"
+        L, R, A = self.lay, self.R, self.lay.A
+        store = self.store_acts and t < self.T
+        st = (_p(self.st_x), _p(self.st_g), _p(self.st_c), _p(self.st_h)) if store else (None,) * 4
+        off = lambda t_, per_row: C.c_void_p(t_.data_ptr() + r0 * per_row * t_.element_size())
+        _lib.check(_lib.lib().tscl_policy_step_v2r(
+            self._h, _p(self.P), _p(self.Wp), off(self.obs_hist[t], L.n_obs), C.c_int64(n),
+            off(self.c_fw, L.h), off(self.h_fw, L.h), off(self.c_fw, L.h), off(self.h_fw, L.h),
+            off(self.pi, A * L.max_na), off(self.val, A), off(self.act, A), C.c_int32(1 if done else 0),
+            C.c_uint64(self.seed), C.c_int64(n_forward), C.c_int64(self.replica0 + r0), None, *st,
+            C.c_int32(t if store else 0), C.c_int32(self.T), C.c_int64(self.chunk), C.c_int64(R), C.c_int64(r0),
+            self._st()))
+        self.kernel_launches += 1
+        if t < self.T:
+            self._acts_ok[t] = store
+        return self.pi[r0:r0 + n], self.val[r0:r0 + n], self.act[r0:r0 + n]
+
+    def end_forward_ranges(self):
+        """One decision step has been issued for every range."""
+        self.n_forward += 1
+
+    def add_transition_range(self, r0: int, n: int, reward: torch.Tensor):
+        """add_transition() data movement for one replica range (reward [n, A]); finish the step with
+        end_transition_ranges(done_pre, done_post)."""
+        t = self.t
+        r = reward
+        if self.reward_norm:
+            r = r / self.reward_norm
+        if self.reward_clip:
+            r = torch.clamp(r, -self.reward_clip, self.reward_clip)
+        self.rew_hist[t, r0:r0 + n].copy_(r)
+        self.act_hist[t, r0:r0 + n].copy_(self.act[r0:r0 + n])
+        self.val_hist[t, r0:r0 + n].copy_(self.val[r0:r0 + n])
+
+    def end_transition_ranges(self, done_pre: bool, done_post: bool):
+        t = self.t
+        self.done_pre[t] = 1.0 if done_pre else 0.0
+        self.done_post[t] = 1.0 if done_post else 0.0
+        self.t += 1
+
     # ------------------------------------------------------------------------------------------
     def obs_slot(self, t: Optional[int] = None) -> torch.Tensor:
         return self.obs_hist[self.t if t is None else t]

@@ -107,6 +107,72 @@ class BatchedTrainer:
         if m.t == m.T:
             self.update()
 
+    def control_step_host_pipelined(self, n_parts: int = 2):
+        """control_step_host() with the replicas split into `n_parts` ranges, one CUDA stream each: while range k sits on
+        the PCIe link (tsc_step_host_range: actions H2D, kernel, observations D2H; then observations H2D into the
+        learner), the other ranges run their policy forward / simulator kernels.  Same results as control_step_host():
+        ranges are independent and the sampling RNG is keyed by the absolute replica.  The host still receives every
+        range's observations / rewards in page-locked numpy buffers before the learner consumes them."""
+        sim, m = self.sim, self.model
+        R, A = sim.R, m.lay.A
+        if not hasattr(self, '_pp'):
+            n_parts = max(1, min(n_parts, R))
+            bounds = [R * k // n_parts for k in range(n_parts + 1)]
+            pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
+            self._pp = dict(parts=[(bounds[k], bounds[k + 1] - bounds[k]) for k in range(n_parts)],
+                            streams=[torch.cuda.Stream(device=sim.device) for _ in range(n_parts)],
+                            ev=[torch.cuda.Event() for _ in range(n_parts)], primed=False,
+                            act=pin(R, A, dtype=torch.int32), pi=pin(R, A, m.lay.max_na), obs=pin(R, sim.net.n_obs),
+                            rew=pin(R, A), grew=pin(R), done=pin(R, dtype=torch.uint8))
+        pp = self._pp
+        ma2c = self.agent == 'ma2c'
+
+        def issue_forward(k, t, nf, done):
+            r0, n = pp['parts'][k]
+            pi, val, act = m.forward_range(r0, n, done, t, nf)
+            pp['act'][r0:r0 + n].copy_(act, non_blocking=True)
+            if ma2c:
+                pp['pi'][r0:r0 + n].copy_(pi, non_blocking=True)
+            pp['ev'][k].record()
+
+        if not pp['primed']:
+            cur = torch.cuda.current_stream(sim.device)
+            for k, st in enumerate(pp['streams']):
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    issue_forward(k, m.t, m.n_forward, self.done)
+            m.end_forward_ranges()
+            pp['primed'] = True
+        t = m.t
+        self.step_in_episode += 1
+        new_done = self.step_in_episode >= self.T_episode
+        boundary = (t + 1 == m.T)                       # an update (and possibly an episode end) follows this step
+        npv = lambda x, r0, n: x[r0:r0 + n].numpy()
+        for k, st in enumerate(pp['streams']):
+            r0, n = pp['parts'][k]
+            pp['ev'][k].synchronize()                   # the host holds this range's actions / fingerprints
+            with torch.cuda.stream(st):
+                sim.step_host_range(r0, n, npv(pp['act'], r0, n), npv(pp['pi'], r0, n) if ma2c else None,
+                                    npv(pp['obs'], r0, n), npv(pp['rew'], r0, n), npv(pp['grew'], r0, n),
+                                    npv(pp['done'], r0, n))
+                # ... and now its observations / rewards: hand them to the learner
+                m.obs_hist[t + 1, r0:r0 + n].copy_(pp['obs'][r0:r0 + n], non_blocking=True)
+                m.add_transition_range(r0, n, pp['rew'][r0:r0 + n].to(sim.device, non_blocking=True))
+                self._rew_acc[r0:r0 + n].add_(pp['grew'][r0:r0 + n].to(sim.device, non_blocking=True))
+                if not boundary:
+                    issue_forward(k, t + 1, m.n_forward, False)
+        m.end_transition_ranges(self.done, new_done)
+        self.done = new_done
+        self.n_env_steps += 1
+        if not boundary:
+            m.end_forward_ranges()
+        else:
+            cur = torch.cuda.current_stream(sim.device)
+            for st in pp['streams']:
+                cur.wait_stream(st)
+            pp['primed'] = False
+            self.update()
+
     def update(self):
         m = self.model
         boot = None

@@ -164,6 +164,9 @@ struct StepTC {
   __nv_bfloat16 *st_x, *st_g, *st_c, *st_h;
   int t, T;
   int64_t rc;
+  // replica-range launches (v2 only): the per-unit state arrays have `ld` rows per unit (0: R) and the activation
+  // store is indexed by the absolute replica row0 + r; every pointer is the base of the range's slice
+  int64_t ld, row0;
 };
 
 extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -514,6 +517,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
   const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
   const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.dx >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
   const int64_t n_tiles = (a.R + TC_M - 1) / TC_M;
+  const int64_t ld = a.ld > 0 ? a.ld : a.R;
   const int64_t n_items = n_tiles * 2 * d.A;
   const int64_t it_lo = n_items * blockIdx.x / gridDim.x, it_hi = n_items * (blockIdx.x + 1) / gridDim.x;
   int cur_u = -1;
@@ -526,7 +530,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     const int64_t r0 = (it - (int64_t)u * n_tiles) * TC_M;
     const int ag = u >> 1;
     // row of the activation store (chunk-outermost [R/rc][2A][T][rc][w]) for tile row `row`: one division per item
-    const int64_t st_c0 = r0 / a.rc, st_rin0 = r0 - st_c0 * a.rc;
+    const int64_t st_c0 = (a.row0 + r0) / a.rc, st_rin0 = (a.row0 + r0) - st_c0 * a.rc;
     auto store_row = [&](int row) -> int64_t {
       int64_t c = st_c0, rin = st_rin0 + row;
       while (rin >= a.rc) { rin -= a.rc; ++c; }
@@ -563,7 +567,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         const int an = un >> 1;
         const float* op = a.obs + rn * d.n_obs + d.obs_off[an] + (tid & 1) * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(op));
-        const int64_t so = ((int64_t)un * a.R + rn) * TC_H + (tid & 1) * 32;
+        const int64_t so = ((int64_t)un * ld + rn) * TC_H + (tid & 1) * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.c_in + so));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h_in + so));
       }
@@ -637,7 +641,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       const int row = tid >> 1, half = tid & 1;
       const int64_t r = r0 + row;
       const bool live = r < a.R && !a.done;
-      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * a.R + (r < a.R ? r : 0)) * TC_H + half * 32);
+      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * ld + (r < a.R ? r : 0)) * TC_H + half * 32);
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         __align__(16) __nv_bfloat16 v[8];
@@ -671,7 +675,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       const int row = q * 32 + lane;
       const int64_t r = r0 + row;
       const bool valid = r < a.R;
-      const int64_t srow = ((int64_t)u * a.R + (valid ? r : 0)) * TC_H + half * 32;
+      const int64_t srow = ((int64_t)u * ld + (valid ? r : 0)) * TC_H + half * 32;
       float lg[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) lg[j] = 0.f;
@@ -682,7 +686,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         tmem_ld16(tbase, zi); tmem_ld16(tbase + 64, zf); tmem_ld16(tbase + 128, zo); tmem_ld16(tbase + 192, zu);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (a.zdbg && valid) {
-          float* z = a.zdbg + ((int64_t)u * a.R + r) * TC_N + half * 32 + jb * 16;
+          float* z = a.zdbg + ((int64_t)u * ld + r) * TC_N + half * 32 + jb * 16;
 #pragma unroll
           for (int e = 0; e < 16; ++e) { z[e] = zi[e]; z[64 + e] = zf[e]; z[128 + e] = zo[e]; z[192 + e] = zu[e]; }
         }
@@ -786,21 +790,22 @@ static size_t tc2_smem_bytes(int K) {
   return (size_t)KC * 4096 + (size_t)KC * 2048 + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + 16;
 }
 
-extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs,
+extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs,
                                    int64_t R, const float* c_in, const float* h_in, float* c_out, float* h_out,
                                    float* pi, float* val, int32_t* act, int32_t done, uint64_t seed, int64_t step,
                                    int64_t replica0, float* zdbg, void* st_x, void* st_g, void* st_c, void* st_h,
-                                   int32_t t, int32_t T, int64_t rc, void* stream) {
-  if (!h || !params || !wpack_bf16 || !obs || R <= 0) return tsc_set_error("tscl_policy_step_v2: bad argument");
-  if (st_x && (rc <= 0 || R % rc != 0)) return tsc_set_error("tscl_policy_step_v2: store chunk must divide R");
+                                   int32_t t, int32_t T, int64_t rc, int64_t ld_state, int64_t row0, void* stream) {
+  if (!h || !params || !wpack_bf16 || !obs || R <= 0) return tsc_set_error("tscl_policy_step_v2r: bad argument");
+  if (st_x && (rc <= 0 || (ld_state > 0 ? ld_state : R) % rc != 0)) return tsc_set_error("tscl_policy_step_v2r: store chunk must divide the replica count");
+  if (ld_state > 0 && (row0 < 0 || row0 + R > ld_state)) return tsc_set_error("tscl_policy_step_v2r: replica range outside [0, ld_state)");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
   const int K = d.dx + TC_H;
-  if ((d.dx % 32) != 0 || d.dx > 256) return tsc_set_error("tscl_policy_step_v2: dx must be a multiple of 32, <= 256");
-  if (d.kw == 0) return tsc_set_error("tscl_policy_step_v2: observation slice does not fit the 64-column input tile");
-  if (8 * d.dx * 16 > (d.dx / 8) * 2048) return tsc_set_error("tscl_policy_step_v2: fc operand does not fit its staging region");
+  if ((d.dx % 32) != 0 || d.dx > 256) return tsc_set_error("tscl_policy_step_v2r: dx must be a multiple of 32, <= 256");
+  if (d.kw == 0) return tsc_set_error("tscl_policy_step_v2r: observation slice does not fit the 64-column input tile");
+  if (8 * d.dx * 16 > (d.dx / 8) * 2048) return tsc_set_error("tscl_policy_step_v2r: fc operand does not fit its staging region");
   const size_t smem = tc2_smem_bytes(K);
-  if (smem > 232448) return tsc_set_error("tscl_policy_step_v2: operand tiles exceed shared memory");
+  if (smem > 232448) return tsc_set_error("tscl_policy_step_v2r: operand tiles exceed shared memory");
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {
     PCK(cudaFuncSetAttribute(policy_step_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -815,10 +820,19 @@ extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const vo
   a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done; a.swap_lbo_sbo = 0;
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.step = (uint32_t)step; a.replica0 = replica0;
   a.st_x = (__nv_bfloat16*)st_x; a.st_g = (__nv_bfloat16*)st_g; a.st_c = (__nv_bfloat16*)st_c; a.st_h = (__nv_bfloat16*)st_h;
-  a.t = t; a.T = T > 0 ? T : 1; a.rc = rc > 0 ? rc : R;
+  a.t = t; a.T = T > 0 ? T : 1; a.rc = rc > 0 ? rc : R; a.ld = ld_state; a.row0 = ld_state > 0 ? row0 : 0;
   policy_step_tc2_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int tscl_policy_step_v2(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs, int64_t R,
+                                   const float* c_in, const float* h_in, float* c_out, float* h_out, float* pi, float* val,
+                                   int32_t* act, int32_t done, uint64_t seed, int64_t step, int64_t replica0, float* zdbg,
+                                   void* st_x, void* st_g, void* st_c, void* st_h, int32_t t, int32_t T, int64_t rc,
+                                   void* stream) {
+  return tscl_policy_step_v2r(h, params, wpack_bf16, obs, R, c_in, h_in, c_out, h_out, pi, val, act, done, seed, step, replica0,
+                              zdbg, st_x, st_g, st_c, st_h, t, T, rc, 0, 0, stream);
 }
 
 // ===================================================================================================

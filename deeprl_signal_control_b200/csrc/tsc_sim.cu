@@ -76,6 +76,7 @@ struct StepArgs {
   int32_t ctl_words;
   int32_t n_sub;      // sub-steps to run (0 = observe only)
   int32_t train_mode;
+  int32_t rep0;       // first replica of this launch (replica-range launches of the host-buffer pipeline)
   // io
   const int32_t* action;
   const float* fp;
@@ -273,7 +274,7 @@ tsc_step_kernel(const StepArgs A) {
   const DevNet& n = A.net;
   const tsc_cfg& c = A.cfg;
   const int tid = threadIdx.x;
-  const int rep = blockIdx.x;
+  const int rep = blockIdx.x + A.rep0;
   const int L = n.n_lanes, N = n.n_nodes;
 
   // ---- shared-memory carve-up ----
@@ -970,10 +971,11 @@ extern "C" int tsc_set_train_mode(tsc_handle* h, int32_t m) {
 }
 
 static int launch(tsc_handle* h, int n_sub, const int32_t* action, const float* fp, float* obs, float* reward,
-                  float* greward, uint8_t* done, cudaStream_t st) {
+                  float* greward, uint8_t* done, cudaStream_t st, int rep0 = 0, int count = -1) {
   StepArgs a = h->args;
   a.n_sub = n_sub; a.action = action; a.fp = fp; a.obs = obs; a.reward = reward; a.greward = greward; a.done = done;
-  tsc_step_kernel<<<h->R, TSC_THREADS, h->smem, st>>>(a);
+  a.rep0 = rep0;
+  tsc_step_kernel<<<count < 0 ? h->R : count, TSC_THREADS, h->smem, st>>>(a);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1008,6 +1010,28 @@ extern "C" int tsc_step_host(tsc_handle* h, const int32_t* action_host, const fl
   if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward, R * N * 4, cudaMemcpyDeviceToHost, st));
   if (greward_host) CK(cudaMemcpyAsync(greward_host, h->d_greward, R * 4, cudaMemcpyDeviceToHost, st));
   if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, R, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host,
+                                   const float* fp_host, float* obs_host, float* reward_host, float* greward_host,
+                                   uint8_t* done_host, void* stream) {
+  if (!h || !action_host || rep0 < 0 || count <= 0 || rep0 + count > h->R) return fail("tsc_step_host_range: bad argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = h->n_nodes, r0 = (size_t)rep0, n = (size_t)count;
+  // the kernel indexes its io arrays by absolute replica: device scratch is used at offset rep0, host pointers are slice bases
+  CK(cudaMemcpyAsync(h->d_action + r0 * N, action_host, n * N * 4, cudaMemcpyHostToDevice, st));
+  if (fp_host) CK(cudaMemcpyAsync(h->d_fp + r0 * N * h->max_na, fp_host, n * N * h->max_na * 4, cudaMemcpyHostToDevice, st));
+  if (launch(h, h->args.cfg.control_interval_sec, h->d_action, fp_host ? h->d_fp : nullptr, obs_host ? h->d_obs : nullptr,
+             reward_host ? h->d_reward : nullptr, greward_host ? h->d_greward : nullptr,
+             done_host ? h->d_done : nullptr, st, rep0, count))
+    return -1;
+  if (obs_host) CK(cudaMemcpyAsync(obs_host, h->d_obs + r0 * h->n_obs, n * h->n_obs * 4, cudaMemcpyDeviceToHost, st));
+  if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward + r0 * N, n * N * 4, cudaMemcpyDeviceToHost, st));
+  if (greward_host) CK(cudaMemcpyAsync(greward_host, h->d_greward + r0, n * 4, cudaMemcpyDeviceToHost, st));
+  if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done + r0, n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }

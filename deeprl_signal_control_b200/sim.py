@@ -105,6 +105,14 @@ class BatchedSim:
                                             _np(greward, C.c_float), _np(done, C.c_uint8), self._stream()))
         return obs, reward, greward, done
 
+    def step_host_range(self, r0: int, n: int, action: np.ndarray, fp: Optional[np.ndarray], obs: np.ndarray,
+                        reward: np.ndarray, greward: np.ndarray, done: np.ndarray):
+        """`tsc_step_host_range`: the host-buffer step for replicas [r0, r0 + n) on the current stream; all arrays are
+        the slices of that range (page-locked for full PCIe speed).  Blocks until the slice's results are on the host."""
+        _lib.check(_lib.lib().tsc_step_host_range(self._h, C.c_int32(r0), C.c_int32(n), _np(action, C.c_int32),
+                                                  _np(fp, C.c_float), _np(obs, C.c_float), _np(reward, C.c_float),
+                                                  _np(greward, C.c_float), _np(done, C.c_uint8), self._stream()))
+
     # ---- parity taps ---------------------------------------------------------------------
     def counts(self):
         n = self.net

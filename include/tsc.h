@@ -148,6 +148,12 @@ int tsc_step(tsc_handle* h, const int32_t* action_dev, const float* fp_dev, floa
 int tsc_step_host(tsc_handle* h, const int32_t* action_host, const float* fp_host, float* obs_host,
                   float* reward_host, float* greward_host, uint8_t* done_host, void* stream);
 
+/* The same call for the replica range [rep0, rep0 + count): host pointers are the bases of that range's slices
+ * (action [count][n_nodes], obs [count][n_obs], ...).  Ranges are independent, so a caller can keep one range on the
+ * PCIe link while another one computes (one stream per range; see agents/trainer.py:control_step_host_pipelined). */
+int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host, const float* fp_host,
+                        float* obs_host, float* reward_host, float* greward_host, uint8_t* done_host, void* stream);
+
 /* Integer parity taps measured at the end of the last step, per detector lane
  * (lanearea.getLastStepVehicleNumber / getLastStepHaltingNumber / head getWaitingTime,
  * envs/env.py:333-349,377-395) and per node (the phase index = action applied).

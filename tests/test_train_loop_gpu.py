@@ -58,3 +58,44 @@ def test_training_loop_runs_and_updates(agent):
     # observation slot consumed by forward == observation produced by the simulator
     assert float(b.obs_hist[0].abs().sum()) > 0
     assert sim.mean_live() > 20
+
+
+def test_pipelined_host_step_matches_device_loop():
+    """control_step_host_pipelined (replica ranges on separate streams through tsc_step_host_range /
+    tscl_policy_step_v2r) reproduces the device-resident loop bit for bit up to the first update, and keeps running
+    across the update / re-priming boundary."""
+    from deeprl_signal_control_b200.agents.layout import PolicyLayout
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C
+    from deeprl_signal_control_b200.agents.trainer import BatchedTrainer
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    from deeprl_signal_control_b200.sim import BatchedSim
+    agent, R, T = "ma2c", 300, 12
+    net, par = build_large_grid(agent=agent), EnvParams(agent=agent)
+    lay = PolicyLayout(net.n_s_ls, net.n_a_ls, net.n_w_ls, net.n_f_ls, net.node_obs_off, net.n_obs, fw=128, ft=32,
+                       ff=64, h=64)
+    trs = []
+    for _ in range(3):
+        sim = BatchedSim(net, par, R)
+        m = BatchedA2C(lay, R, n_step=T, reward_norm=2000.0, reward_clip=2.0, seed=3, chunk=150)
+        trs.append(BatchedTrainer(sim, m, agent, lr=5e-4, beta=0.01, seed0=7))
+    dev, host, pipe = trs
+    for _ in range(T - 1):
+        dev.control_step(); host.control_step_host(); pipe.control_step_host_pipelined(n_parts=3)
+    torch.cuda.synchronize()
+    for other in (host, pipe):
+        assert torch.equal(dev.model.act_hist[:T - 1], other.model.act_hist[:T - 1])
+        assert torch.equal(dev.model.rew_hist[:T - 1], other.model.rew_hist[:T - 1])
+        assert torch.equal(dev.model.obs_hist[:T], other.model.obs_hist[:T])
+        assert torch.equal(dev.model.val_hist[:T - 1], other.model.val_hist[:T - 1])
+    assert torch.equal(dev._rew_acc, pipe._rew_acc)      # (the pipelined loop's recurrent state is one decision ahead)
+    assert all(pipe.model._acts_ok[:T - 1]) == all(dev.model._acts_ok[:T - 1])
+    # across the update and the re-priming after it
+    for _ in range(T + 3):
+        dev.control_step(); pipe.control_step_host_pipelined(n_parts=3)
+    torch.cuda.synchronize()
+    assert dev.n_updates == pipe.n_updates == 2 and dev.model.t == pipe.model.t
+    assert dev.model.n_forward == pipe.model.n_forward
+    assert torch.isfinite(pipe.model.P).all()
+    # gradients are accumulated with fp32 atomics (order-dependent), so parameters agree to rounding only
+    assert float((dev.model.P - pipe.model.P).abs().max()) < 1e-4

@@ -350,13 +350,13 @@ def main():
     line = {"metric": "agent-env-steps/sec", "value": value, "unit": "agent-env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if (mode == "sim" or args.fp32_gemm) else "f32 (sim, cell, loss, optimizer) + tf32 GEMMs",
+            "dtype": "f32" if mode == "sim" else "f32 (sim, LSTM cell, loss, optimizer) + bf16 tensor-core operands with f32 accumulation (learner GEMMs)",
             "data": "synthetic",
             "config": {"workload": workload_name(R, mode), "replicas_per_gpu": R, "agents": net.n_nodes,
                        "burnin_control_steps": args.burnin, "mode": mode, "n_step": N_STEP,
                        "updates_in_timed_region": n_updates_timed, "untimed_alignment_steps": align_steps,
-                       "learner_gemm_library": "cuBLAS %s (3 plain batched GEMMs per update chunk + 1 per step)"
-                       % ("fp32" if args.fp32_gemm else "TF32 tensor cores, fp32 accumulate")
+                       "learner_gemm_library": "own tcgen05 kernels for the forward, BPTT and all weight gradients; cuBLAS "
+                                               "bf16 only for dX = dZ.Wx^T (1 plain batched GEMM per update chunk)"
                        if mode == "train" else None,
                        "l2": "inputs larger than L2: %.0f MB of replica state per GPU is streamed every step"
                              % (R * sim.info()["state_bytes_per_replica"] / 1e6),

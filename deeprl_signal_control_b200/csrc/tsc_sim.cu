@@ -77,6 +77,13 @@ struct StepArgs {
   int32_t n_sub;      // sub-steps to run (0 = observe only)
   int32_t train_mode;
   int32_t rep0;       // first replica of this launch (replica-range launches of the host-buffer pipeline)
+  int32_t sub0;       // first sub-step of this launch within the control interval (0 except in record mode, which
+                      // advances one simulated second per launch so that per-second traffic statistics can be read)
+  // record mode (evaluation runs, envs/env.py:498-542): per-vehicle trip word and the arrival log
+  uint32_t* trip;     // [R][n_slots]  depart:12 | total wait s:12 | wait episodes:8, parallel to veh
+  uint32_t* trip_log; // [R][trip_cap][2]  {depart:12 | arrival:12 | route:8, wait s:16 | wait episodes:16}
+  int32_t* trip_cnt;  // [R]
+  int32_t trip_cap;
   // io
   const int32_t* action;
   const float* fp;
@@ -156,7 +163,10 @@ __device__ __forceinline__ float clipf(float x, float hi) {
 }
 
 // Vehicle record = 12 bytes {pos f32, speed f32, meta0}; stored SoA both in HBM and in shared memory.
-struct Ring { float* x; float* v; uint32_t* m; };
+struct Ring { float* x; float* v; uint32_t* m; uint32_t* t; };   // t: trip word (record mode only, else null)
+#define T1_DEPART(t) ((t) & 4095u)
+#define T1_WAIT(t) (((t) >> 12) & 4095u)
+#define T1_WCNT(t) ((t) >> 24)
 __device__ __forceinline__ uint3 ld3(const Ring& r, int i) {
   return make_uint3(__float_as_uint(r.x[i]), __float_as_uint(r.v[i]), r.m[i]);
 }
@@ -269,6 +279,8 @@ __device__ __forceinline__ void node_signal(const DevNet& n, int i, int a, int p
 // ------------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// REC = record mode: a fourth ring word per vehicle (trip word) and the arrival log; compiled out of the hot variant.
+template <bool REC>
 __global__ void __launch_bounds__(TSC_THREADS, TSC_MIN_BLOCKS)
 tsc_step_kernel(const StepArgs A) {
   const DevNet& n = A.net;
@@ -282,7 +294,8 @@ tsc_step_kernel(const StepArgs A) {
   ring.x = reinterpret_cast<float*>(smem_raw);
   ring.v = ring.x + n.n_slots;
   ring.m = reinterpret_cast<uint32_t*>(ring.v + n.n_slots);
-  int32_t* s_cnt = reinterpret_cast<int32_t*>(ring.m + n.n_slots);
+  ring.t = REC ? ring.m + n.n_slots : nullptr;
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(ring.m + (REC ? 2 : 1) * n.n_slots);
   int32_t* s_head = s_cnt + L;
   int32_t* s_pre = s_head + L;              // L + 1
   float* s_headlim = reinterpret_cast<float*>(s_pre + L + 1);
@@ -327,10 +340,11 @@ tsc_step_kernel(const StepArgs A) {
       int lane = find_lane(s_pre, L, k);
       int rank = k - s_pre[lane];
       st3(ring, __ldg(&n.lane[lane].slot0) + rank, make_uint3(g_x[k], g_v[k], g_m[k]));
+      if constexpr (REC) ring.t[__ldg(&n.lane[lane].slot0) + rank] = A.trip[(size_t)rep * n.n_slots + k];
     }
   }
   for (int i = tid; i < N; i += TSC_THREADS)
-    node_signal(n, i, s_act[i], s_prev[i], c.yellow_interval_sec > 0, s_opn, s_maj, s_yel);
+    node_signal(n, i, s_act[i], s_prev[i], A.sub0 < c.yellow_interval_sec, s_opn, s_maj, s_yel);
   __syncthreads();
 
   const uint32_t seed_lo = (uint32_t)s_misc[1], seed_hi = (uint32_t)s_misc[2];
@@ -343,7 +357,7 @@ tsc_step_kernel(const StepArgs A) {
   //   [A1 + scan part 1] | [scan part 2 + A2] | B (1 barrier per batch + 1) | C | [D + E]  -> 6 barriers.
   const int per = (L + TSC_THREADS - 1) / TSC_THREADS;
   const int l_lo = tid * per, l_hi = min(L, l_lo + per);
-  for (int sub = 0; sub < A.n_sub; ++sub) {
+  for (int sub = A.sub0; sub < A.sub0 + A.n_sub; ++sub) {
     const uint32_t t_abs = (uint32_t)cur_sec;
     // A1: approach masks + reset of per-lane scratch (own lanes)
     for (int l = l_lo; l < l_hi; ++l) {
@@ -487,6 +501,15 @@ tsc_step_kernel(const StepArgs A) {
             }
           }
           uint32_t w = M0_WAIT(me.z);
+          if constexpr (REC) {      // tripinfo waitingTime / waitingCount (envs/env.py:498-515)
+            if (vn < 0.1f) {
+              uint32_t t1 = ring.t[slot];
+              uint32_t wt = T1_WAIT(t1), wc = T1_WCNT(t1);
+              if (wt < 4095u) wt++;
+              if (w == 0 && wc < 255u) wc++;
+              ring.t[slot] = T1_DEPART(t1) | (wt << 12) | (wc << 24);     // own slot: nobody else reads the trip word
+            }
+          }
           if (vn < 0.1f) {
             if (w < 1023u) w++;
           } else {
@@ -541,6 +564,7 @@ tsc_step_kernel(const StepArgs A) {
         e.x = __float_as_uint(x);
         e.z = (h.z & ~(63u << 10)) | ((hop + 1) << 10);
         st3(ring, tc.slot0 + idx, e);
+        if constexpr (REC) ring.t[tc.slot0 + idx] = ring.t[sc2.slot0 + s_head[src]];
         cur++; tail_x = x; have_tail = true;
         s_acc[src] = 1;
       }
@@ -561,7 +585,19 @@ tsc_step_kernel(const StepArgs A) {
       if (cl > 0) {
         const uint8_t f = s_hflag[l];
         bool pop = false;
-        if (f == F_ARRIVE) { pop = true; atomicAdd(&s_misc[4], 1); }
+        if (f == F_ARRIVE) {
+          pop = true; atomicAdd(&s_misc[4], 1);
+          if constexpr (REC) {      // one tripinfo row
+            const int slot_h = lc.slot0 + s_head[l];
+            const uint32_t t1 = ring.t[slot_h], m0 = ring.m[slot_h];
+            const int at = atomicAdd(&s_misc[5], 1);
+            if (at < A.trip_cap) {
+              uint32_t* row = A.trip_log + ((size_t)rep * A.trip_cap + at) * 2;
+              row[0] = T1_DEPART(t1) | (((uint32_t)(cur_sec + 1) & 4095u) << 12) | (M0_ROUTE(m0) << 24);
+              row[1] = T1_WAIT(t1) | (T1_WCNT(t1) << 16);
+            }
+          }
+        }
         else if (f == F_CROSS) {
           if (s_acc[l]) pop = true;
           else {
@@ -611,6 +647,7 @@ tsc_step_kernel(const StepArgs A) {
               e.y = __float_as_uint(0.0f);
               e.z = ((uint32_t)__ldg(&n.src_route[q]) << 16) | ((uint32_t)sfq << 24);
               st3(ring, lc.slot0 + idx, e);
+              if constexpr (REC) ring.t[lc.slot0 + idx] = (uint32_t)t_abs & 4095u;      // depart second
               cl++;
               b_new--;
               n_dep_add++;
@@ -719,12 +756,17 @@ tsc_step_kernel(const StepArgs A) {
       if (idx >= lc.cap) idx -= lc.cap;
       const uint3 e = ld3(ring, lc.slot0 + idx);
       g_x[k] = e.x; g_v[k] = e.y; g_m[k] = e.z;
+      if constexpr (REC) A.trip[(size_t)rep * n.n_slots + k] = ring.t[lc.slot0 + idx];
     }
   }
   uint8_t* g_cnt_w = A.lane_cnt + (size_t)rep * n.lpad;
   for (int l = tid; l < L; l += TSC_THREADS) g_cnt_w[l] = (uint8_t)s_cnt[l];
-  if (tid == 0) { g_ctl[0] = cur_sec; g_ctl[3] = s_misc[3]; g_ctl[4] = s_misc[4]; }
-  for (int i = tid; i < N; i += TSC_THREADS) g_ctl[CTL_FIXED + i] = s_act[i];   // prev_action = action
+  if (tid == 0) {
+    g_ctl[0] = cur_sec; g_ctl[3] = s_misc[3]; g_ctl[4] = s_misc[4];
+    if constexpr (REC) { g_ctl[5] = s_misc[5]; A.trip_cnt[rep] = s_misc[5] < A.trip_cap ? s_misc[5] : A.trip_cap; }
+  }
+  if (A.sub0 + A.n_sub >= c.control_interval_sec)      // the interval is complete: prev_action = action
+    for (int i = tid; i < N; i += TSC_THREADS) g_ctl[CTL_FIXED + i] = s_act[i];
   for (int q = tid; q < n.n_src; q += TSC_THREADS) g_ctl[CTL_FIXED + N + q] = s_backlog[q];
   if (A.meas) {
     int32_t* m = A.meas + (size_t)rep * (3 * n.n_det + N);
@@ -752,7 +794,8 @@ __global__ void tsc_reset_kernel(uint8_t* lane_cnt, int32_t* ctl, int32_t* meas,
 // stats[r] = {n_live, n_departed_total, n_arrived_total, avg_wait, avg_speed, avg_queue, std_queue, backlog}
 // avg/std_queue: lane halting number (speed < 0.1 m/s, whole lane) over the detector lanes (envs/env.py:422-427).
 __global__ void tsc_stats_kernel(const DevNet n, const uint32_t* __restrict__ veh, const uint8_t* __restrict__ lane_cnt,
-                                 const int32_t* __restrict__ ctl, int ctl_words, float* __restrict__ stats) {
+                                 const int32_t* __restrict__ ctl, int ctl_words, float* __restrict__ stats,
+                                 int row_stride) {
   extern __shared__ int32_t sh[];
   int32_t* s_pre = sh;                 // [L + 1]
   int32_t* s_halt = sh + n.n_lanes + 1; // [L]
@@ -791,7 +834,7 @@ __global__ void tsc_stats_kernel(const DevNet n, const uint32_t* __restrict__ ve
     if (var < 0.f) var = 0.f;
     int backlog = 0;
     for (int s2 = 0; s2 < n.n_src; ++s2) backlog += c[CTL_FIXED + n.n_nodes + s2];
-    float* o = stats + (size_t)rep * 8;
+    float* o = stats + (size_t)rep * row_stride;
     o[0] = (float)V; o[1] = (float)c[3]; o[2] = (float)c[4];
     o[3] = V > 0 ? red[0] / (float)V : 0.f; o[4] = V > 0 ? red[1] / (float)V : 0.f;
     o[5] = mq; o[6] = sqrtf(var); o[7] = (float)backlog;
@@ -823,7 +866,9 @@ struct tsc_handle {
   int device = 0;
   int R = 0;
   StepArgs args{};
-  int smem = 0;
+  int smem = 0, smem_rec = 0;
+  bool record = false;       // record mode (tsc_set_record): trip words + arrival log, one simulated second per launch
+  uint32_t* d_trip = nullptr; uint32_t* d_trip_log = nullptr; int32_t* d_trip_cnt = nullptr; int trip_cap = 0;
   std::vector<void*> owned;  // device allocations
   // io scratch for the host-buffer entry point
   int32_t* d_action = nullptr; float* d_fp = nullptr; float* d_obs = nullptr; float* d_reward = nullptr;
@@ -935,7 +980,10 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
         ((size_t)(net->n_slots + 31) / 32 + 1) * 4 + (size_t)net->n_det * 8;
   h->smem = (int)sm;
   if (sm > 227 * 1024) { tsc_destroy(h); return fail("tsc_create: replica state exceeds 227 KB of shared memory"); }
-  CK(cudaFuncSetAttribute(tsc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  CK(cudaFuncSetAttribute(tsc_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  h->smem_rec = h->smem + (int)net->n_slots * 4;
+  if (h->smem_rec <= 232448)
+    CK(cudaFuncSetAttribute(tsc_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_rec));
   std::vector<uint64_t> seeds(R, 0);
   *out = h;
   return tsc_reset(h, seeds.data(), nullptr);
@@ -971,11 +1019,18 @@ extern "C" int tsc_set_train_mode(tsc_handle* h, int32_t m) {
 }
 
 static int launch(tsc_handle* h, int n_sub, const int32_t* action, const float* fp, float* obs, float* reward,
-                  float* greward, uint8_t* done, cudaStream_t st, int rep0 = 0, int count = -1) {
+                  float* greward, uint8_t* done, cudaStream_t st, int rep0 = 0, int count = -1, int sub0 = 0) {
   StepArgs a = h->args;
   a.n_sub = n_sub; a.action = action; a.fp = fp; a.obs = obs; a.reward = reward; a.greward = greward; a.done = done;
   a.rep0 = rep0;
-  tsc_step_kernel<<<count < 0 ? h->R : count, TSC_THREADS, h->smem, st>>>(a);
+  if (h->record) {
+    a.trip = h->d_trip; a.trip_log = h->d_trip_log; a.trip_cnt = h->d_trip_cnt; a.trip_cap = h->trip_cap;
+    a.sub0 = sub0;
+    tsc_step_kernel<true><<<count < 0 ? h->R : count, TSC_THREADS, h->smem_rec, st>>>(a);
+  } else {
+    a.sub0 = sub0;
+    tsc_step_kernel<false><<<count < 0 ? h->R : count, TSC_THREADS, h->smem, st>>>(a);
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1033,6 +1088,61 @@ extern "C" int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, c
   if (greward_host) CK(cudaMemcpyAsync(greward_host, h->d_greward + r0, n * 4, cudaMemcpyDeviceToHost, st));
   if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done + r0, n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- evaluation / recording path (envs/env.py:409-437, 498-542) ---------------------------------------------------
+extern "C" int tsc_set_record(tsc_handle* h, int32_t on) {
+  if (!h) return fail("tsc_set_record: null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  if (on && !h->d_trip) {
+    if (h->smem_rec > 232448) return fail("tsc_set_record: the record-mode ring image does not fit in shared memory");
+    h->trip_cap = 8192;
+    if (dalloc(h, (size_t)h->R * h->args.net.n_slots, &h->d_trip)) return -1;
+    if (dalloc(h, (size_t)h->R * h->trip_cap * 2, &h->d_trip_log)) return -1;
+    if (dalloc(h, (size_t)h->R, &h->d_trip_cnt)) return -1;
+  }
+  if (on) {      // a fresh log; trip words of vehicles already in the network start from zero
+    CK(cudaMemset(h->d_trip, 0, (size_t)h->R * h->args.net.n_slots * 4));
+    CK(cudaMemset(h->d_trip_cnt, 0, (size_t)h->R * 4));
+  }
+  h->record = on != 0;
+  return 0;
+}
+
+extern "C" int tsc_step_record(tsc_handle* h, const int32_t* action_dev, const float* fp_dev, float* obs_dev,
+                               float* reward_dev, float* greward_dev, uint8_t* done_dev, float* sub_stats_dev,
+                               void* stream) {
+  if (!h || !action_dev) return fail("tsc_step_record: bad argument");
+  if (!h->record) return fail("tsc_step_record: record mode is off (tsc_set_record)");
+  CK(cudaSetDevice(h->device));
+  const int ci = h->args.cfg.control_interval_sec;
+  const DevNet& d = h->args.net;
+  for (int t = 0; t < ci; ++t) {
+    const bool last = t + 1 == ci;
+    if (launch(h, 1, action_dev, fp_dev, last ? obs_dev : nullptr, last ? reward_dev : nullptr,
+               last ? greward_dev : nullptr, last ? done_dev : nullptr, (cudaStream_t)stream, 0, -1, t))
+      return -1;
+    if (sub_stats_dev) {
+      tsc_stats_kernel<<<h->R, 128, (2 * d.n_lanes + 1) * 4, (cudaStream_t)stream>>>(
+          d, h->args.veh, h->args.lane_cnt, h->args.ctl, h->args.ctl_words, sub_stats_dev + (size_t)t * 8, ci * 8);
+      CK(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+extern "C" int tsc_get_trips(tsc_handle* h, int32_t replica, uint32_t* rows_host, int32_t max_rows, int32_t* n_rows) {
+  if (!h || replica < 0 || replica >= h->R || !rows_host || !n_rows) return fail("tsc_get_trips: bad argument");
+  if (!h->d_trip_log) { *n_rows = 0; return 0; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  int32_t cnt = 0;
+  CK(cudaMemcpy(&cnt, h->d_trip_cnt + replica, 4, cudaMemcpyDeviceToHost));
+  if (cnt > max_rows) cnt = max_rows;
+  if (cnt > 0) CK(cudaMemcpy(rows_host, h->d_trip_log + (size_t)replica * h->trip_cap * 2, (size_t)cnt * 8, cudaMemcpyDeviceToHost));
+  *n_rows = cnt;
   return 0;
 }
 
@@ -1101,7 +1211,7 @@ extern "C" int tsc_get_traffic_stats(tsc_handle* h, float* stats_dev, void* stre
   CK(cudaSetDevice(h->device));
   const DevNet& d = h->args.net;
   tsc_stats_kernel<<<h->R, 128, (2 * d.n_lanes + 1) * 4, (cudaStream_t)stream>>>(d, h->args.veh, h->args.lane_cnt,
-                                                                                   h->args.ctl, h->args.ctl_words, stats_dev);
+                                                                                   h->args.ctl, h->args.ctl_words, stats_dev, 8);
   CK(cudaGetLastError());
   return 0;
 }

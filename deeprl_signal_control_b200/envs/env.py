@@ -165,7 +165,7 @@ class TrafficSimulator:
     def _init_policy(self):                                           # envs/env.py:263-269
         return [np.array([1. / self.nodes[n].n_a] * self.nodes[n].n_a) for n in self.node_names]
 
-    # ---- data recording (eval path; CSV writers are SURVEY §8f.1, not built this round) --------
+    # ---- data recording (evaluation runs): envs/env.py:409-437, 498-542 ---------------------------
     def init_data(self, is_record, record_stats, output_path):
         self.is_record = is_record
         self.record_stats = record_stats
@@ -179,15 +179,38 @@ class TrafficSimulator:
         self.test_num = len(test_seeds)
         self.test_seeds = test_seeds
 
+    def _record_traffic(self, stats, sec0):
+        """`_measure_traffic_step` rows (envs/env.py:409-437) of replica 0 from the per-second statistics of one
+        control step; departed / arrived are per second there, cumulative in the library."""
+        for k, st in enumerate(stats):
+            dep, arr = int(st[1]), int(st[2])
+            self.traffic_data.append({'episode': self.cur_episode, 'time_sec': sec0 + k + 1,
+                                      'number_total_car': int(st[0]),
+                                      'number_departed_car': dep - self._n_dep_prev,
+                                      'number_arrived_car': arr - self._n_arr_prev,
+                                      'avg_wait_sec': float(st[3]), 'avg_speed_mps': float(st[4]),
+                                      'std_queue': float(st[6]), 'avg_queue': float(st[5])})
+            self._n_dep_prev, self._n_arr_prev = dep, arr
+
     def collect_tripinfo(self):
-        logging.warning('Env: trip info recording is not built in this round (SURVEY §8f.1)')
+        """Trip rows of the episode that just finished (the reference parses SUMO's --tripinfo-output,
+        envs/env.py:498-515; here: the arrival log of replica 0, `tsc_get_trips`)."""
+        if not self.is_record or self._sim is None:
+            return
+        for dep, arr, route, wsec, wcnt in self._sim.trips(0):
+            self.trip_data.append({'episode': self.cur_episode, 'id': 'r%d.%d' % (route, dep),
+                                   'depart_sec': float(dep), 'arrival_sec': float(arr),
+                                   'duration_sec': float(arr - dep), 'wait_step': int(wcnt), 'wait_sec': float(wsec)})
 
     def output_data(self):
         if not self.is_record:
             logging.error('Env: no record to output!')
             return
         import pandas as pd
-        pd.DataFrame(self.control_data).to_csv(self.output_path + ('%s_%s_control.csv' % (self.name, self.agent)))
+        base = self.output_path + ('%s_%s_' % (self.name, self.agent))
+        pd.DataFrame(self.control_data).to_csv(base + 'control.csv')
+        pd.DataFrame(self.traffic_data).to_csv(base + 'traffic.csv')
+        pd.DataFrame(self.trip_data).to_csv(base + 'trip.csv')
 
     # ---- simulator lifecycle --------------------------------------------------------------------
     def _ensure_sim(self):
@@ -211,6 +234,9 @@ class TrafficSimulator:
         sim = self._ensure_sim()
         sim.reset(self._episode_seeds(seed))
         sim.set_train_mode(self.train_mode)
+        if self.is_record:
+            sim.set_record(True)                                      # trip words + arrival log from second 0
+            self._n_dep_prev = self._n_arr_prev = 0
         self.cur_sec = 0
         self.cur_episode += 1
         if self.agent == 'ma2c':
@@ -246,7 +272,14 @@ class TrafficSimulator:
         sim = self._ensure_sim()
         sim.set_train_mode(self.train_mode)
         act = np.asarray(action, dtype=np.int32).reshape(self.n_replicas, -1)
-        obs, reward, greward, done = sim.step_host(act, self._fp_array())
+        if self.is_record:
+            import torch
+            fp = self._fp_array()
+            o, r, g, d, st = sim.step_record(torch.from_numpy(act), None if fp is None else torch.from_numpy(fp).to(sim.device))
+            obs, reward, greward, done = o.cpu().numpy(), r.cpu().numpy(), g.cpu().numpy(), d.cpu().numpy()
+            self._record_traffic(st[0].cpu().numpy(), self.cur_sec)
+        else:
+            obs, reward, greward, done = sim.step_host(act, self._fp_array())
         self.cur_sec += self.control_interval_sec
         for name, a in zip(self.node_names, act[0]):
             self.nodes[name].prev_action = int(a)

@@ -113,6 +113,35 @@ class BatchedSim:
                                                   _np(fp, C.c_float), _np(obs, C.c_float), _np(reward, C.c_float),
                                                   _np(greward, C.c_float), _np(done, C.c_uint8), self._stream()))
 
+    # ---- evaluation / recording path (envs/env.py:409-437, 498-542) ------------------------
+    def set_record(self, on: bool = True) -> None:
+        """Record mode: per-vehicle trip words + arrival log (call right after reset())."""
+        _lib.check(_lib.lib().tsc_set_record(self._h, C.c_int32(1 if on else 0)))
+        self.record = bool(on)
+
+    def step_record(self, action: torch.Tensor, fp: Optional[torch.Tensor] = None):
+        """step() one simulated second per launch; also returns the per-second traffic statistics
+        [R, control_interval_sec, 8] (fields of traffic_stats())."""
+        n = self.net
+        action = action.to(self.device, torch.int32).contiguous()
+        obs = torch.empty(self.R, n.n_obs, dtype=torch.float32, device=self.device)
+        reward = torch.empty(self.R, n.n_nodes, dtype=torch.float32, device=self.device)
+        greward = torch.empty(self.R, dtype=torch.float32, device=self.device)
+        done = torch.empty(self.R, dtype=torch.uint8, device=self.device)
+        stats = torch.zeros(self.R, self.params.control_interval_sec, 8, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().tsc_step_record(self._h, _ptr(action), _ptr(fp), _ptr(obs), _ptr(reward), _ptr(greward),
+                                              _ptr(done), _ptr(stats), self._stream()))
+        return obs, reward, greward, done, stats
+
+    def trips(self, replica: int = 0) -> np.ndarray:
+        """tripinfo rows of one replica: int array [n, 5] = depart_sec, arrival_sec, route, wait_sec, wait_count."""
+        rows = np.zeros((8192, 2), np.uint32)
+        nr = C.c_int32(0)
+        _lib.check(_lib.lib().tsc_get_trips(self._h, C.c_int32(replica), _np(rows, C.c_uint32), C.c_int32(len(rows)),
+                                            C.byref(nr)))
+        w0, w1 = rows[:nr.value, 0].astype(np.int64), rows[:nr.value, 1].astype(np.int64)
+        return np.stack([w0 & 4095, (w0 >> 12) & 4095, w0 >> 24, w1 & 65535, w1 >> 16], axis=1)
+
     # ---- parity taps ---------------------------------------------------------------------
     def counts(self):
         n = self.net

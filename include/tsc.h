@@ -154,6 +154,19 @@ int tsc_step_host(tsc_handle* h, const int32_t* action_host, const float* fp_hos
 int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host, const float* fp_host,
                         float* obs_host, float* reward_host, float* greward_host, uint8_t* done_host, void* stream);
 
+/* ---- evaluation / recording path (replaces the per-second TraCI reads of `_measure_traffic_step` and SUMO's
+ * --tripinfo-output; reference envs/env.py:409-437, 461-471, 498-542) ------------------------------------------
+ * tsc_set_record(on): keep a trip word per vehicle (depart second, total waiting seconds, waiting episodes) and log
+ *   one row per arrival.  Call right after tsc_reset; costs one more 4-byte word per vehicle slot in shared memory.
+ * tsc_step_record: tsc_step advanced one simulated second per launch; sub_stats_dev [R][control_interval_sec][8]
+ *   (may be NULL) receives the tsc_get_traffic_stats fields after every second.  Results equal tsc_step's.
+ * tsc_get_trips: the arrival log of one replica, rows_host [max_rows][2] uint32:
+ *   word 0 = depart_sec:12 | arrival_sec:12 | route:8,  word 1 = waiting seconds:16 | waiting episodes:16. */
+int tsc_set_record(tsc_handle* h, int32_t on);
+int tsc_step_record(tsc_handle* h, const int32_t* action_dev, const float* fp_dev, float* obs_dev, float* reward_dev,
+                    float* greward_dev, uint8_t* done_dev, float* sub_stats_dev, void* stream);
+int tsc_get_trips(tsc_handle* h, int32_t replica, uint32_t* rows_host, int32_t max_rows, int32_t* n_rows);
+
 /* Integer parity taps measured at the end of the last step, per detector lane
  * (lanearea.getLastStepVehicleNumber / getLastStepHaltingNumber / head getWaitingTime,
  * envs/env.py:333-349,377-395) and per node (the phase index = action applied).

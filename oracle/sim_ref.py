@@ -101,3 +101,40 @@ class RefSim:
         lib().ref_get_misc(self.h, C.c_int32(replica), _p(out, C.c_int32))
         return dict(cur_sec=int(out[0]), departed=int(out[1]), arrived=int(out[2]),
                     backlog=int(out[3]), live=int(out[4]))
+
+    # ---- evaluation / recording path (envs/env.py:409-437, 498-542) --------------------------
+    def set_record(self, on: bool = True):
+        lib().ref_set_record(self.h, int(on))
+
+    def traffic_stats(self):
+        out = np.zeros((self.R, 8), np.float32)
+        lib().ref_traffic_stats(self.h, _p(out, C.c_float))
+        return out
+
+    def step_record(self, action, fp=None):
+        """step() one simulated second at a time; also returns the per-second traffic statistics
+        [R, control_interval_sec, 8]."""
+        n = self.net
+        action = np.ascontiguousarray(action, np.int32).reshape(self.R, n.n_nodes)
+        fp = None if fp is None else np.ascontiguousarray(fp, np.float32)
+        obs = np.zeros((self.R, n.n_obs), np.float32)
+        reward = np.zeros((self.R, n.n_nodes), np.float32)
+        greward = np.zeros(self.R, np.float32)
+        done = np.zeros(self.R, np.uint8)
+        stats = np.zeros((self.R, self.params.control_interval_sec, 8), np.float32)
+        lib().ref_step_record(self.h, _p(action, C.c_int32), _p(fp, C.c_float), _p(obs, C.c_float),
+                              _p(reward, C.c_float), _p(greward, C.c_float), _p(done, C.c_uint8),
+                              _p(stats, C.c_float))
+        return obs, reward, greward, done, stats
+
+    def trips(self, replica: int = 0):
+        """tripinfo rows of one replica: int array [n, 5] = depart_sec, arrival_sec, route, wait_sec, wait_count."""
+        rows = np.zeros((8192, 2), np.uint32)
+        nr = C.c_int32(0)
+        lib().ref_get_trips(self.h, C.c_int32(replica), _p(rows, C.c_uint32), C.c_int32(len(rows)), C.byref(nr))
+        return decode_trips(rows[:nr.value])
+
+
+def decode_trips(rows: np.ndarray) -> np.ndarray:
+    w0, w1 = rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64)
+    return np.stack([w0 & 4095, (w0 >> 12) & 4095, w0 >> 24, w1 & 65535, w1 >> 16], axis=1)

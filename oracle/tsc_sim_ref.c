@@ -59,6 +59,12 @@ typedef struct {
   int32_t* det_veh;     /* [n_det] */
   int32_t* det_halt;
   int32_t* det_wait;
+  /* record mode (evaluation runs, envs/env.py:498-542): trip word per ring slot, parallel to `ring`
+   * (depart:12 | total wait s:12 | wait episodes:8), and the arrival log = tripinfo rows
+   * {depart:12 | arrival:12 | route:8, wait s:16 | wait episodes:16}; NULL when record mode is off */
+  uint32_t* trip;       /* [n_slots] */
+  uint32_t* trip_log;   /* [trip_cap][2] */
+  int32_t trip_cnt, trip_cap;
 } replica_t;
 
 typedef struct ref_sim {
@@ -145,6 +151,9 @@ static inline veh_t* veh_at(const tsc_net* n, replica_t* r, int lane, int rank) 
 #define M0_HOP(m) (((m) >> 10) & 63u)
 #define M0_ROUTE(m) (((m) >> 16) & 255u)
 #define M0_SFQ(m) ((m) >> 24)
+#define T1_DEPART(t) ((t) & 4095u)
+#define T1_WAIT(t) (((t) >> 12) & 4095u)
+#define T1_WCNT(t) ((t) >> 24)
 
 /* signal state of every node for one sub-step: reference envs/env.py:128-152 */
 static void node_signal(const ref_sim* s, const replica_t* r, int yellow_phase, uint32_t* open,
@@ -281,6 +290,13 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       v->pos = xnew[slot];
       v->spd = vnew[slot];
       uint32_t w = M0_WAIT(v->m0);
+      if (r->trip && v->spd < 0.1f) { /* tripinfo waitingTime / waitingCount */
+        uint32_t t1 = r->trip[slot];
+        uint32_t wt = T1_WAIT(t1), wc = T1_WCNT(t1);
+        if (wt < 4095u) wt++;
+        if (w == 0 && wc < 255u) wc++;
+        r->trip[slot] = T1_DEPART(t1) | (wt << 12) | (wc << 24);
+      }
       if (v->spd < 0.1f) {
         if (w < 1023u) w++;
       } else {
@@ -321,6 +337,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       e->pos = x;
       e->m0 = (h->m0 & ~(63u << 10)) | ((hop + 1) << 10);
       flag[n->lane_slot0[t] + idx] = 0;
+      if (r->trip) r->trip[n->lane_slot0[t] + idx] = r->trip[hslot];
       cur++; tail_x = x; have_tail = 1;
       accepted[src] = 1;
     }
@@ -332,7 +349,18 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       veh_t* h = veh_at(n, r, l, 0);
       int hslot = (int)(h - r->ring);
       int pop = 0;
-      if (flag[hslot] == F_ARRIVE) { pop = 1; r->n_arrived++; }
+      if (flag[hslot] == F_ARRIVE) {
+        pop = 1; r->n_arrived++;
+        if (r->trip) { /* one tripinfo row */
+          if (r->trip_cnt < r->trip_cap) {
+            uint32_t t1 = r->trip[hslot];
+            uint32_t* row = r->trip_log + 2 * (size_t)r->trip_cnt;
+            row[0] = T1_DEPART(t1) | (((uint32_t)(r->cur_sec + 1) & 4095u) << 12) | (M0_ROUTE(h->m0) << 24);
+            row[1] = T1_WAIT(t1) | (T1_WCNT(t1) << 16);
+          }
+          r->trip_cnt++;
+        }
+      }
       else if (flag[hslot] == F_CROSS) {
         if (accepted[l]) pop = 1;
         else { h->pos = n->lane_len[l] - 0.01f; h->spd = 0.0f; }
@@ -387,6 +415,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       veh_t* e = &r->ring[n->lane_slot0[lane] + idx];
       e->pos = pos; e->spd = 0.0f;
       e->m0 = ((uint32_t)n->src_route[q] << 16) | ((uint32_t)sfq << 24);
+      if (r->trip) r->trip[n->lane_slot0[lane] + idx] = t_abs & 4095u; /* depart second */
       r->cnt[lane] = cnt + 1;
       r->backlog[q]--;
       r->n_departed++;
@@ -522,6 +551,7 @@ void ref_destroy(ref_sim* s) {
     replica_t* r = &s->rep[i];
     free(r->ring); free(r->head); free(r->cnt); free(r->prev_action); free(r->cur_action);
     free(r->backlog); free(r->det_veh); free(r->det_halt); free(r->det_wait);
+    free(r->trip); free(r->trip_log);
   }
   free(s->rep);
   free(s); /* table copies are leaked on purpose-free builds: test infrastructure */
@@ -537,7 +567,7 @@ void ref_reset(ref_sim* s, const uint64_t* seeds) {
     memset(r->backlog, 0, 4 * (size_t)n->n_src);
     memset(r->det_veh, 0, 4 * (size_t)n->n_det); memset(r->det_halt, 0, 4 * (size_t)n->n_det);
     memset(r->det_wait, 0, 4 * (size_t)n->n_det);
-    r->cur_sec = 0; r->n_departed = 0; r->n_arrived = 0;
+    r->cur_sec = 0; r->n_departed = 0; r->n_arrived = 0; r->trip_cnt = 0;
     r->seed_lo = (uint32_t)(seeds[i] & 0xffffffffu); r->seed_hi = (uint32_t)(seeds[i] >> 32);
   }
 }
@@ -615,6 +645,102 @@ void ref_step_mt(ref_sim* s, const int32_t* action, const float* fp, float* obs,
 void ref_step(ref_sim* s, const int32_t* action, const float* fp, float* obs, float* reward,
               float* greward, uint8_t* done) {
   ref_step_mt(s, action, fp, obs, reward, greward, done, 1);
+}
+
+/* ---- evaluation / recording path (envs/env.py:409-437, 498-542) --------------------------------- */
+/* record mode on: allocate the trip words and the arrival log (call right after ref_reset) */
+void ref_set_record(ref_sim* s, int32_t on) {
+  const tsc_net* n = &s->net;
+  for (int i = 0; i < s->R; ++i) {
+    replica_t* r = &s->rep[i];
+    free(r->trip); free(r->trip_log);
+    r->trip = 0; r->trip_log = 0; r->trip_cnt = 0; r->trip_cap = 0;
+    if (on) {
+      r->trip = (uint32_t*)calloc((size_t)n->n_slots, 4);
+      r->trip_cap = 8192;
+      r->trip_log = (uint32_t*)calloc((size_t)r->trip_cap * 2, 4);
+    }
+  }
+}
+
+/* _measure_traffic_step for every replica: out[r] = {n_live, departed_total, arrived_total, avg_wait, avg_speed,
+ * avg_queue, std_queue, backlog}; queue = vehicles slower than 0.1 m/s on the whole detector lane
+ * (lane.getLastStepHaltingNumber, envs/env.py:425) */
+void ref_traffic_stats(ref_sim* s, float* out) {
+  const tsc_net* n = &s->net;
+  for (int i = 0; i < s->R; ++i) {
+    replica_t* r = &s->rep[i];
+    int V = 0, wsum = 0, backlog = 0;
+    float sp = 0.0f;
+    int32_t* halt = (int32_t*)calloc((size_t)n->n_lanes, 4);
+    for (int l = 0; l < n->n_lanes; ++l)
+      for (int k = 0; k < r->cnt[l]; ++k) {
+        veh_t* v = veh_at(n, r, l, k);
+        V++; wsum += (int)M0_WAIT(v->m0); sp = sp + v->spd;
+        if (v->spd < 0.1f) halt[l]++;
+      }
+    float q = 0.0f, q2 = 0.0f;
+    for (int d = 0; d < n->n_det; ++d) { float h = (float)halt[n->det_lane[d]]; q = q + h; q2 = q2 + h * h; }
+    float nd = (float)(n->n_det > 0 ? n->n_det : 1);
+    float mq = q / nd;
+    float var = q2 / nd - mq * mq;
+    if (var < 0.0f) var = 0.0f;
+    for (int q3 = 0; q3 < n->n_src; ++q3) backlog += r->backlog[q3];
+    float* o = out + 8 * (size_t)i;
+    o[0] = (float)V; o[1] = (float)r->n_departed; o[2] = (float)r->n_arrived;
+    o[3] = V > 0 ? (float)wsum / (float)V : 0.0f; o[4] = V > 0 ? sp / (float)V : 0.0f;
+    o[5] = mq; o[6] = sqrtf(var); o[7] = (float)backlog;
+    free(halt);
+  }
+}
+
+/* step(action) one simulated second at a time, with the traffic statistics after every second:
+ * sub_stats [R][control_interval_sec][8].  Same results as ref_step. */
+void ref_step_record(ref_sim* s, const int32_t* action, const float* fp, float* obs, float* reward,
+                     float* greward, uint8_t* done, float* sub_stats) {
+  const tsc_net* n = &s->net;
+  const tsc_cfg* c = &s->cfg;
+  float* vnew = (float*)malloc(4 * (size_t)n->n_slots);
+  float* xnew = (float*)malloc(4 * (size_t)n->n_slots);
+  uint8_t* flag = (uint8_t*)calloc((size_t)n->n_slots, 1);
+  float* head_lim = (float*)malloc(4 * (size_t)n->n_lanes);
+  uint32_t* approach = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
+  uint32_t* open = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
+  uint32_t* major = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
+  uint32_t* ymask = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
+  uint8_t* accepted = (uint8_t*)malloc((size_t)n->n_lanes);
+  int32_t* cnt_add = (int32_t*)malloc(4 * (size_t)n->n_lanes);
+  float* st = (float*)malloc(4 * 8 * (size_t)s->R);
+  const int ci = c->control_interval_sec;
+  for (int i = 0; i < s->R; ++i)
+    for (int k = 0; k < n->n_nodes; ++k) s->rep[i].cur_action[k] = action[(size_t)i * n->n_nodes + k];
+  for (int t = 0; t < ci; ++t) {
+    for (int i = 0; i < s->R; ++i)
+      substep(s, &s->rep[i], t < c->yellow_interval_sec, vnew, xnew, flag, head_lim, approach, open, major, ymask,
+              accepted, cnt_add);
+    if (sub_stats) {
+      ref_traffic_stats(s, st);
+      for (int i = 0; i < s->R; ++i) memcpy(sub_stats + ((size_t)i * ci + t) * 8, st + 8 * (size_t)i, 32);
+    }
+  }
+  for (int i = 0; i < s->R; ++i) {
+    replica_t* r = &s->rep[i];
+    for (int k = 0; k < n->n_nodes; ++k) r->prev_action[k] = r->cur_action[k];
+    measure(s, r);
+    outputs(s, r, fp ? fp + (size_t)i * n->n_nodes * n->max_na : 0, obs ? obs + (size_t)i * n->n_obs : 0,
+            reward ? reward + (size_t)i * n->n_nodes : 0, greward ? greward + i : 0, done ? done + i : 0);
+  }
+  free(vnew); free(xnew); free(flag); free(head_lim); free(approach); free(open); free(major);
+  free(ymask); free(accepted); free(cnt_add); free(st);
+}
+
+/* tripinfo rows of one replica (arrival order): rows [n][2] as in replica_t.trip_log */
+void ref_get_trips(ref_sim* s, int32_t replica, uint32_t* rows, int32_t max_rows, int32_t* n_rows) {
+  replica_t* r = &s->rep[replica];
+  int m = r->trip_cnt < r->trip_cap ? r->trip_cnt : r->trip_cap;
+  if (m > max_rows) m = max_rows;
+  if (m > 0 && r->trip_log) memcpy(rows, r->trip_log, 8 * (size_t)m);
+  *n_rows = r->trip_log ? m : 0;
 }
 
 void ref_get_counts(ref_sim* s, int32_t* veh, int32_t* halt, int32_t* headwait, int32_t* phase) {

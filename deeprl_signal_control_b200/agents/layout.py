@@ -40,7 +40,10 @@ def ortho_init(rng: np.random.RandomState, shape, scale=np.sqrt(2)):
 class PolicyLayout:
     def __init__(self, n_s_ls: Sequence[int], n_a_ls: Sequence[int], n_w_ls: Sequence[int],
                  n_f_ls: Sequence[int], obs_off: Sequence[int], n_obs: int, fw: int, ft: int, ff: int = 0,
-                 h: int = 64, max_na: int | None = None):
+                 h: int = 64, max_na: int | None = None, recurrent: bool = True):
+        """recurrent=False: FcACPolicy (agents/policies.py:214-256) — the LSTM block is replaced by one fc layer
+        `wx` [dx, h] + `bl` [h] (relu), `wh` is empty."""
+        self.recurrent = bool(recurrent)
         self.A = len(n_s_ls)
         self.U = 2 * self.A
         self.n_a = np.asarray(n_a_ls, np.int32)
@@ -58,10 +61,12 @@ class PolicyLayout:
         self.kw = 32 if mw <= 32 else (48 if (mw <= 48 and self.ft == 0) else 0)
         self.fc_bwd_tc_ok = self.kw > 0 and mw < self.kw and self.dx % 8 == 0 and self.dx <= 256
         self.max_na = int(max_na or self.n_a.max())
-        U, dx, g4 = self.U, self.dx, 4 * self.h
+        U, dx, g4 = self.U, self.dx, (4 if self.recurrent else 1) * self.h
+        hr = self.h if self.recurrent else 0              # rows of wh
+        self.g4, self.hr = g4, hr
         off = 0
         self.off_wx = off; off += U * dx * g4
-        self.off_wh = off; off += U * self.h * g4
+        self.off_wh = off; off += U * hr * g4
         self.off_bl = off; off += U * g4
         self.off_wo = off; off += U * self.h * self.max_na
         self.off_bo = off; off += U * self.max_na
@@ -81,7 +86,7 @@ class PolicyLayout:
         ag = np.zeros(off, np.uint8)
         unit_agent = np.repeat(np.arange(self.A, dtype=np.uint8), 2)
         ag[self.off_wx:self.off_wh] = np.repeat(unit_agent, dx * g4)
-        ag[self.off_wh:self.off_bl] = np.repeat(unit_agent, self.h * g4)
+        ag[self.off_wh:self.off_bl] = np.repeat(unit_agent, hr * g4)
         ag[self.off_bl:self.off_wo] = np.repeat(unit_agent, g4)
         ag[self.off_wo:self.off_bo] = np.repeat(unit_agent, self.h * self.max_na)
         ag[self.off_bo:int(self.off_fcw_w[0])] = np.repeat(unit_agent, self.max_na)
@@ -106,9 +111,9 @@ class PolicyLayout:
 
     def views(self, flat):
         """Named views into a flat numpy array or torch tensor."""
-        U, dx, g4, h, mna = self.U, self.dx, 4 * self.h, self.h, self.max_na
+        U, dx, g4, h, mna = self.U, self.dx, self.g4, self.h, self.max_na
         v = {"wx": flat[self.off_wx:self.off_wh].reshape(U, dx, g4),
-             "wh": flat[self.off_wh:self.off_bl].reshape(U, h, g4),
+             "wh": flat[self.off_wh:self.off_bl].reshape(U, self.hr, g4),
              "bl": flat[self.off_bl:self.off_wo].reshape(U, g4),
              "wo": flat[self.off_wo:self.off_bo].reshape(U, h, mna),
              "bo": flat[self.off_bo:int(self.off_fcw_w[0])].reshape(U, mna)}
@@ -136,8 +141,9 @@ class PolicyLayout:
                 v["fcf_w%d" % u][...] = ortho_init(rng, (int(self.n_fp[a]), self.ff))
             if self.ft > 0 and self.n_wait[a] > 0:
                 v["fct_w%d" % u][...] = ortho_init(rng, (int(self.n_wait[a]), self.ft))
-            v["wx"][u] = ortho_init(rng, (self.dx, 4 * self.h))
-            v["wh"][u] = ortho_init(rng, (self.h, 4 * self.h))
+            v["wx"][u] = ortho_init(rng, (self.dx, self.g4))
+            if self.recurrent:
+                v["wh"][u] = ortho_init(rng, (self.h, 4 * self.h))
             n_out = int(self.n_a[a]) if u % 2 == 0 else 1
             v["wo"][u][:, :n_out] = ortho_init(rng, (self.h, n_out))
         return flat

@@ -28,7 +28,9 @@ class IA2C:
     name = 'ia2c'
 
     def __init__(self, n_s_ls, n_a_ls, n_w_ls, total_step, model_config, seed=0, n_f_ls=None,
-                 n_replicas=1, device=0, obs_off=None, **learner_kw):
+                 n_replicas=1, device=0, obs_off=None, policy='lstm', **learner_kw):
+        """policy='lstm': LstmACPolicy / FPLstmACPolicy, what the reference builds (agents/models.py:40-51);
+        policy='fc': FcACPolicy (agents/policies.py:214-256), the FC variant of BASELINE config 2."""
         self.n_agent = len(n_s_ls)
         self.reward_clip = model_config.getfloat('reward_clip')
         self.reward_norm = model_config.getfloat('reward_norm')
@@ -43,8 +45,12 @@ class IA2C:
         ff = model_config.getint('num_fp') if self.name == 'ma2c' else 0
         self.layout = PolicyLayout(self.n_s_ls, self.n_a_ls, self.n_w_ls, self.n_f_ls, obs_off, n_obs,
                                    fw=model_config.getint('num_fw'), ft=model_config.getint('num_ft'), ff=ff,
-                                   h=model_config.getint('num_lstm'))
-        self.batched = BatchedA2C(
+                                   h=model_config.getint('num_lstm'), recurrent=(policy != 'fc'))
+        if policy == 'fc':
+            from .learner_fc import BatchedFcA2C as _Learner
+        else:
+            _Learner = BatchedA2C
+        self.batched = _Learner(
             self.layout, n_replicas, self.n_step, gamma=model_config.getfloat('gamma'),
             v_coef=model_config.getfloat('value_coef'), max_grad_norm=model_config.getfloat('max_grad_norm'),
             alpha=model_config.getfloat('rmsp_alpha'), eps=model_config.getfloat('rmsp_epsilon'),

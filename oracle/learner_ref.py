@@ -2,6 +2,7 @@
 
   fc / lstm              reference agents/utils.py:66-74, 88-116  (gate order i,f,o,u; done masks c,h)
   FPLstmACPolicy         reference agents/policies.py:191-211     (h = concat(fcw, fcf, fct))
+  FcACPolicy             reference agents/policies.py:214-256     (h = relu(fc(concat(fcw, fct))), no state)
   A2C loss               reference agents/policies.py:41-52
   n-step returns         reference agents/utils.py:202-214
   clip + RMSProp         reference agents/policies.py:54-61 (TF1: rms slot starts at 1, eps inside sqrt)
@@ -36,6 +37,12 @@ def unit_forward(v, lay, u, obs, dones, c, h):
         parts.append(torch.relu(wait @ v["fct_w%d" % u] + v["fct_b%d" % u]))
     x = torch.cat(parts, -1)
     H = lay.h
+    if not getattr(lay, "recurrent", True):      # FcACPolicy: one more fc layer instead of the LSTM
+        Hs = torch.relu(x @ v["wx"][u] + v["bl"][u])
+        n_out = int(lay.n_a[a]) if u % 2 == 0 else 1
+        out = Hs @ v["wo"][u][:, :n_out] + v["bo"][u][:n_out]
+        out = torch.softmax(out, -1) if u % 2 == 0 else out.squeeze(-1)
+        return out, Hs, c, h
     hs = []
     for t in range(obs.shape[0]):
         keep = 1.0 - dones[t]

@@ -49,3 +49,26 @@ def test_layout_matches_reference_parameter_count():
         np.testing.assert_allclose(w.T @ w if w.shape[0] >= w.shape[1] else w @ w.T,
                                    2 * np.eye(min(w.shape)), atol=1e-4)   # orthogonal, scale sqrt(2)
         assert np.all(v["bl"] == 0)
+
+
+def test_fc_policy_layout_matches_reference_variable_shapes():
+    """FcACPolicy (agents/policies.py:214-256): per net fcw [n_wave,128]+b, fct [n_wait,32]+b, fc [160,64]+b, head."""
+    import torch
+    from deeprl_signal_control_b200.agents.layout import PolicyLayout
+    from oracle.learner_ref import unit_forward
+    n_w, n_wave, n_a = [6, 6], [18, 30], [5, 4]
+    n_s = [w + t for w, t in zip(n_wave, n_w)]
+    off = np.concatenate([[0], np.cumsum(n_s)]).astype(np.int32)
+    lay = PolicyLayout(n_s, n_a, n_w, [0, 0], off, int(off[-1]), fw=128, ft=32, ff=0, h=64, recurrent=False)
+    assert lay.dx == 160 and not lay.recurrent
+    v = lay.views(lay.init_params(3))
+    assert v["wx"].shape == (4, 160, 64) and v["wh"].size == 0 and v["bl"].shape == (4, 64)
+    expect = sum(2 * (nw * 128 + 128 + nt * 32 + 32 + 160 * 64 + 64 + 64 * 5 + 5) for nw, nt in zip(n_wave, n_w))
+    assert lay.n_params == expect
+    # float64 restatement runs and normalises
+    P = torch.from_numpy(lay.init_params(3).astype(np.float64))
+    obs = torch.rand(2, 7, lay.n_obs, dtype=torch.float64)
+    pi = unit_forward(lay.views(P), lay, 0, obs, [0.0, 0.0], None, None)[0]
+    val = unit_forward(lay.views(P), lay, 1, obs, [0.0, 0.0], None, None)[0]
+    assert pi.shape == (2, 7, 5) and val.shape == (2, 7)
+    np.testing.assert_allclose(pi.sum(-1).numpy(), 1.0, rtol=1e-12)

@@ -165,3 +165,77 @@ def test_clip_rmsprop_matches_tf1_semantics():
     np.testing.assert_allclose(m.MS.cpu().numpy(), MS0, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(m.P.cpu().numpy(), P0, rtol=1e-5, atol=1e-6)
     assert norms[0] > 40.0 > norms[1]
+
+
+def _fc_layout():
+    from deeprl_signal_control_b200.agents.layout import PolicyLayout
+    n_w, n_wave = [6, 6, 6], [18, 24, 30]
+    n_s = [w + t for w, t in zip(n_wave, n_w)]
+    off = np.concatenate([[0], np.cumsum(n_s)]).astype(np.int32)
+    return PolicyLayout(n_s, [5, 4, 5], n_w, [0, 0, 0], off, int(off[-1]) + 3, fw=128, ft=32, ff=0, h=64, max_na=5,
+                        recurrent=False)
+
+
+def test_fc_policy_forward_and_gradients_match_oracle():
+    """FcACPolicy (agents/policies.py:214-256, BASELINE config 2): forward vs the float64 restatement, gradients vs
+    float64 autograd (rel. 3e-4 of each tensor's max), with the fp32 front-end gradient kernel and the tcgen05 one."""
+    from deeprl_signal_control_b200.agents.learner_fc import BatchedFcA2C
+    from oracle.learner_ref import a2c_loss, nstep_returns, unit_forward
+    lay = _fc_layout()
+    R, T = 37, 5
+    gamma, v_coef, beta = 0.99, 0.5, 0.01
+    for fc_tc in (False, True):
+        m = BatchedFcA2C(lay, R, n_step=T, gamma=gamma, v_coef=v_coef, max_grad_norm=0.0, seed=7, chunk=16,
+                         reward_norm=3.0, reward_clip=2.0, allow_tf32=False)
+        m.fc_bwd_tc = fc_tc and lay.fc_bwd_tc_ok
+        rng = np.random.default_rng(2)
+        P0 = m.P.cpu().numpy().copy()
+        P0 = P0 + rng.normal(0, 0.05, P0.shape).astype(np.float32) * (P0 == 0)       # non-zero biases
+        mask = np.ones_like(P0); vm = lay.views(mask)
+        for u in range(lay.U):
+            n_out = int(lay.n_a[u // 2]) if u % 2 == 0 else 1
+            vm["wo"][u][:, n_out:] = 0; vm["bo"][u][n_out:] = 0
+        P0 = P0 * mask
+        m.P.copy_(torch.from_numpy(P0))
+        vr = lay.views(torch.from_numpy(P0.astype(np.float64)))
+        dones_pre = [0.0, 1.0, 0.0, 0.0, 0.0]
+        dones_post = dones_pre[1:] + [0.0]
+        obs_all, act_all, rew_all, val_all = [], [], [], []
+        for t in range(T):
+            obs = rng.random((R, lay.n_obs)).astype(np.float32) * 2
+            m.obs_slot().copy_(torch.from_numpy(obs))
+            pi, val, act = m.forward(m.obs_slot(), bool(dones_pre[t]))
+            torch.cuda.synchronize()
+            o64 = torch.from_numpy(obs.astype(np.float64))[None]
+            for a in range(lay.A):
+                p_ref = unit_forward(vr, lay, 2 * a, o64, [0.0], None, None)[0]
+                v_ref = unit_forward(vr, lay, 2 * a + 1, o64, [0.0], None, None)[0]
+                na = int(lay.n_a[a])
+                np.testing.assert_allclose(pi[:, a, :na].cpu().numpy(), p_ref[0].numpy(), rtol=2e-4, atol=2e-5)
+                np.testing.assert_allclose(val[:, a].cpu().numpy(), v_ref[0].numpy(), rtol=2e-4, atol=2e-5)
+                assert int(act[:, a].max()) < na and int(act[:, a].min()) >= 0
+            rew = rng.normal(0, 4, (R, lay.A)).astype(np.float32)
+            obs_all.append(obs); act_all.append(act.cpu().numpy().copy()); val_all.append(val.cpu().numpy().copy())
+            rew_all.append(np.clip(rew / 3.0, -2.0, 2.0))
+            m.add_transition(torch.from_numpy(rew).cuda(), bool(dones_pre[t]), bool(dones_post[t]))
+        boot = rng.normal(0, 1, (R, lay.A)).astype(np.float32)
+        m.backward(torch.from_numpy(boot).cuda(), lr=0.0, beta=beta)
+        torch.cuda.synchronize()
+        G = m.G.cpu().numpy().astype(np.float64)
+        Rs_ref, Adv_ref = nstep_returns(list(np.stack(rew_all).astype(np.float64)), list(np.stack(val_all).astype(np.float64)),
+                                        dones_post, boot.astype(np.float64), gamma)
+        np.testing.assert_allclose(m.Rs.cpu().numpy(), Rs_ref, rtol=1e-5, atol=1e-5)
+        P = torch.from_numpy(P0.astype(np.float64)).requires_grad_(True)
+        zeros = [None] * lay.U
+        loss, parts = a2c_loss(P, lay, torch.from_numpy(np.stack(obs_all).astype(np.float64)),
+                               torch.from_numpy(np.stack(act_all)), torch.from_numpy(m.Rs.cpu().numpy().astype(np.float64)),
+                               torch.from_numpy(m.Adv.cpu().numpy().astype(np.float64)), dones_pre, zeros, zeros, v_coef, beta)
+        loss.backward()
+        gv, rv = lay.views(G), lay.views(P.grad.numpy())
+        tol = 2e-2 if m.fc_bwd_tc else 3e-4           # the tcgen05 kernel multiplies bf16-rounded operands
+        for k in gv:
+            if rv[k].size == 0 or (m.fc_bwd_tc and not k.startswith("fc")):
+                continue
+            scale = max(np.abs(rv[k]).max(), 1e-8)
+            assert np.abs(gv[k] - rv[k]).max() / scale < tol, (k, fc_tc)
+        assert m.t == 0

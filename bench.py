@@ -55,14 +55,18 @@ def parse():
     p.add_argument("--fp32-gemm", action="store_true", help="plain fp32 (no TF32 tensor cores) in the learner GEMMs")
     p.add_argument("--seed", type=int, default=12)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--agent", default="ma2c", choices=["ma2c", "ia2c"],
+                   help="ma2c = BASELINE configs[2] (the headline workload); ia2c with --policy fc = configs[1]")
+    p.add_argument("--policy", default="lstm", choices=["lstm", "fc"], help="fc = FcACPolicy (agents/policies.py:214-256)")
     p.add_argument("--e2e-parts", type=int, default=2,
                    help="replica ranges of the host-buffer (e2e) loop, one stream each (1: single blocking tsc_step_host)")
     return p.parse_args()
 
 
-def workload_name(R, mode):
-    return ("5x5 large_grid MA2C (configs[2]), %d env replicas per GPU, %s" %
-            (R, "policy+sim+update" if mode == "train" else "sim control step, uniform-random actions"))
+def workload_name(R, mode, agent="ma2c", policy="lstm"):
+    tag = "MA2C (configs[2])" if agent == "ma2c" else ("IA2C, FC policy (configs[1])" if policy == "fc" else "IA2C, LSTM policy")
+    return ("5x5 large_grid %s, %d env replicas per GPU, %s" %
+            (tag, R, "policy+sim+update" if mode == "train" else "sim control step, uniform-random actions"))
 
 
 def algorithmic_bytes(net, v_live):
@@ -152,7 +156,7 @@ def main():
     mode = args.mode or "train"
     from deeprl_signal_control_b200.net.large_grid import build_large_grid
     from deeprl_signal_control_b200.net.tables import EnvParams
-    net, par = build_large_grid(agent="ma2c"), EnvParams(agent="ma2c")
+    net, par = build_large_grid(agent=args.agent), EnvParams(agent=args.agent)
     cores = len(os.sched_getaffinity(0))
 
     # ---------------- reference arm: the CPU implementation of the path ----------------------
@@ -165,7 +169,7 @@ def main():
                 "unit": "agent-env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * el / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args.replicas, mode),
+                "config": {"workload": workload_name(args.replicas, mode, args.agent, args.policy),
                            "note": "each reference step is a bounded sample: %d replicas instead of %d"
                                    % (R_cpu, args.replicas)},
                 "cpu_baseline": cb,
@@ -201,12 +205,16 @@ def main():
         from deeprl_signal_control_b200.agents.trainer import BatchedTrainer
         # config/config_ma2c_large.ini [MODEL_CONFIG]
         lay = PolicyLayout(net.n_s_ls, net.n_a_ls, net.n_w_ls, net.n_f_ls, net.node_obs_off, net.n_obs,
-                           fw=128, ft=32, ff=64, h=64)
-        model = BatchedA2C(lay, R, n_step=N_STEP, gamma=0.99, v_coef=0.5, max_grad_norm=40.0, alpha=0.99, eps=1e-5,
-                           reward_norm=2000.0, reward_clip=2.0, seed=args.seed, device=local_rank,
-                           chunk=args.chunk, replica0=rank * R, total_replicas=world * R,
-                           process_group=dist.group.WORLD if world > 1 else None, allow_tf32=not args.fp32_gemm)
-        trainer = BatchedTrainer(sim, model, "ma2c", lr=5e-4, beta=0.01, seed0=args.seed, replica0=rank * R)
+                           fw=128, ft=32, ff=64 if args.agent == "ma2c" else 0, h=64, recurrent=args.policy != "fc")
+        if args.policy == "fc":
+            from deeprl_signal_control_b200.agents.learner_fc import BatchedFcA2C as Learner
+        else:
+            Learner = BatchedA2C
+        model = Learner(lay, R, n_step=N_STEP, gamma=0.99, v_coef=0.5, max_grad_norm=40.0, alpha=0.99, eps=1e-5,
+                        reward_norm=2000.0 if args.agent == "ma2c" else 3000.0, reward_clip=2.0, seed=args.seed,
+                        device=local_rank, chunk=args.chunk, replica0=rank * R, total_replicas=world * R,
+                        process_group=dist.group.WORLD if world > 1 else None, allow_tf32=not args.fp32_gemm)
+        trainer = BatchedTrainer(sim, model, args.agent, lr=5e-4, beta=0.01, seed0=args.seed, replica0=rank * R)
 
         def one_step(i):
             trainer.control_step()
@@ -278,6 +286,8 @@ def main():
     # ---------------- e2e: the environment driven through the host-buffer C-ABI call ------------
     if trainer is not None:
         e2e_steps = N_STEP                     # one full rollout + one update
+        if args.policy == "fc":
+            args.e2e_parts = 1                 # the replica-range forward exists for the fused LSTM kernel only
         if args.e2e_parts > 1:
             host_step = lambda: trainer.control_step_host_pipelined(n_parts=args.e2e_parts)
         else:
@@ -352,7 +362,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if mode == "sim" else "f32 (sim, LSTM cell, loss, optimizer) + bf16 tensor-core operands with f32 accumulation (learner GEMMs)",
             "data": "synthetic",
-            "config": {"workload": workload_name(R, mode), "replicas_per_gpu": R, "agents": net.n_nodes,
+            "config": {"workload": workload_name(R, mode, args.agent, args.policy), "replicas_per_gpu": R, "agents": net.n_nodes,
                        "burnin_control_steps": args.burnin, "mode": mode, "n_step": N_STEP,
                        "updates_in_timed_region": n_updates_timed, "untimed_alignment_steps": align_steps,
                        "learner_gemm_library": "own tcgen05 kernels for the forward, BPTT and all weight gradients; cuBLAS "

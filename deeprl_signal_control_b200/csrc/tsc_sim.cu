@@ -63,6 +63,10 @@ struct DevNet {
   const uint8_t* src_due;
   const int32_t* lane_src0;  // [n_lanes] first demand source entering at this lane or -1
   const int32_t* src_next;   // [n_src]   next source on the same lane (ascending index) or -1
+  const int32_t* src_group;  // stochastic demand (tsc.h) or null
+  const float* src_plo;
+  const float* src_phi;
+  int32_t n_pint, pint_sec;
 };
 
 struct StepArgs {
@@ -617,10 +621,31 @@ tsc_step_kernel(const StepArgs A) {
       if (q >= 0) {
         const bool in_h = (int)t_abs < n.horizon;
         bool lane_free = true;   // the lane belongs to the first source (by index) with a backlog
+        int pick = -1;
+        if (n.src_group) {
+          // stochastic demand: first update every backlog of the lane with this second's draws, then the lane goes to
+          // the source with the LONGEST backlog (ties: lowest index), which keeps the realised route shares at the
+          // turn ratios when the entry lane saturates (a fixed order would starve the later siblings)
+          int best = 0;
+          for (int q2 = q; q2 >= 0; q2 = __ldg(&n.src_next[q2])) {
+            int due = in_h ? (int)__ldg(&n.src_due[t_abs * n.n_src + q2]) : 0;
+            const int gq = __ldg(&n.src_group[q2]);
+            if (gq >= 0 && due > 0) {
+              const float ug = u01(rng_u32(seed_lo, seed_hi, t_abs, 0x20000u + (uint32_t)gq, 7u));
+              int iv = (int)t_abs / n.pint_sec;
+              if (iv >= n.n_pint) iv = n.n_pint - 1;
+              if (!(ug >= __ldg(&n.src_plo[iv * n.n_src + q2]) && ug < __ldg(&n.src_phi[iv * n.n_src + q2]))) due = 0;
+            }
+            int b2 = s_backlog[q2] + due;
+            if (b2 > 65535) b2 = 65535;
+            s_backlog[q2] = b2;
+            if (b2 > best) { best = b2; pick = q2; }
+          }
+        }
         for (; q >= 0; q = __ldg(&n.src_next[q])) {
-          int b_new = s_backlog[q] + (in_h ? (int)__ldg(&n.src_due[t_abs * n.n_src + q]) : 0);
+          int b_new = n.src_group ? s_backlog[q] : s_backlog[q] + (in_h ? (int)__ldg(&n.src_due[t_abs * n.n_src + q]) : 0);
           if (b_new > 65535) b_new = 65535;
-          if (b_new > 0 && lane_free) {
+          if (n.src_group ? (q == pick) : (b_new > 0 && lane_free)) {
             lane_free = false;
             bool ok = cl < lc.cap;
             float free_back = lc.len;
@@ -946,6 +971,13 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   rc |= upload(h, net->src_lane, (size_t)net->n_src, &d.src_lane);
   rc |= upload(h, net->src_route, (size_t)net->n_src, &d.src_route);
   rc |= upload(h, net->src_due, (size_t)net->horizon * net->n_src, &d.src_due);
+  d.src_group = nullptr; d.src_plo = d.src_phi = nullptr; d.n_pint = 0; d.pint_sec = 1;
+  if (net->src_group && net->n_pint > 0 && net->pint_sec > 0) {
+    rc |= upload(h, net->src_group, (size_t)net->n_src, &d.src_group);
+    rc |= upload(h, net->src_plo, (size_t)net->n_pint * net->n_src, &d.src_plo);
+    rc |= upload(h, net->src_phi, (size_t)net->n_pint * net->n_src, &d.src_phi);
+    d.n_pint = net->n_pint; d.pint_sec = net->pint_sec;
+  }
   {
     std::vector<int32_t> lane_src0(net->n_lanes, -1), src_next(net->n_src > 0 ? net->n_src : 1, -1);
     for (int q = net->n_src - 1; q >= 0; --q) {      // descending, so the lists come out in ascending index order

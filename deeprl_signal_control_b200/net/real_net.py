@@ -386,7 +386,8 @@ def load_tables(path: str) -> NetTables:
                     max_hops=meta['max_hops'], horizon=meta['horizon'], max_phases=meta['max_phases'],
                     max_na=meta['max_na'])
     for k in NetTables._ARRAYS:
-        setattr(net, k, z[k])
+        if k in z.files:                     # caches written before a table was added keep their defaults
+            setattr(net, k, z[k])
     for k in _LIST_FIELDS:
         setattr(net, k, [x for x in meta[k]])
     return net.finalize()

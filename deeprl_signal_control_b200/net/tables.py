@@ -47,6 +47,8 @@ class CNet(C.Structure):
         ("obs_idx", _P(C.c_int32)), ("obs_scale", _P(C.c_float)),
         ("src_lane", _P(C.c_int32)), ("src_route", _P(C.c_int32)),
         ("src_due", _P(C.c_uint8)),
+        ("src_group", _P(C.c_int32)), ("src_plo", _P(C.c_float)), ("src_phi", _P(C.c_float)),
+        ("n_pint", C.c_int32), ("pint_sec", C.c_int32),
     ]
 
 
@@ -162,6 +164,11 @@ class NetTables:
     src_lane: np.ndarray = None
     src_route: np.ndarray = None
     src_due: np.ndarray = None
+    # stochastic demand (small_grid): see include/tsc.h; defaults = off
+    src_group: np.ndarray = None
+    src_plo: np.ndarray = None
+    src_phi: np.ndarray = None
+    pint_sec: int = 1
     # derived per-agent dims, reference envs/env.py:303-323
     n_s_ls: List[int] = field(default_factory=list)
     n_a_ls: List[int] = field(default_factory=list)
@@ -186,13 +193,19 @@ class NetTables:
     def n_obs(self): return len(self.obs_kind)
     @property
     def n_slots(self): return int(self.lane_cap.sum())
+    @property
+    def n_pint(self): return 0 if self.src_plo is None else int(np.asarray(self.src_plo).reshape(-1, max(self.n_src, 1)).shape[0])
 
     _ARRAYS = [f for f, _ in CNet._fields_ if f not in (
         "n_lanes", "n_links", "n_nodes", "n_routes", "max_hops", "n_src", "horizon",
-        "n_det", "n_obs", "max_phases", "max_na", "n_slots")]
+        "n_det", "n_obs", "max_phases", "max_na", "n_slots", "n_pint", "pint_sec")]
 
     def finalize(self) -> "NetTables":
         """Coerce dtypes / contiguity so `as_c` can hand out raw pointers."""
+        if self.src_group is None:                      # deterministic demand only
+            self.src_group = np.full(self.n_src, -1, np.int32)
+            self.src_plo = np.zeros((0, self.n_src), np.float32)
+            self.src_phi = np.zeros((0, self.n_src), np.float32)
         want = dict(CNet._fields_)
         for name in self._ARRAYS:
             ct = want[name]._type_
@@ -207,7 +220,7 @@ class NetTables:
         """ctypes struct whose pointers alias this object's arrays (keep `self` alive)."""
         c = CNet()
         for name in ("n_lanes", "n_links", "n_nodes", "n_routes", "max_hops", "n_src",
-                     "horizon", "n_det", "n_obs", "max_phases", "max_na", "n_slots"):
+                     "horizon", "n_det", "n_obs", "max_phases", "max_na", "n_slots", "n_pint", "pint_sec"):
             setattr(c, name, int(getattr(self, name)))
         want = dict(CNet._fields_)
         for name in self._ARRAYS:

@@ -84,6 +84,14 @@ typedef struct tsc_net {
   const int32_t* src_lane;      /* [n_src] origin lane                                             */
   const int32_t* src_route;     /* [n_src]                                                         */
   const uint8_t* src_due;       /* [horizon][n_src] vehicles becoming due in second t              */
+  /* stochastic demand (small_grid: JTRRouter turn ratios and `probability=` flows,
+   * small_grid/data/build_file.py:167-307).  A due vehicle of source q with src_group[q] = g >= 0 is kept iff
+   * src_plo[iv][q] <= u < src_phi[iv][q], u = U[0,1) drawn per (replica seed, second, g), iv = min(t / pint_sec,
+   * n_pint - 1): sources of one group share u, so route choice among them is exclusive.  NULL / -1: off. */
+  const int32_t* src_group;     /* [n_src] or NULL                                                 */
+  const float*   src_plo;       /* [n_pint][n_src]                                                 */
+  const float*   src_phi;       /* [n_pint][n_src]                                                 */
+  int32_t n_pint, pint_sec;
 } tsc_net;
 
 /* ---- scalar configuration: vType + [ENV_CONFIG] (config/config_ma2c_large.ini:24-48) ---------- */

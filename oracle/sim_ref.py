@@ -102,6 +102,11 @@ class RefSim:
         return dict(cur_sec=int(out[0]), departed=int(out[1]), arrived=int(out[2]),
                     backlog=int(out[3]), live=int(out[4]))
 
+    def backlog(self, replica: int = 0):
+        out = np.zeros(self.net.n_src, np.int32)
+        lib().ref_get_backlog(self.h, C.c_int32(replica), _p(out, C.c_int32))
+        return out
+
     # ---- evaluation / recording path (envs/env.py:409-437, 498-542) --------------------------
     def set_record(self, on: bool = True):
         lib().ref_set_record(self.h, int(on))

@@ -377,7 +377,14 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
    *    large_grid/data/build_file.py:277; at most one insertion per lane per second) */
   if ((int)t_abs < n->horizon)
     for (int q = 0; q < n->n_src; ++q) {
-      int b = r->backlog[q] + n->src_due[t_abs * n->n_src + q];
+      int due = n->src_due[t_abs * n->n_src + q];
+      if (n->src_group && n->n_pint > 0 && due > 0 && n->src_group[q] >= 0) { /* stochastic demand (tsc.h) */
+        float ug = u01(rng_u32(r->seed_lo, r->seed_hi, t_abs, 0x20000u + (uint32_t)n->src_group[q], 7u));
+        int iv = (int)t_abs / n->pint_sec;
+        if (iv >= n->n_pint) iv = n->n_pint - 1;
+        if (!(ug >= n->src_plo[iv * n->n_src + q] && ug < n->src_phi[iv * n->n_src + q])) due = 0;
+      }
+      int b = r->backlog[q] + due;
       r->backlog[q] = b > 65535 ? 65535 : b;
     }
   {
@@ -385,8 +392,16 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
     int32_t* owner_ok = (int32_t*)alloca(sizeof(int32_t) * (size_t)n->n_src);
     for (int q = 0; q < n->n_src; ++q) {
       owner_ok[q] = r->backlog[q] > 0;
-      for (int p = 0; p < q; ++p)
-        if (n->src_lane[p] == n->src_lane[q] && r->backlog[p] > 0) owner_ok[q] = 0;
+      if (n->src_group && n->n_pint > 0) {
+        /* stochastic demand: the lane goes to the source with the longest backlog (ties: lowest index) */
+        for (int p = 0; p < n->n_src; ++p)
+          if (p != q && n->src_lane[p] == n->src_lane[q] &&
+              (r->backlog[p] > r->backlog[q] || (r->backlog[p] == r->backlog[q] && p < q)))
+            owner_ok[q] = 0;
+      } else {
+        for (int p = 0; p < q; ++p)
+          if (n->src_lane[p] == n->src_lane[q] && r->backlog[p] > 0) owner_ok[q] = 0;
+      }
     }
     for (int q = 0; q < n->n_src; ++q) {
       if (!owner_ok[q]) continue;
@@ -531,6 +546,12 @@ ref_sim* ref_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R) {
   DUP(obs_idx, net->n_obs, int32_t); DUP(obs_scale, net->n_obs, float);
   DUP(src_lane, net->n_src, int32_t); DUP(src_route, net->n_src, int32_t);
   DUP(src_due, (size_t)net->horizon * net->n_src, uint8_t);
+  if (net->src_group && net->n_pint > 0 && net->pint_sec > 0) {
+    DUP(src_group, net->n_src, int32_t);
+    DUP(src_plo, (size_t)net->n_pint * net->n_src, float); DUP(src_phi, (size_t)net->n_pint * net->n_src, float);
+  } else {
+    s->net.src_group = 0; s->net.src_plo = 0; s->net.src_phi = 0; s->net.n_pint = 0; s->net.pint_sec = 1;
+  }
   s->rep = (replica_t*)calloc((size_t)R, sizeof(replica_t));
   for (int i = 0; i < R; ++i) {
     replica_t* r = &s->rep[i];
@@ -768,6 +789,11 @@ void ref_dump_state(ref_sim* s, int32_t replica, int32_t* lane_cnt, uint32_t* ve
     }
   }
   *n_veh = w;
+}
+
+/* pending (not yet inserted) vehicles of every demand source of one replica */
+void ref_get_backlog(ref_sim* s, int32_t replica, int32_t* out /* [n_src] */) {
+  memcpy(out, s->rep[replica].backlog, 4 * (size_t)s->net.n_src);
 }
 
 void ref_get_misc(ref_sim* s, int32_t replica, int32_t* out /* cur_sec, departed, arrived, backlog_sum, live */) {

@@ -1603,12 +1603,8 @@ wgrad_tc_kernel(const DDimsTC d, const WGradTC a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-// All-bf16 variant (the training loop's): 64-row tiles, three stages, every 16 B piece goes global -> shared with
-// cp.async (no registers) two tiles ahead of the MMAs.  Rows with done[t] (Hp = 0) and the t = 0 rows (Hp = h0, fp32)
-// take the register path.  CTAs 2p and 2p+1 walk the same (unit, tile) range, one per 128-column half of dZ.
+// All-bf16 variant (the training loop's): 64-row tiles, two smem stages + one register stage.  CTAs 2p and 2p+1 walk the
+// same (unit, tile) range, one per 128-column half of dZ, so the second reader of an X / Hp tile finds it in L2.
 #define WGA_ROWS 64
 #define WGA_SBO (WGA_ROWS * 16 + 16)
 #define WGA_STAGE ((WG_A_CHUNKS + WG_Z_CHUNKS) * WGA_SBO)
@@ -1620,7 +1616,6 @@ wgrad_tc_async_kernel(const DDimsTC d, const WGradTC a) {
   uint64_t* sBar = reinterpret_cast<uint64_t*>(tc_smem + WGA_STAGES * WGA_STAGE);
   uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + WGA_STAGES);
   float* sDone = reinterpret_cast<float*>(sTmem + 2);
-  const uint32_t scratch = smem_u32(sDone + WGA_MAXT);      // 16 B sink for pieces that fall outside the tile
   const uint32_t bar0 = smem_u32(sBar);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
@@ -1794,7 +1789,7 @@ extern "C" int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const void* dz_bf1
   const DDimsTC& d = *tscl_dims_of(h);
   if ((d.dx % 8) != 0 || d.dx / 8 + 9 > WG_A_CHUNKS) return tsc_set_error("tscl_wgrad_tc: dx must be a multiple of 8, <= 240");
   const size_t smem = 2 * (size_t)WG_STAGE + 32;
-  const size_t smem_async = (size_t)WGA_STAGES * WGA_STAGE + 8 * WGA_STAGES + 8 + 4 * WGA_MAXT + 16;
+  const size_t smem_async = (size_t)WGA_STAGES * WGA_STAGE + 8 * WGA_STAGES + 8 + 4 * WGA_MAXT;
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {
     PCK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -58,7 +58,7 @@ def parse():
     p.add_argument("--agent", default="ma2c", choices=["ma2c", "ia2c"],
                    help="ma2c = BASELINE configs[2] (the headline workload); ia2c with --policy fc = configs[1]")
     p.add_argument("--policy", default="lstm", choices=["lstm", "fc"], help="fc = FcACPolicy (agents/policies.py:214-256)")
-    p.add_argument("--e2e-parts", type=int, default=2,
+    p.add_argument("--e2e-parts", type=int, default=3,
                    help="replica ranges of the host-buffer (e2e) loop, one stream each (1: single blocking tsc_step_host)")
     return p.parse_args()
 

@@ -16,7 +16,7 @@ _lib = None
 
 # every symbol include/tsc.h declares
 SYMBOLS = ["tsc_last_error", "tsc_create", "tsc_destroy", "tsc_reset", "tsc_set_train_mode",
-           "tsc_observe", "tsc_step", "tsc_step_host", "tsc_step_host_range", "tsc_set_record", "tsc_step_record", "tsc_get_trips", "tsc_get_counts", "tsc_get_traffic_stats",
+           "tsc_observe", "tsc_step", "tsc_step_host", "tsc_step_host_range", "tsc_step_host_range_async", "tsc_set_record", "tsc_step_record", "tsc_get_trips", "tsc_get_counts", "tsc_get_traffic_stats",
            "tsc_dump_state", "tsc_info", "tsc_mean_live",
            # include/tsc_learn.h
            "tscl_create", "tscl_destroy", "tscl_fc_embed", "tscl_lstm_seq_fwd", "tscl_heads", "tscl_returns",

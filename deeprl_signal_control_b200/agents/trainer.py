@@ -148,14 +148,18 @@ class BatchedTrainer:
         new_done = self.step_in_episode >= self.T_episode
         boundary = (t + 1 == m.T)                       # an update (and possibly an episode end) follows this step
         npv = lambda x, r0, n: x[r0:r0 + n].numpy()
-        for k, st in enumerate(pp['streams']):
+        for k, st in enumerate(pp['streams']):       # every range's env step is enqueued as soon as its actions are here
             r0, n = pp['parts'][k]
             pp['ev'][k].synchronize()                   # the host holds this range's actions / fingerprints
             with torch.cuda.stream(st):
                 sim.step_host_range(r0, n, npv(pp['act'], r0, n), npv(pp['pi'], r0, n) if ma2c else None,
                                     npv(pp['obs'], r0, n), npv(pp['rew'], r0, n), npv(pp['grew'], r0, n),
-                                    npv(pp['done'], r0, n))
-                # ... and now its observations / rewards: hand them to the learner
+                                    npv(pp['done'], r0, n), sync=False)
+        for k, st in enumerate(pp['streams']):
+            r0, n = pp['parts'][k]
+            st.synchronize()                            # the host holds this range's observations / rewards ...
+            with torch.cuda.stream(st):
+                # ... and hands them to the learner
                 m.obs_hist[t + 1, r0:r0 + n].copy_(pp['obs'][r0:r0 + n], non_blocking=True)
                 m.add_transition_range(r0, n, pp['rew'][r0:r0 + n].to(sim.device, non_blocking=True))
                 self._rew_acc[r0:r0 + n].add_(pp['grew'][r0:r0 + n].to(sim.device, non_blocking=True))

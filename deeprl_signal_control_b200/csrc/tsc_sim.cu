@@ -1101,9 +1101,9 @@ extern "C" int tsc_step_host(tsc_handle* h, const int32_t* action_host, const fl
   return 0;
 }
 
-extern "C" int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host,
-                                   const float* fp_host, float* obs_host, float* reward_host, float* greward_host,
-                                   uint8_t* done_host, void* stream) {
+static int step_host_range(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host,
+                           const float* fp_host, float* obs_host, float* reward_host, float* greward_host,
+                           uint8_t* done_host, void* stream, bool sync) {
   if (!h || !action_host || rep0 < 0 || count <= 0 || rep0 + count > h->R) return fail("tsc_step_host_range: bad argument");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1119,8 +1119,20 @@ extern "C" int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, c
   if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward + r0 * N, n * N * 4, cudaMemcpyDeviceToHost, st));
   if (greward_host) CK(cudaMemcpyAsync(greward_host, h->d_greward + r0, n * 4, cudaMemcpyDeviceToHost, st));
   if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done + r0, n, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (sync) CK(cudaStreamSynchronize(st));
   return 0;
+}
+
+extern "C" int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host,
+                                   const float* fp_host, float* obs_host, float* reward_host, float* greward_host,
+                                   uint8_t* done_host, void* stream) {
+  return step_host_range(h, rep0, count, action_host, fp_host, obs_host, reward_host, greward_host, done_host, stream, true);
+}
+
+extern "C" int tsc_step_host_range_async(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host,
+                                         const float* fp_host, float* obs_host, float* reward_host, float* greward_host,
+                                         uint8_t* done_host, void* stream) {
+  return step_host_range(h, rep0, count, action_host, fp_host, obs_host, reward_host, greward_host, done_host, stream, false);
 }
 
 // ---- evaluation / recording path (envs/env.py:409-437, 498-542) ---------------------------------------------------

@@ -106,12 +106,14 @@ class BatchedSim:
         return obs, reward, greward, done
 
     def step_host_range(self, r0: int, n: int, action: np.ndarray, fp: Optional[np.ndarray], obs: np.ndarray,
-                        reward: np.ndarray, greward: np.ndarray, done: np.ndarray):
+                        reward: np.ndarray, greward: np.ndarray, done: np.ndarray, sync: bool = True):
         """`tsc_step_host_range`: the host-buffer step for replicas [r0, r0 + n) on the current stream; all arrays are
-        the slices of that range (page-locked for full PCIe speed).  Blocks until the slice's results are on the host."""
-        _lib.check(_lib.lib().tsc_step_host_range(self._h, C.c_int32(r0), C.c_int32(n), _np(action, C.c_int32),
-                                                  _np(fp, C.c_float), _np(obs, C.c_float), _np(reward, C.c_float),
-                                                  _np(greward, C.c_float), _np(done, C.c_uint8), self._stream()))
+        the slices of that range (page-locked for full PCIe speed).  Blocks until the slice's results are on the host;
+        with sync=False (`tsc_step_host_range_async`) the work is only enqueued and the caller synchronises the stream."""
+        fn = _lib.lib().tsc_step_host_range if sync else _lib.lib().tsc_step_host_range_async
+        _lib.check(fn(self._h, C.c_int32(r0), C.c_int32(n), _np(action, C.c_int32),
+                      _np(fp, C.c_float), _np(obs, C.c_float), _np(reward, C.c_float),
+                      _np(greward, C.c_float), _np(done, C.c_uint8), self._stream()))
 
     # ---- evaluation / recording path (envs/env.py:409-437, 498-542) ------------------------
     def set_record(self, on: bool = True) -> None:

@@ -161,6 +161,11 @@ int tsc_step_host(tsc_handle* h, const int32_t* action_host, const float* fp_hos
  * PCIe link while another one computes (one stream per range; see agents/trainer.py:control_step_host_pipelined). */
 int tsc_step_host_range(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host, const float* fp_host,
                         float* obs_host, float* reward_host, float* greward_host, uint8_t* done_host, void* stream);
+/* Same without the final synchronisation: the copies and the kernel are only enqueued on `stream` (host buffers must be
+ * page-locked and stay valid); the results are on the host once the caller has synchronised that stream. */
+int tsc_step_host_range_async(tsc_handle* h, int32_t rep0, int32_t count, const int32_t* action_host,
+                              const float* fp_host, float* obs_host, float* reward_host, float* greward_host,
+                              uint8_t* done_host, void* stream);
 
 /* ---- evaluation / recording path (replaces the per-second TraCI reads of `_measure_traffic_step` and SUMO's
  * --tripinfo-output; reference envs/env.py:409-437, 461-471, 498-542) ------------------------------------------

@@ -121,3 +121,51 @@ def test_traffic_stats_match_state_dump(grid_ma2c):
         np.testing.assert_allclose(st[r, 5], halt.mean(), rtol=1e-5)
         np.testing.assert_allclose(st[r, 6], halt.std(), rtol=1e-3, atol=1e-4)
         assert st[r, 1] - st[r, 2] == len(veh)          # departed - arrived = live
+
+
+def test_gridlock_full_rings_and_teleport_bit_exact():
+    """Edge cases of the junction logic: one phase held for minutes (red approaches fill their lanes to capacity,
+    transfers are refused, source backlogs grow), a short teleport threshold so that heads waiting longer than
+    `teleport_sec` ignore the signal (envs/env.py:281-284), then random actions to drain."""
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    net, par = build_large_grid(agent="ia2c"), EnvParams(agent="ia2c", teleport_sec=45)
+    R = 4
+    gpu, ref = _mk(net, par, R)
+    seeds = np.array([1, 2, 3, 4], dtype=np.uint64)
+    gpu.reset(seeds); ref.reset(seeds)
+    rng = np.random.default_rng(9)
+    full_seen = teleport_seen = False
+    for step in range(420):
+        if step < 300:
+            act = np.full((R, net.n_nodes), 3 if step < 150 else 4, np.int32)      # one approach green only
+        else:
+            act = rng.integers(0, 5, size=(R, net.n_nodes), dtype=np.int32)
+        _compare_step(gpu, ref, act, None, check_state_of=(0, R - 1) if step % 30 == 0 else ())
+        if step % 10 == 0:
+            cnt, _ = ref.dump_state(0)
+            full_seen |= bool((cnt >= net.lane_cap - 1).any())
+            teleport_seen |= bool((ref.counts()[2] >= 45).any())
+    assert full_seen and teleport_seen
+    assert ref.misc(0)["backlog"] > 0
+
+
+def test_single_replica_and_observe_only():
+    """R = 1 (the reference's own configuration) and observe() without stepping leave the state untouched."""
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    net, par = build_large_grid(agent="ma2c"), EnvParams(agent="ma2c")
+    gpu, ref = _mk(net, par, 1)
+    seeds = np.array([77], dtype=np.uint64)
+    gpu.reset(seeds); ref.reset(seeds)
+    rng = np.random.default_rng(3)
+    for step in range(60):
+        act = rng.integers(0, 5, size=(1, net.n_nodes), dtype=np.int32)
+        fp = rng.random((1, net.n_nodes, net.max_na), dtype=np.float32)
+        _compare_step(gpu, ref, act, fp, check_state_of=(0,) if step % 20 == 0 else ())
+        if step % 15 == 0:
+            c0, v0 = gpu.dump_state(0)
+            o1 = gpu.observe(torch.from_numpy(fp).cuda()).cpu().numpy()
+            np.testing.assert_array_equal(o1.view(np.uint32), ref.observe(fp).view(np.uint32))
+            c1, v1 = gpu.dump_state(0)
+            np.testing.assert_array_equal(c0, c1); np.testing.assert_array_equal(v0, v1)

@@ -132,13 +132,11 @@ def cpu_reference(net, par, args, threads, budget_s=12.0, quiet=True):
     sim = RefSim(net, par, R_cpu)
     sim.reset(np.arange(R_cpu, dtype=np.uint64) + np.uint64(args.seed))
     fp = rng.random((R_cpu, net.n_nodes, net.max_na), dtype=np.float32)
-    for _ in range(args.burnin):
-        sim.step(rng.integers(0, 5, (R_cpu, net.n_nodes), dtype=np.int32), fp, threads=threads)
-    acts = [rng.integers(0, 5, (R_cpu, net.n_nodes), dtype=np.int32) for _ in range(8)]
-    n, t0 = 0, time.perf_counter()
-    for i in range(n_t):
-        sim.step(acts[i % 8], fp, threads=threads)
-        n += 1
+    acts = rng.integers(0, 5, (8, R_cpu, net.n_nodes), dtype=np.int32)
+    # one call per phase: every thread walks its replicas through all the steps (ref_run_mt), threads are created once
+    sim.run(acts, args.burnin, fp, threads=threads)
+    n, t0 = n_t, time.perf_counter()
+    sim.run(acts, n_t, fp, threads=threads)
     el = time.perf_counter() - t0
     live = float(np.mean([sim.misc(r)["live"] for r in range(R_cpu)]))
     return {"value": R_cpu * net.n_nodes * n / el, "unit": "agent-env-steps/s", "cores": threads,
@@ -356,7 +354,7 @@ def main():
                         "fused sub-steps per 32 B of state traffic (DESIGN.md §5)"}
     cb = None
     if not args.no_cpu_baseline:
-        cb, _, _, _ = cpu_reference(net, par, args, cores, budget_s=10.0)
+        cb, _, _, _ = cpu_reference(net, par, args, cores, budget_s=20.0)
     line = {"metric": "agent-env-steps/sec", "value": value, "unit": "agent-env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -77,6 +77,21 @@ class RefSim:
                           C.c_int32(threads))
         return obs, reward, greward, done
 
+    def run(self, actions, n_steps: int, fp=None, threads: int = 1):
+        """n_steps control steps in ONE call (actions [n_act, R, n_nodes] cycled): each thread walks its replica range
+        through all steps, so the thread pool is created once.  Returns the last step's (obs, reward, greward, done)."""
+        n = self.net
+        actions = np.ascontiguousarray(actions, np.int32).reshape(-1, self.R, n.n_nodes)
+        fp = None if fp is None else np.ascontiguousarray(fp, np.float32)
+        obs = np.zeros((self.R, n.n_obs), np.float32)
+        reward = np.zeros((self.R, n.n_nodes), np.float32)
+        greward = np.zeros(self.R, np.float32)
+        done = np.zeros(self.R, np.uint8)
+        lib().ref_run_mt(self.h, _p(actions, C.c_int32), C.c_int32(len(actions)), C.c_int32(n_steps), _p(fp, C.c_float),
+                         _p(obs, C.c_float), _p(reward, C.c_float), _p(greward, C.c_float), _p(done, C.c_uint8),
+                         C.c_int32(threads))
+        return obs, reward, greward, done
+
     def counts(self):
         n = self.net
         veh = np.zeros((self.R, n.n_det), np.int32)

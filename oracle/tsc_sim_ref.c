@@ -663,6 +663,42 @@ void ref_step_mt(ref_sim* s, const int32_t* action, const float* fp, float* obs,
   for (int t = 0; t < n_threads; ++t) pthread_join(th[t], 0);
 }
 
+/* n_steps control steps in one call: every thread advances its replica range through ALL steps (replicas are
+ * independent), so threads are created once — the fair way to time the CPU path on many cores.
+ * actions [n_act][R][n_nodes] are cycled; obs / reward receive the last step's outputs. */
+typedef struct { step_job job; const int32_t* actions; int32_t n_act, n_steps; } run_job;
+
+static void* run_range(void* arg) {
+  run_job* rj = (run_job*)arg;
+  const tsc_net* n = &rj->job.s->net;
+  const size_t stride = (size_t)rj->job.s->R * n->n_nodes;
+  for (int t = 0; t < rj->n_steps; ++t) {
+    step_job j = rj->job;
+    j.action = rj->actions + (size_t)(t % rj->n_act) * stride;
+    step_range(&j);
+  }
+  return 0;
+}
+
+void ref_run_mt(ref_sim* s, const int32_t* actions, int32_t n_act, int32_t n_steps, const float* fp, float* obs,
+                float* reward, float* greward, uint8_t* done, int32_t n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > s->R) n_threads = s->R;
+  if (n_threads > 256) n_threads = 256;
+  run_job jobs[256];
+  pthread_t th[256];
+  int per = (s->R + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    int i0 = t * per, i1 = i0 + per > s->R ? s->R : i0 + per;
+    if (i0 > s->R) i0 = s->R;
+    step_job jb = {s, i0, i1, 0, fp, obs, reward, greward, done};
+    jobs[t].job = jb; jobs[t].actions = actions; jobs[t].n_act = n_act; jobs[t].n_steps = n_steps;
+  }
+  if (n_threads == 1) { run_range(&jobs[0]); return; }
+  for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], 0, run_range, &jobs[t]);
+  for (int t = 0; t < n_threads; ++t) pthread_join(th[t], 0);
+}
+
 void ref_step(ref_sim* s, const int32_t* action, const float* fp, float* obs, float* reward,
               float* greward, uint8_t* done) {
   ref_step_mt(s, action, fp, obs, reward, greward, done, 1);

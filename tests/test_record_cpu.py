@@ -66,3 +66,25 @@ def test_record_mode_does_not_change_the_hot_state():
         o1 = a.step(act)[0]; o2 = b.step(act)[0]          # plain step() with record mode on
         np.testing.assert_array_equal(o1, o2)
     assert len(b.trips(0)) == b.misc(0)["arrived"]
+
+
+def test_multi_step_run_equals_stepping():
+    """ref_run_mt (one thread pool for n steps: the CPU-baseline driver of bench.py) == n calls of ref_step_mt."""
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    from oracle.sim_ref import RefSim
+    net, par = build_large_grid(agent="ma2c"), EnvParams(agent="ma2c")
+    R = 6
+    a, b = RefSim(net, par, R), RefSim(net, par, R)
+    seeds = np.arange(R, dtype=np.uint64) + np.uint64(40)
+    a.reset(seeds); b.reset(seeds)
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 5, (4, R, net.n_nodes), dtype=np.int32)
+    fp = rng.random((R, net.n_nodes, net.max_na), dtype=np.float32)
+    for t in range(30):
+        oa = a.step(acts[t % 4], fp, threads=3)
+    ob = b.run(acts, 30, fp, threads=4)
+    for x, y in zip(oa, ob):
+        np.testing.assert_array_equal(x, y)
+    for r in range(R):
+        np.testing.assert_array_equal(a.dump_state(r)[1], b.dump_state(r)[1])

@@ -16,6 +16,7 @@
 // Operand layouts (bytes, 16-byte "core rows", no swizzle; cute canonical ((8,n),2):((1,SBO),LBO)):
 //   A tile  [KC][128 rows][16 B]   : LBO = 2048 (next K chunk of 8 bf16), SBO = 128 (next 8 rows)
 //   B tile  [KC][256 cols][16 B]   : LBO = 4096,                          SBO = 128
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -870,9 +871,15 @@ struct BwdTC {
                              //           ZG may then be null (needs Gb / Cb)
 };
 
-#define BW_THREADS 512      // thread = (replica row, 16 hidden units): 16 warps keep the issue slots busy between the per-step MMAs
-__global__ void __launch_bounds__(BW_THREADS, 1)
+// NT = 512: thread = (replica row, 16 hidden units), one CTA per SM.
+// NT = 256: thread = (replica row, 32 hidden units) processed 8 at a time, TWO CTAs per SM (<= 128 registers): while one
+//           tile waits for its per-step MMA / barrier the other one has its loads in flight.
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
+  constexpr int HPT = 8192 / NT;            // hidden units per thread
+  constexpr int NSUB = HPT / 8;
+  constexpr int NQ = NT / 128;              // hidden groups (threads per row)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* sB = tc_smem;                       // 32 * 1024  : Wh^T image
   unsigned char* sA = sB + BW_KC * 1024;             // 32 * 2048  : dz tile
@@ -897,8 +904,8 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
   const int64_t n_items = n_tiles * 2 * d.A;
   int cur_u = -1;
   uint32_t parity = 0;
-  const int q = warp & 3, qt = warp >> 2;            // TMEM lane quadrant, hidden-unit quarter
-  const int row = q * 32 + lane, jq = qt * 16;
+  const int q = warp & 3, qt = warp >> 2;            // TMEM lane quadrant, hidden-unit group
+  const int row = q * 32 + lane, jq = qt * HPT;
   auto bf8 = [](const uint4 v, float* o) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -917,54 +924,43 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
       cur_u = u;
       const uint4* src = reinterpret_cast<const uint4*>(a.Wt + (int64_t)u * BW_KC * TC_H * 8);
       uint4* dst = reinterpret_cast<uint4*>(sB);
-      for (int i = tid; i < BW_KC * TC_H; i += BW_THREADS) dst[i] = src[i];
+      for (int i = tid; i < BW_KC * TC_H; i += NT) dst[i] = src[i];
     }
-    float dc[16], dhc[16];
+    float dc[HPT], dhc[HPT];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { dc[e] = 0.f; dhc[e] = 0.f; }
+    for (int e = 0; e < HPT; ++e) { dc[e] = 0.f; dhc[e] = 0.f; }
     for (int t = a.T - 1; t >= 0; --t) {
       const float keep = 1.0f - a.done[t];
       const int64_t m = ((int64_t)u * a.T + t) * a.Rc + (valid ? r : 0);
       if (t > 0 && valid) {      // pull step t-1's operands towards L2 while step t is being processed
         const int64_t mp = m - a.Rc;
-        if (a.Gb) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Gb + mp * TC_N + qt * 64));
-          if (qt == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + mp * TC_H));
-          if (qt == 1 && t > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + (mp - a.Rc) * TC_H));
-        } else {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + qt * 64));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + qt * 64 + 32));
-          if (qt < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.C + mp * TC_H + qt * 32));
+        constexpr int LP = 4 / NQ;                 // 128-byte lines of a 512-byte row per thread
+#pragma unroll
+        for (int ln = 0; ln < LP; ++ln) {
+          const int li = qt * LP + ln;             // 0..3
+          if (a.Gb) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Gb + mp * TC_N + li * 64));
+            if (li == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + mp * TC_H));
+            if (li == 1 && t > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + (mp - a.Rc) * TC_H));
+          } else {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + li * 64));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ZG + mp * TC_N + li * 64 + 32));
+            if (li < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.C + mp * TC_H + li * 32));
+          }
+          if (li >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + (li - 2) * 32));
         }
-        if (qt >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + (qt - 2) * 32));
-      }
-      // the second half's loads are issued before the first half is consumed (their latencies overlap)
-      uint4 rg[4], rc, rp;
-      if (valid && a.Gb) {
-        const int jo = jq + 8;
-        const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rg[g] = *reinterpret_cast<const uint4*>(zb + g * 64);
-        rc = *reinterpret_cast<const uint4*>(a.Cb + m * TC_H + jo);
-        if (t > 0) rp = *reinterpret_cast<const uint4*>(a.Cb + (m - a.Rc) * TC_H + jo);
       }
 #pragma unroll
-      for (int jb = 0; jb < 2; ++jb) {
+      for (int jb = 0; jb < NSUB; ++jb) {
         const int jo = jq + jb * 8;
         float gi[8], gf[8], go[8], gu[8], ct[8], cp[8], dh[8];
         if (valid) {
           if (a.Gb) {
-            if (jb == 0) {
-              const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
-              bf8(*reinterpret_cast<const uint4*>(zb), gi); bf8(*reinterpret_cast<const uint4*>(zb + 64), gf);
-              bf8(*reinterpret_cast<const uint4*>(zb + 128), go); bf8(*reinterpret_cast<const uint4*>(zb + 192), gu);
-              bf8(*reinterpret_cast<const uint4*>(a.Cb + m * TC_H + jo), ct);
-              if (t > 0) bf8(*reinterpret_cast<const uint4*>(a.Cb + (m - a.Rc) * TC_H + jo), cp);
-            } else {
-              bf8(rg[0], gi); bf8(rg[1], gf); bf8(rg[2], go); bf8(rg[3], gu);
-              bf8(rc, ct);
-              if (t > 0) bf8(rp, cp);
-            }
+            const __nv_bfloat16* zb = a.Gb + m * TC_N + jo;
+            bf8(*reinterpret_cast<const uint4*>(zb), gi); bf8(*reinterpret_cast<const uint4*>(zb + 64), gf);
+            bf8(*reinterpret_cast<const uint4*>(zb + 128), go); bf8(*reinterpret_cast<const uint4*>(zb + 192), gu);
+            bf8(*reinterpret_cast<const uint4*>(a.Cb + m * TC_H + jo), ct);
+            if (t > 0) bf8(*reinterpret_cast<const uint4*>(a.Cb + (m - a.Rc) * TC_H + jo), cp);
             if (t == 0) f8(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo, cp);
             f8(a.dH + m * TC_H + jo, dh);
           } else {
@@ -1029,14 +1025,16 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
         mbar_wait(bar, parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float dhp[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)jq, dhp);
+        float dhp[HPT];
+#pragma unroll
+        for (int c16 = 0; c16 < HPT / 16; ++c16)
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(jq + c16 * 16), dhp + c16 * 16);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dhc[e] = dhp[e] * keep;
+        for (int e = 0; e < HPT; ++e) dhc[e] = dhp[e] * keep;
       } else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dhc[e] = 0.f;
+        for (int e = 0; e < HPT; ++e) dhc[e] = 0.f;
       }
     }
   }
@@ -1065,7 +1063,8 @@ extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* 
   const size_t smem = BW_KC * 1024 + BW_KC * 2048 + 16;
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {
-    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = tscl_device_of(h);
   }
   int n_sm = 0;
@@ -1075,7 +1074,11 @@ extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* 
   BwdTC a;
   a.Wt = (const __nv_bfloat16*)wt_bf16; a.ZG = ZG; a.C = C; a.dH = dH; a.c0 = c0; a.done = done; a.T = T; a.Rc = Rc;
   a.ld_state = ld_state; a.r0 = r0; a.Gb = (const __nv_bfloat16*)gates_bf16; a.Cb = (const __nv_bfloat16*)c_bf16; a.dZb = (__nv_bfloat16*)dz_bf16;
-  lstm_bwd_tc_kernel<<<grid, BW_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  // measured (R = 8192, 1 x B200): the one-CTA-per-SM 512-thread variant 2.097 ms per control step, the two-CTA 256-thread
+  // variant 2.144 ms; TSC_BPTT_THREADS=256 selects the latter for experiments
+  static const int bw_threads = []() { const char* e = getenv("TSC_BPTT_THREADS"); return e && atoi(e) == 256 ? 256 : 512; }();
+  if (bw_threads == 512) lstm_bwd_tc_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
+  else lstm_bwd_tc_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
 }

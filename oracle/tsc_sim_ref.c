@@ -827,6 +827,17 @@ void ref_dump_state(ref_sim* s, int32_t replica, int32_t* lane_cnt, uint32_t* ve
   *n_veh = w;
 }
 
+/* test probe of the car-following helpers: kind 0 brake_gap(v=a, b=b), 1 stop_speed(gap=a, b=b, tau=c),
+ * 2 follow_speed(gap=a, v_lead=b, b=c, tau=d), 3 free_speed(dist=a, target=b, b=c) */
+float ref_probe_krauss(int32_t kind, float a, float b, float c, float d) {
+  switch (kind) {
+    case 0: return brake_gap(a, b);
+    case 1: return stop_speed(a, b, c);
+    case 2: return follow_speed(a, b, c, d);
+    default: return free_speed(a, b, c);
+  }
+}
+
 /* pending (not yet inserted) vehicles of every demand source of one replica */
 void ref_get_backlog(ref_sim* s, int32_t replica, int32_t* out /* [n_src] */) {
   memcpy(out, s->rep[replica].backlog, 4 * (size_t)s->net.n_src);

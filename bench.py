@@ -55,6 +55,7 @@ def parse():
     p.add_argument("--fp32-gemm", action="store_true", help="plain fp32 (no TF32 tensor cores) in the learner GEMMs")
     p.add_argument("--seed", type=int, default=12)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work of the oracle sample (both arms)")
     p.add_argument("--agent", default="ma2c", choices=["ma2c", "ia2c"],
                    help="ma2c = BASELINE configs[2] (the headline workload); ia2c with --policy fc = configs[1]")
     p.add_argument("--policy", default="lstm", choices=["lstm", "fc"], help="fc = FcACPolicy (agents/policies.py:214-256)")
@@ -162,7 +163,7 @@ def main():
         if rank != 0:
             return
         t_steps = max(args.steps, 1)
-        cb, n, el, R_cpu = cpu_reference(net, par, args, cores, budget_s=20.0)
+        cb, n, el, R_cpu = cpu_reference(net, par, args, cores, budget_s=args.cpu_budget)
         line = {"impl": "reference", "metric": "agent-env-steps/sec", "value": cb["value"],
                 "unit": "agent-env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * el / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -354,7 +355,7 @@ def main():
                         "fused sub-steps per 32 B of state traffic (DESIGN.md §5)"}
     cb = None
     if not args.no_cpu_baseline:
-        cb, _, _, _ = cpu_reference(net, par, args, cores, budget_s=20.0)
+        cb, _, _, _ = cpu_reference(net, par, args, cores, budget_s=args.cpu_budget)
     line = {"metric": "agent-env-steps/sec", "value": value, "unit": "agent-env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -24,11 +24,20 @@ from oracle.sim_ref import RefSim                                       # noqa: 
 from tests.test_real_net_cpu import real_params                         # noqa: E402
 
 
+TAU = 1.0          # set by __main__: 1.0 = the current reference (README.md:63 removed tau="0.5"), 0.5 = the paper-era vType
+
+
+def _params():
+    par = real_params("greedy")
+    par.tau = TAU
+    return par
+
+
 def replay(agent, n_episodes=10):
     ctrl = pd.read_csv(os.path.join(REF, "real_net_%s_control.csv" % agent))
     traffic = pd.read_csv(os.path.join(REF, "real_net_%s_traffic.csv" % agent))
     trips = pd.read_csv(os.path.join(REF, "real_net_%s_trip.csv" % agent))
-    net, par = real_net_tables("greedy"), real_params("greedy")
+    net, par = real_net_tables("greedy"), _params()
     eps = sorted(ctrl.episode.unique())[:n_episodes]
     R = len(eps)
     acts = np.stack([np.array([[int(x) for x in s.split(",")] for s in ctrl[ctrl.episode == e].action], np.int32)
@@ -75,7 +84,7 @@ def closed_loop_greedy(n_episodes=10):
     traffic = pd.read_csv(os.path.join(REF, "real_net_greedy_traffic.csv"))
     trips = pd.read_csv(os.path.join(REF, "real_net_greedy_trip.csv"))
     ctrl_csv = pd.read_csv(os.path.join(REF, "real_net_greedy_control.csv"))
-    net, par = real_net_tables("greedy"), real_params("greedy")
+    net, par = real_net_tables("greedy"), _params()
     nodes = {}
     for name in net.node_names:
         nd = Node(name)
@@ -115,10 +124,14 @@ def closed_loop_greedy(n_episodes=10):
 
 
 if __name__ == "__main__":
-    out = [closed_loop_greedy()] + [replay(a) for a in ("greedy", "ma2c", "ia2c")]
-    json.dump({"what": __doc__.split("\n\n")[0].replace("\n", " "), "rows": out},
-              open(os.path.join(HERE, "monaco_replay_summary.json"), "w"), indent=1)
-    for r in out:
-        print(r["agent"])
-        for k in r["ours"]:
-            print("   %-28s ours %9.3f   sumo %9.3f" % (k, r["ours"][k], r["sumo_recorded"][k]))
+    result = {"what": __doc__.split("\n\n")[0].replace("\n", " "), "by_tau": {}}
+    for tau in (1.0, 0.5):
+        TAU = tau
+        out = [closed_loop_greedy()] + [replay(a) for a in ("greedy", "ma2c", "ia2c")]
+        result["by_tau"]["%.1f" % tau] = out
+        print("=== tau = %.1f ===" % tau)
+        for r in out:
+            print(r["agent"])
+            for k in r["ours"]:
+                print("   %-28s ours %9.3f   sumo %9.3f" % (k, r["ours"][k], r["sumo_recorded"][k]))
+    json.dump(result, open(os.path.join(HERE, "monaco_replay_summary.json"), "w"), indent=1)

@@ -83,6 +83,9 @@ class TrafficSimulator:
         self.norms = {'wave': config.getfloat('norm_wave'), 'wait': config.getfloat('norm_wait')}
         self.clips = {'wave': config.getfloat('clip_wave'), 'wait': config.getfloat('clip_wait')}
         self.coef_wait = config.getfloat('coef_wait')
+        # optional key (not in the reference's configs): the driver reaction time of the vType.  1.0 = SUMO's default, which
+        # the current reference uses; the paper-era runs used tau="0.5" (reference README.md:63)
+        self.tau = config.getfloat('tau', fallback=1.0)
         self.train_mode = True
         test_seeds = [int(s) for s in config.get('test_seeds').split(',')]
         self.n_replicas = int(n_replicas)
@@ -119,7 +122,7 @@ class TrafficSimulator:
             coef_wait=self.coef_wait, coop_gamma=self.coop_gamma, objective=self.obj, agent=self.agent,
             real_net_norm=real, use_wait='wait' in self.state_names,
             det_len=-1.0 if real else 50.0,                            # envs/env.py:333,376-377
-            halt_speed=0.1 if real else 1.39, queue_cap=10 if real else (1 << 20))
+            halt_speed=0.1 if real else 1.39, queue_cap=10 if real else (1 << 20), tau=self.tau)
 
     def _init_nodes(self):                                            # envs/env.py:207-242
         t = self._tables

@@ -45,6 +45,8 @@ class PolicyLayout:
         `wx` [dx, h] + `bl` [h] (relu), `wh` is empty."""
         self.recurrent = bool(recurrent)
         self.A = len(n_s_ls)
+        if self.A > 255:
+            raise ValueError("agent_of is a uint8 map (per-agent gradient-norm groups): at most 255 agents, got %d" % self.A)
         self.U = 2 * self.A
         self.n_a = np.asarray(n_a_ls, np.int32)
         self.n_wait = np.asarray(n_w_ls, np.int32)

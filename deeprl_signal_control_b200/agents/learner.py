@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from .. import dist as _dist
 from .layout import PolicyLayout
 
 
@@ -91,7 +92,7 @@ class BatchedA2C:
         self._upd_bufs = None
         self.kernel_launches = 0
         # fused tensor-core forward (csrc/tsc_policy_tc.cu): bf16 image of [Wx;Wh], refreshed after every update
-        self.use_tc = bool(use_tc) and (L.dx % 16 == 0)
+        self.use_tc = bool(use_tc) and (L.dx % 16 == 0) and layout.kw > 0    # else: the fp32 kernels
         self.tc_v2 = self.use_tc and (L.dx % 32 == 0)          # fc front end on the tensor cores too
         self.Wp = torch.zeros(U, ((L.dx + L.h) // 8) * 4 * L.h * 8 + 8 * L.dx * 8, dtype=torch.bfloat16,
                               device=self.dev)
@@ -293,7 +294,7 @@ class BatchedA2C:
                                     C.c_float(self.gamma), C.c_int32(T), C.c_int64(R), _p(self.Rs), _p(self.Adv), st()))
         self.G.zero_()
         self.stats.zero_()
-        scale = 1.0 / (T * self.total_replicas)
+        scale = _dist.grad_scale(T, 1, self.total_replicas)       # local SUM x 1/(n_step * R_total); ranks add up
         use_store = self.store_acts and all(self._acts_ok)
         n_obs = L.n_obs
         for r0 in range(0, R, self.chunk):
@@ -381,7 +382,7 @@ class BatchedA2C:
                                            C.c_int64(R * n_obs), _p(self.G), st()))
             self.kernel_launches += 4 if use_store else 5
         if self.pg is not None:
-            torch.distributed.all_reduce(self.G, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            _dist.allreduce_sum_(self.G, self.pg)
         _lib.check(lib.tscl_clip_rmsprop(self._h, _p(self.P), _p(self.G), _p(self.MS), _p(self.agent_of),
                                          C.c_float(self.max_grad_norm), C.c_float(lr), C.c_float(self.alpha),
                                          C.c_float(self.eps), _p(self.norms), st()))

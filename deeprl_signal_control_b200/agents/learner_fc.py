@@ -17,6 +17,7 @@ from typing import Optional
 import torch
 
 from .. import _lib
+from .. import dist as _dist
 from .layout import PolicyLayout
 from .learner import BatchedA2C, _p
 
@@ -63,7 +64,7 @@ class BatchedFcA2C(BatchedA2C):
                                     C.c_float(self.gamma), C.c_int32(T), C.c_int64(R), _p(self.Rs), _p(self.Adv), st()))
         self.G.zero_()
         self.stats.zero_()
-        scale = 1.0 / (T * self.total_replicas)
+        scale = _dist.grad_scale(T, 1, self.total_replicas)
         n_obs = L.n_obs
         for r0 in range(0, R, self.chunk):
             rc = min(self.chunk, R - r0)
@@ -92,7 +93,7 @@ class BatchedFcA2C(BatchedA2C):
                                            C.c_int64(R * n_obs), _p(self.G), st()))
             self.kernel_launches += 3
         if self.pg is not None:
-            torch.distributed.all_reduce(self.G, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            _dist.allreduce_sum_(self.G, self.pg)
         _lib.check(lib.tscl_clip_rmsprop(self._h, _p(self.P), _p(self.G), _p(self.MS), _p(self.agent_of),
                                          C.c_float(self.max_grad_norm), C.c_float(lr), C.c_float(self.alpha),
                                          C.c_float(self.eps), _p(self.norms), st()))

@@ -32,6 +32,7 @@ class IA2C:
         """policy='lstm': LstmACPolicy / FPLstmACPolicy, what the reference builds (agents/models.py:40-51);
         policy='fc': FcACPolicy (agents/policies.py:214-256), the FC variant of BASELINE config 2."""
         self.n_agent = len(n_s_ls)
+        self._pre_done = False
         self.reward_clip = model_config.getfloat('reward_clip')
         self.reward_norm = model_config.getfloat('reward_norm')
         self.n_s_ls, self.n_a_ls, self.n_w_ls = list(n_s_ls), list(n_a_ls), list(n_w_ls)
@@ -86,6 +87,8 @@ class IA2C:
         b = self.batched
         slot = b.obs_slot() if ('p' in out_type and b.t < b.T) else self._obs_dev
         slot.copy_(self._pack(obs))
+        if 'p' in out_type:
+            self._pre_done = bool(done)     # the pre-decision done of this step (utils.py:279-281, agents/utils.py:226)
         pi, val, _ = b.forward(slot, bool(done), out_type, sample=False)
         pol = [pi[0, i, :self.n_a_ls[i]].cpu().numpy() for i in range(self.n_agent)] if 'p' in out_type else None
         vals = [float(v) for v in val[0].cpu().numpy()] if 'v' in out_type else None
@@ -100,10 +103,13 @@ class IA2C:
         val = torch.tensor(np.asarray(values, np.float32).reshape(1, -1), device=dev)
         rew = torch.tensor(np.asarray(rewards, np.float32).reshape(1, -1) * np.ones((1, self.n_agent), np.float32),
                            device=dev)
+        # the observation of step t is the one the preceding forward('p') consumed (reference: the caller passes the
+        # same `ob` to forward and to add_transition, utils.py:148,165); keep the slot authoritative but verify it
+        row = np.concatenate([np.asarray(o, np.float32) for o in obs])
+        if not np.array_equal(b.obs_slot()[0, :row.shape[0]].cpu().numpy(), row):
+            b.obs_slot()[0, :row.shape[0]].copy_(torch.from_numpy(row))
+            b._acts_ok[b.t] = False         # stored activations belong to another observation: recompute in backward
         b.add_transition(rew, self._pre_done, bool(done), act=act, val=val)
-        self._pre_done = bool(done)
-
-    _pre_done = False
 
     def backward(self, R_ls, summary_writer=None, global_step=None):
         cur_lr = self.lr_scheduler.get(self.n_step)
@@ -114,13 +120,18 @@ class IA2C:
     def reset(self):
         self.batched.reset()
 
-    # ---- checkpoints: same file-name convention as the reference (agents/models.py:83-108) -------
+    # ---- checkpoints: reference file-name convention and VARIABLE NAMES (agents/models.py:83-108, checkpoint.py) ---
     def save(self, model_dir, global_step):
+        """`checkpoint-<step>.npz` keyed by the reference's TF variable names (`<policy>_<i>a/pi_fcw/w`, ...); the
+        RMSProp slot travels under `__b200__/` so that our own runs can resume (the reference's Saver does not store it)."""
+        from . import checkpoint as ck
         b = self.batched
-        torch.save({'params': b.P.cpu(), 'rms': b.MS.cpu(), 'step': int(global_step), 'name': self.name},
-                   os.path.join(model_dir, 'checkpoint-%d.pt' % int(global_step)))
+        named = ck.export_named(self.layout, b.P.cpu().numpy())
+        ck.save_npz(os.path.join(model_dir, 'checkpoint-%d.npz' % int(global_step)), named,
+                    {'rms': b.MS.cpu().numpy(), 'step': np.int64(global_step), 'name': np.array(self.name)})
 
     def load(self, model_dir, checkpoint=None):
+        from . import checkpoint as ck
         save_file, save_step = None, 0
         if os.path.exists(model_dir):
             if checkpoint is None:
@@ -129,13 +140,23 @@ class IA2C:
                         tokens = file.split('.')[0].split('-')
                         if len(tokens) != 2:
                             continue
-                        if int(tokens[1]) > save_step:
-                            save_file, save_step = file, int(tokens[1])
+                        if int(tokens[1]) >= save_step:
+                            save_file, save_step = 'checkpoint-%d' % int(tokens[1]), int(tokens[1])
             else:
-                save_file = 'checkpoint-%d.pt' % int(checkpoint)
-        if save_file is not None and os.path.exists(os.path.join(model_dir, save_file)):
-            ck = torch.load(os.path.join(model_dir, save_file))
-            self.batched.P.copy_(ck['params']); self.batched.MS.copy_(ck['rms'])
+                save_file = 'checkpoint-%d' % int(checkpoint)
+        base = os.path.join(model_dir, save_file) if save_file is not None else None
+        if base is not None and os.path.exists(base + '.npz'):
+            named, extra = ck.load_npz(base + '.npz')
+            b = self.batched
+            b.P.copy_(torch.from_numpy(ck.import_named(self.layout, named)))
+            if 'rms' in extra and extra['rms'].shape == tuple(b.MS.shape):
+                b.MS.copy_(torch.from_numpy(extra['rms']))
+            b.pack_weights()
+            logging.info('Checkpoint loaded: %s' % save_file)
+            return True
+        if base is not None and os.path.exists(base + '.pt'):          # round-1 format
+            c = torch.load(base + '.pt')
+            self.batched.P.copy_(c['params']); self.batched.MS.copy_(c['rms'])
             self.batched.pack_weights()
             logging.info('Checkpoint loaded: %s' % save_file)
             return True
@@ -206,7 +227,9 @@ class IQL:
                           total_step * model_config.getfloat('epsilon_ratio'), decay=eps_decay)
             buffer_size = model_config.getfloat('buffer_size')
             self.trans_buffer_ls = [ReplayBuffer(buffer_size, self.n_step) for _ in range(self.n_agent)]
-            self.opts = [torch.optim.Adam(list(p.values()), lr=lr_init) for p in self.nets]
+            # TF1 AdamOptimizer state (agents/policies.py:327): first / second moments per tensor and the step count
+            self.adam = [dict(t=0, m={k: torch.zeros_like(v) for k, v in p.items()},
+                              v={k: torch.zeros_like(v) for k, v in p.items()}) for p in self.nets]
 
     def _q(self, i, S):
         p, n_w = self.nets[i], self.n_w_ls[i]
@@ -247,46 +270,81 @@ class IQL:
         for i in range(self.n_agent):
             self.trans_buffer_ls[i].add_transition(obs[i], actions[i], rewards[i], next_obs[i], done)
 
+    def td_update(self, i, obs, acts, next_obs, dones, rs, cur_lr):
+        """One minibatch update of agent i = QPolicy.prepare_loss + backward (agents/policies.py:307-338,362-377):
+        loss = mean((q(s)[a] - stop_grad(done ? r : r + gamma max_a' q(s')[a']))^2), same network for both (no target
+        net), tf.clip_by_global_norm (g * clip / max(norm, clip)), TF1 Adam (lr_t = lr sqrt(1-b2^t)/(1-b1^t),
+        var -= lr_t m / (sqrt(v) + 1e-8)).  Returns (loss, grad_norm)."""
+        p = self.nets[i]
+        S = torch.as_tensor(np.asarray(obs, np.float32), device=self.dev)
+        S1 = torch.as_tensor(np.asarray(next_obs, np.float32), device=self.dev)
+        A = torch.as_tensor(np.asarray(acts).astype(np.int64), device=self.dev)
+        R = torch.as_tensor(np.asarray(rs, np.float32), device=self.dev)
+        D = torch.as_tensor(np.asarray(dones).astype(bool), device=self.dev)
+        q0 = self._q(i, S).gather(1, A[:, None])[:, 0]
+        with torch.no_grad():
+            tq = torch.where(D, R, R + self.gamma * self._q(i, S1).max(1)[0])
+        loss = ((q0 - tq) ** 2).mean()
+        keys = list(p.keys())
+        grads = torch.autograd.grad(loss, [p[k] for k in keys])
+        norm = torch.sqrt(sum((g * g).sum() for g in grads))
+        if self.max_grad_norm > 0:
+            scale = self.max_grad_norm / torch.clamp(norm, min=self.max_grad_norm)
+            grads = [g * scale for g in grads]
+        st = self.adam[i]
+        st['t'] += 1
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        lr_t = cur_lr * np.sqrt(1.0 - b2 ** st['t']) / (1.0 - b1 ** st['t'])
+        with torch.no_grad():
+            for k, g in zip(keys, grads):
+                st['m'][k] += (g - st['m'][k]) * (1.0 - b1)
+                st['v'][k] += (g * g - st['v'][k]) * (1.0 - b2)
+                p[k] -= lr_t * st['m'][k] / (torch.sqrt(st['v'][k]) + eps)
+        return float(loss.detach()), float(norm)
+
     def backward(self, summary_writer=None, global_step=None):
         cur_lr = self.lr_scheduler.get(self.n_step)
         if self.trans_buffer_ls[0].size < self.trans_buffer_ls[0].batch_size:
             return
         for i in range(self.n_agent):
-            for g in self.opts[i].param_groups:
-                g['lr'] = cur_lr
-            for _ in range(10):
+            for _ in range(10):                                   # agents/models.py:337-345
                 obs, acts, next_obs, rs, dones = self.trans_buffer_ls[i].sample_transition()
-                S = torch.as_tensor(obs.astype(np.float32), device=self.dev)
-                S1 = torch.as_tensor(next_obs.astype(np.float32), device=self.dev)
-                A = torch.as_tensor(acts.astype(np.int64), device=self.dev)
-                R = torch.as_tensor(rs.astype(np.float32), device=self.dev)
-                D = torch.as_tensor(dones.astype(bool), device=self.dev)
-                q0 = self._q(i, S).gather(1, A[:, None])[:, 0]
-                with torch.no_grad():
-                    tq = torch.where(D, R, R + self.gamma * self._q(i, S1).max(1)[0])
-                loss = ((q0 - tq) ** 2).mean()
-                self.opts[i].zero_grad()
-                loss.backward()
-                if self.max_grad_norm > 0:
-                    torch.nn.utils.clip_grad_norm_(list(self.nets[i].values()), self.max_grad_norm)
-                self.opts[i].step()
+                self.td_update(i, obs, acts, next_obs, dones, rs, cur_lr)
 
     def reset(self):
         return
 
+    def _prefix(self, i):
+        return '%s_%da_q/' % ('dqn' if self.model_type == 'dqn' else 'lr', i)      # agents/policies.py:343,346,383,386
+
+    def named_weights(self):
+        return {self._prefix(i) + k: v.detach().cpu().numpy() for i, p in enumerate(self.nets) for k, v in p.items()}
+
+    def load_named(self, named):
+        for i, p in enumerate(self.nets):
+            for k in p:
+                arr = np.asarray(named[self._prefix(i) + k], np.float32)
+                if tuple(arr.shape) != tuple(p[k].shape):
+                    raise ValueError('tensor %r has shape %s, expected %s' % (self._prefix(i) + k, arr.shape, tuple(p[k].shape)))
+                p[k].data.copy_(torch.from_numpy(arr))
+
     def save(self, model_dir, global_step):
-        torch.save({'nets': [{k: v.detach().cpu() for k, v in p.items()} for p in self.nets], 'step': int(global_step)},
-                   os.path.join(model_dir, 'checkpoint-%d.pt' % int(global_step)))
+        from . import checkpoint as ck
+        ck.save_npz(os.path.join(model_dir, 'checkpoint-%d.npz' % int(global_step)), self.named_weights(),
+                    {'step': np.int64(global_step)})
 
     def load(self, model_dir, checkpoint=None):
+        from . import checkpoint as ck
         files = [f for f in os.listdir(model_dir)] if os.path.exists(model_dir) else []
-        steps = [int(f.split('.')[0].split('-')[1]) for f in files if f.startswith('checkpoint-')]
+        steps = [int(f.split('.')[0].split('-')[1]) for f in files
+                 if f.startswith('checkpoint-') and len(f.split('.')[0].split('-')) == 2]
         if checkpoint is None and not steps:
             logging.error('Can not find old checkpoint for %s' % model_dir)
             return False
         step = int(checkpoint) if checkpoint is not None else max(steps)
-        ck = torch.load(os.path.join(model_dir, 'checkpoint-%d.pt' % step))
-        for p, q in zip(self.nets, ck['nets']):
-            for k in p:
-                p[k].data.copy_(q[k])
+        path = os.path.join(model_dir, 'checkpoint-%d.npz' % step)
+        if not os.path.exists(path):
+            logging.error('Can not find old checkpoint for %s' % model_dir)
+            return False
+        self.load_named(ck.load_npz(path)[0])
         return True

@@ -13,16 +13,22 @@ from typing import Optional
 import numpy as np
 import torch
 
+from .. import dist as _dist
 from ..sim import BatchedSim
 from .learner import BatchedA2C
 
 
 class BatchedTrainer:
-    def __init__(self, sim: BatchedSim, model: BatchedA2C, agent: str, lr: float, beta: float,
+    def __init__(self, sim: BatchedSim, model: BatchedA2C, agent: str, lr, beta,
                  seed0: int = 12, replica0: int = 0):
+        """lr / beta: floats (the 'constant' schedules of every shipped A2C config) or objects with the reference's
+        `Scheduler.get(n_step)` (agents/utils.py:268-281, agents/models.py:175-176); a schedule advances by n_step per
+        update exactly as in the reference (its unit is control steps of ONE environment)."""
         self.sim, self.model, self.agent = sim, model, agent
         self.lr, self.beta = lr, beta
-        self.seed, self.replica0 = seed0, replica0
+        self.seed0, self.replica0 = int(seed0), int(replica0)
+        self.total_replicas = int(getattr(model, "total_replicas", sim.R))
+        self.episode = 0
         self.T_episode = int(np.ceil(sim.params.episode_length_sec / sim.params.control_interval_sec))
         assert self.T_episode % model.T == 0                      # utils.py:121
         self.step_in_episode = 0
@@ -37,8 +43,9 @@ class BatchedTrainer:
 
     def start_episode(self):
         sim, m = self.sim, self.model
-        seeds = np.arange(sim.R, dtype=np.uint64) + np.uint64(self.seed + self.replica0)
-        self.seed += max(sim.R, 1)                                 # envs/env.py:560 (seed += 1 per episode, per replica)
+        # envs/env.py:560 (seed += 1 per episode and environment): disjoint over all (rank, episode) pairs
+        seeds = _dist.episode_seeds(self.seed0, self.episode, self.replica0, sim.R, max(self.total_replicas, sim.R))
+        self.episode += 1
         sim.reset(seeds)
         sim.set_train_mode(True)
         m.reset()
@@ -182,7 +189,9 @@ class BatchedTrainer:
         boot = None
         if not self.done:
             _, boot, _ = m.forward(m.obs_slot(m.T), False, out_type='v')    # utils.py:190
-        m.backward(boot, self.lr, self.beta)
+        lr = self.lr.get(m.T) if hasattr(self.lr, "get") else self.lr
+        beta = self.beta.get(m.T) if hasattr(self.beta, "get") else self.beta
+        m.backward(boot, lr, beta)
         self.n_updates += 1
         if self.done:
             self.episode_rewards.append(float((self._rew_acc / self.T_episode).mean()))   # utils.py:296-305

@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests are the parity tests proper and need a CUDA device; on a CPU-only box they are skipped (with the
+    reason shown) instead of erroring, so that a plain `pytest tests` is green there too."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200): there is no CPU fallback of the product path")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def grid_ma2c():
     from deeprl_signal_control_b200.net.large_grid import build_large_grid

@@ -57,3 +57,19 @@ def test_gradient_allreduce_convention_world2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_episode_seed_sets_are_disjoint_across_ranks_and_episodes():
+    """Rank k, episode e, replica r plays seed0 + e*R_total + k*R + r: no (rank, episode) pair replays the demand of
+    another one (the 1/(T*R_total) gradient scaling assumes R_total decorrelated trajectories per update)."""
+    from deeprl_signal_control_b200.dist import episode_seeds, shard_replicas
+    world, R, seed0 = 4, 8, 12
+    seen = set()
+    for rank in range(world):
+        replica0, ids, s0 = shard_replicas(rank, world, R, seed0)
+        assert list(s0) == list(episode_seeds(seed0, 0, replica0, R, world * R))
+        for ep in range(5):
+            s = set(int(x) for x in episode_seeds(seed0, ep, replica0, R, world * R))
+            assert len(s) == R and not (s & seen)
+            seen |= s
+    assert seen == set(range(seed0, seed0 + 5 * world * R))      # and contiguous: the reference's seed += 1 per episode

@@ -18,13 +18,19 @@ Before timing, every replica is advanced `--burnin` control steps (default 240 =
 seconds, the demand peak) so that the timed steps see a loaded network; burn-in is state
 preparation, the W warm-up steps are on top of it.
 
-value = (replicas over all ranks) * 25 agents * K / max-over-ranks(device time of K steps).
+value = (replicas over all ranks) * agents (25 grid / 28 Monaco) * K / max-over-ranks(device time of K steps).
 e2e   = same metric through the host-buffer entry point tsc_step_host (actions/fingerprints in
         pinned host memory -> H2D, kernel, obs/reward/done -> D2H, every step).
 roofline = tsc_step_kernel: algorithmic bytes (BASELINE.md §3 formula with the measured mean
         live vehicles) / mean launch duration (CUDA events around every launch) vs measured HBM peak.
-cpu_baseline / --impl reference = the CPU oracle (oracle/tsc_sim_ref.c, "port": SUMO is absent)
-        on all host cores over a bounded sample of the same workload.
+cpu_baseline / --impl reference = the CPU port of the SAME work (SUMO + TF1 are absent): oracle/tsc_sim_ref.c on all
+        usable host threads (cgroup cpu.max respected) for the control step and, in train mode, oracle/learner_cpu.py
+        (torch CPU fp32, all threads) for the policy forward of every step and one n-step A2C update per n_step —
+        a bounded sample of replicas, named in `sample`.
+--scenario real_net = BASELINE configs[3] (Monaco, 28 agents, MA2C, 2048 replicas, n_step 40,
+        config/config_ma2c_real.ini); the default large_grid = configs[2].
+value_steady = the same metric with the update amortised over n_step control steps (the driver's short --steps
+        window is forced to contain one whole update, which over-weights it; both numbers are printed).
 """
 import argparse
 import json
@@ -38,8 +44,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_AGENTS = 25
-N_STEP = 120          # batch_size of config/config_ma2c_large.ini
+N_STEP = {"large_grid": 120, "real_net": 40}     # batch_size of config/config_ma2c_{large,real}.ini
+
+
+def usable_cpus():
+    """Host threads this process can really use: sched affinity capped by the cgroup CPU quota (cpu.max)."""
+    n = len(os.sched_getaffinity(0))
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
 
 
 def parse():
@@ -48,7 +72,9 @@ def parse():
     p.add_argument("--steps", type=int, default=120)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--replicas", type=int, default=8192)
+    p.add_argument("--scenario", default="large_grid", choices=["large_grid", "real_net"],
+                   help="large_grid = BASELINE configs[2] (headline); real_net = configs[3] (Monaco MA2C, 2048 replicas)")
+    p.add_argument("--replicas", type=int, default=None, help="env replicas per GPU (default 8192 grid / 2048 Monaco)")
     p.add_argument("--burnin", type=int, default=240)
     p.add_argument("--mode", default=None, choices=[None, "sim", "train"])
     p.add_argument("--chunk", type=int, default=1024, help="replicas per BPTT chunk in the update")
@@ -64,10 +90,29 @@ def parse():
     return p.parse_args()
 
 
-def workload_name(R, mode, agent="ma2c", policy="lstm"):
+def workload_name(R, mode, agent="ma2c", policy="lstm", scenario="large_grid"):
     tag = "MA2C (configs[2])" if agent == "ma2c" else ("IA2C, FC policy (configs[1])" if policy == "fc" else "IA2C, LSTM policy")
-    return ("5x5 large_grid %s, %d env replicas per GPU, %s" %
-            (tag, R, "policy+sim+update" if mode == "train" else "sim control step, uniform-random actions"))
+    if scenario == "real_net":
+        tag = "MA2C (configs[3])"
+    return ("%s %s, %d env replicas per GPU, %s" %
+            ("Monaco real_net 28-intersection" if scenario == "real_net" else "5x5 large_grid", tag, R,
+             "policy+sim+update" if mode == "train" else "sim control step, uniform-random actions"))
+
+
+def build_scenario(args):
+    """(net tables, env params, n_step, reward_norm, wave block) of the benchmarked configuration."""
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    if args.scenario == "real_net":
+        from deeprl_signal_control_b200.net.real_net import real_net_tables
+        net = real_net_tables(args.agent)
+        # config/config_ma2c_real.ini [ENV_CONFIG]: queue objective, wave-only state, norm_wave 5, clip 2
+        par = EnvParams(agent=args.agent, objective="queue", norm_wave=5.0, norm_wait=100.0, clip_wave=2.0, clip_wait=2.0,
+                        coef_wait=0.0, coop_gamma=0.9, teleport_sec=300, real_net_norm=True, use_wait=False,
+                        det_len=-1.0, halt_speed=0.1, queue_cap=10)
+        return net, par, N_STEP["real_net"], 1.0
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid
+    net, par = build_large_grid(agent=args.agent), EnvParams(agent=args.agent)
+    return net, par, N_STEP["large_grid"], (2000.0 if args.agent == "ma2c" else 3000.0)
 
 
 def algorithmic_bytes(net, v_live):
@@ -113,19 +158,30 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(net, par, args, threads, budget_s=12.0, quiet=True):
-    """Time the CPU oracle on `threads` host threads over a bounded sample of the workload:
-    R_cpu replicas, burn-in to the same simulated time, then timed control steps."""
+def make_layout(net, args):
+    from deeprl_signal_control_b200.agents.layout import PolicyLayout
+    # config/config_ma2c_{large,real}.ini [MODEL_CONFIG]: num_fw 128, num_ft 32, num_fp 64, num_lstm 64
+    return PolicyLayout(net.n_s_ls, net.n_a_ls, net.n_w_ls, net.n_f_ls, net.node_obs_off, net.n_obs, fw=128, ft=32,
+                        ff=64 if args.agent == "ma2c" else 0, h=64, max_na=net.max_na, recurrent=args.policy != "fc")
+
+
+def cpu_reference(net, par, args, threads, n_step, mode, budget_s=12.0):
+    """Time the CPU port on `threads` host threads over a bounded sample of the workload: R_cpu replicas, burn-in to the
+    same simulated time, then timed control steps of the simulator (oracle/tsc_sim_ref.c, pthreads over replicas); in
+    train mode the learner's share of the same steps is timed too (oracle/learner_cpu.py: policy forward of every step,
+    one n-step update per n_step steps) and added — the reference runs env and learner serially (utils.py:142-193)."""
     from oracle.sim_ref import RefSim
     rng = np.random.default_rng(0)
+    na = int(max(net.n_a_ls))
+    acts_of = lambda *shape: (rng.integers(0, 1 << 30, shape + (net.n_nodes,)) % np.asarray(net.n_a_ls)).astype(np.int32)
     # pilot: cost of one replica control step on one thread, at a lightly loaded network
     pilot = RefSim(net, par, threads)
     pilot.reset(np.arange(threads, dtype=np.uint64))
     for _ in range(40):
-        pilot.step(rng.integers(0, 5, (threads, net.n_nodes), dtype=np.int32), None, threads=threads)
+        pilot.step(acts_of(threads), None, threads=threads)
     t0 = time.perf_counter()
     for _ in range(40):
-        pilot.step(rng.integers(0, 5, (threads, net.n_nodes), dtype=np.int32), None, threads=threads)
+        pilot.step(acts_of(threads), None, threads=threads)
     c_step = (time.perf_counter() - t0) / 40            # seconds per (threads replicas) step
     n_t = int(min(max(args.steps, 60), 240))             # timed control steps (stay inside the episode)
     R_cpu = int(np.clip(budget_s / ((args.burnin + n_t) * c_step * 3.0) * threads, threads, 4096))
@@ -133,18 +189,31 @@ def cpu_reference(net, par, args, threads, budget_s=12.0, quiet=True):
     sim = RefSim(net, par, R_cpu)
     sim.reset(np.arange(R_cpu, dtype=np.uint64) + np.uint64(args.seed))
     fp = rng.random((R_cpu, net.n_nodes, net.max_na), dtype=np.float32)
-    acts = rng.integers(0, 5, (8, R_cpu, net.n_nodes), dtype=np.int32)
+    acts = acts_of(8, R_cpu)
     # one call per phase: every thread walks its replicas through all the steps (ref_run_mt), threads are created once
     sim.run(acts, args.burnin, fp, threads=threads)
     n, t0 = n_t, time.perf_counter()
     sim.run(acts, n_t, fp, threads=threads)
-    el = time.perf_counter() - t0
+    el_sim = time.perf_counter() - t0
     live = float(np.mean([sim.misc(r)["live"] for r in range(R_cpu)]))
+    el, learner_note = el_sim, "sim control step only (--mode sim)"
+    if mode == "train":
+        from oracle.learner_cpu import time_learner
+        R_upd = min(R_cpu, 128)
+        t_fwd, t_upd = time_learner(make_layout(net, args), R_cpu, 3, R_upd, n_step, threads)
+        el_fwd = t_fwd * n_t                               # one policy forward per control step
+        el_upd = t_upd * (R_cpu / R_upd) * (n_t / n_step)  # one n-step update per n_step control steps
+        el = el_sim + el_fwd + el_upd
+        learner_note = ("+ policy forward of %d replicas x %d steps (%.2f s) + n-step A2C update amortised %.2f/%d steps "
+                        "(measured on %d replicas: %.2f s, scaled x%.1f) on torch CPU fp32, %d threads"
+                        % (R_cpu, n_t, el_fwd, n_t, n_step, R_upd, t_upd, R_cpu / R_upd, threads))
     return {"value": R_cpu * net.n_nodes * n / el, "unit": "agent-env-steps/s", "cores": threads,
             "kind": "port",
-            "sample": "%d replicas x %d control steps after %d burn-in steps (mean live %.0f veh/replica), "
-                      "oracle/tsc_sim_ref.c on %d pthreads; SUMO+TF1 absent so this is the restatement, not SUMO"
-                      % (R_cpu, n, args.burnin, live, threads)}, n, el, R_cpu
+            "sample": "%d replicas x %d control steps after %d burn-in steps (mean live %.0f veh/replica): "
+                      "oracle/tsc_sim_ref.c on %d pthreads (%.2f s) %s; SUMO + TF1 are absent from the image, so this is "
+                      "the CPU port of the same work, not SUMO / TensorFlow"
+                      % (R_cpu, n, args.burnin, live, threads, el_sim, learner_note),
+            "sim_only_value": R_cpu * net.n_nodes * n / el_sim}, n, el, R_cpu
 
 
 def main():
@@ -153,24 +222,27 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     mode = args.mode or "train"
-    from deeprl_signal_control_b200.net.large_grid import build_large_grid
-    from deeprl_signal_control_b200.net.tables import EnvParams
-    net, par = build_large_grid(agent=args.agent), EnvParams(agent=args.agent)
-    cores = len(os.sched_getaffinity(0))
+    if args.scenario == "real_net":
+        args.agent = "ma2c"
+    if args.replicas is None:
+        args.replicas = 2048 if args.scenario == "real_net" else 8192
+    net, par, n_step, reward_norm = build_scenario(args)
+    cores = usable_cpus()
+    wl = workload_name(args.replicas, mode, args.agent, args.policy, args.scenario)
 
     # ---------------- reference arm: the CPU implementation of the path ----------------------
     if args.impl == "reference":
         if rank != 0:
             return
         t_steps = max(args.steps, 1)
-        cb, n, el, R_cpu = cpu_reference(net, par, args, cores, budget_s=args.cpu_budget)
+        cb, n, el, R_cpu = cpu_reference(net, par, args, cores, n_step, mode, budget_s=args.cpu_budget)
         line = {"impl": "reference", "metric": "agent-env-steps/sec", "value": cb["value"],
                 "unit": "agent-env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * el / n, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args.replicas, mode, args.agent, args.policy),
-                           "note": "each reference step is a bounded sample: %d replicas instead of %d"
-                                   % (R_cpu, args.replicas)},
+                "config": {"workload": wl,
+                           "note": "each reference step is a bounded sample: %d replicas instead of %d; see "
+                                   "cpu_baseline.sample for what was timed" % (R_cpu, args.replicas)},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "agent-env-steps/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
@@ -203,14 +275,13 @@ def main():
         from deeprl_signal_control_b200.agents.learner import BatchedA2C
         from deeprl_signal_control_b200.agents.trainer import BatchedTrainer
         # config/config_ma2c_large.ini [MODEL_CONFIG]
-        lay = PolicyLayout(net.n_s_ls, net.n_a_ls, net.n_w_ls, net.n_f_ls, net.node_obs_off, net.n_obs,
-                           fw=128, ft=32, ff=64 if args.agent == "ma2c" else 0, h=64, recurrent=args.policy != "fc")
+        lay = make_layout(net, args)
         if args.policy == "fc":
             from deeprl_signal_control_b200.agents.learner_fc import BatchedFcA2C as Learner
         else:
             Learner = BatchedA2C
-        model = Learner(lay, R, n_step=N_STEP, gamma=0.99, v_coef=0.5, max_grad_norm=40.0, alpha=0.99, eps=1e-5,
-                        reward_norm=2000.0 if args.agent == "ma2c" else 3000.0, reward_clip=2.0, seed=args.seed,
+        model = Learner(lay, R, n_step=n_step, gamma=0.99, v_coef=0.5, max_grad_norm=40.0, alpha=0.99, eps=1e-5,
+                        reward_norm=reward_norm, reward_clip=2.0, seed=args.seed,
                         device=local_rank, chunk=args.chunk, replica0=rank * R, total_replicas=world * R,
                         process_group=dist.group.WORLD if world > 1 else None, allow_tf32=not args.fp32_gemm)
         trainer = BatchedTrainer(sim, model, args.agent, lr=5e-4, beta=0.01, seed0=args.seed, replica0=rank * R)
@@ -218,12 +289,14 @@ def main():
         def one_step(i):
             trainer.control_step()
     else:
-        seeds = np.arange(R, dtype=np.uint64) + np.uint64(args.seed + rank * R)
+        from deeprl_signal_control_b200.dist import shard_replicas
+        _, _, seeds = shard_replicas(rank, world, R, args.seed)
         sim.reset(seeds)
         gen = torch.Generator(device=dev)
         gen.manual_seed(1234 + rank)
         n_act_sets = 16
-        acts = [torch.randint(0, 5, (R, net.n_nodes), device=dev, dtype=torch.int32, generator=gen)
+        n_a_dev = torch.tensor(net.n_a_ls, device=dev, dtype=torch.int64)
+        acts = [(torch.randint(0, 1 << 30, (R, net.n_nodes), device=dev, generator=gen) % n_a_dev).to(torch.int32)
                 for _ in range(n_act_sets)]
         fp = torch.rand(R, net.n_nodes, net.max_na, device=dev, generator=gen)
         sim_events = []
@@ -243,7 +316,7 @@ def main():
     if trainer is not None:
         # the timed region must never skip the learner update: align it so that it ENDS on an update boundary
         # (ceil(K / n_step) updates inside; for K < n_step this over-counts update work — conservative)
-        while (trainer.model.t + args.steps) % N_STEP != 0:
+        while (trainer.model.t + args.steps) % n_step != 0:
             one_step(0)
             align_steps += 1
     live0 = sim.mean_live()
@@ -251,6 +324,7 @@ def main():
     sampler.start()
     if trainer is not None:
         trainer.sim_events = []
+        trainer.update_events = []
         l0 = trainer.model.kernel_launches
         upd0 = trainer.n_updates
     else:
@@ -265,10 +339,14 @@ def main():
     total_ms = t_start.elapsed_time(t_end)
     evs = trainer.sim_events if trainer is not None else sim_events
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    update_ms = None
     if trainer is not None:
         timed_launches = args.steps + (trainer.model.kernel_launches - l0)
         n_updates_timed = trainer.n_updates - upd0
         trainer.sim_events = None
+        if trainer.update_events:
+            update_ms = float(np.mean([a.elapsed_time(b) for a, b in trainer.update_events]))
+        trainer.update_events = None
     else:
         timed_launches = args.steps
         n_updates_timed = 0
@@ -281,10 +359,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * R * net.n_nodes * args.steps / (total_ms_max * 1e-3)
+    value_steady = None
+    if update_ms is not None and n_updates_timed > 0:
+        # the same measured quantities, re-weighted: K rollout steps + K/n_step updates (instead of n_updates_timed)
+        t = torch.tensor([update_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        upd = float(t.item())
+        roll_ms = (total_ms_max - n_updates_timed * upd) / args.steps
+        value_steady = {"value": world * R * net.n_nodes / ((roll_ms + upd / n_step) * 1e-3), "unit": "agent-env-steps/s",
+                        "rollout_ms_per_step": roll_ms, "update_ms": upd, "n_step": n_step,
+                        "how": "(timed ms - updates_in_timed_region x update_ms) / steps + update_ms / n_step, all "
+                               "measured with CUDA events in this run"}
 
     # ---------------- e2e: the environment driven through the host-buffer C-ABI call ------------
     if trainer is not None:
-        e2e_steps = N_STEP                     # one full rollout + one update
+        e2e_steps = n_step                     # one full rollout + one update
         if args.policy == "fc":
             args.e2e_parts = 1                 # the replica-range forward exists for the fused LSTM kernel only
         if args.e2e_parts > 1:
@@ -302,15 +392,16 @@ def main():
         h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4
         d2h = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
         e2e_api = ("BatchedTrainer.control_step_host: policy forward on device, actions+fingerprints D2H, "
-                   "tsc_step_host (H2D, kernel, D2H), obs+reward H2D, update every 120 steps")
+                   "tsc_step_host (H2D, kernel, D2H), obs+reward H2D, update every %d steps" % n_step)
         if args.e2e_parts > 1:
             e2e_api = ("BatchedTrainer.control_step_host_pipelined: %d replica ranges, one stream each; per range: policy "
                        "forward (tscl_policy_step_v2r), actions+fingerprints D2H to pinned host buffers, "
                        "tsc_step_host_range (H2D, kernel, D2H, host sync), obs+reward H2D into the learner; update "
-                       "every 120 steps" % args.e2e_parts)
+                       "every %d steps" % (args.e2e_parts, n_step))
     else:
         e2e_steps = max(3, min(args.steps, 20))
-        h_act = [torch.randint(0, 5, (R, net.n_nodes), dtype=torch.int32).pin_memory().numpy() for _ in range(4)]
+        h_act = [(torch.randint(0, 1 << 30, (R, net.n_nodes)) % torch.tensor(net.n_a_ls)).to(torch.int32).pin_memory().numpy()
+                 for _ in range(4)]
         h_fp = torch.rand(R, net.n_nodes, net.max_na).pin_memory().numpy()
         sim._h_out = tuple(torch.from_numpy(a).pin_memory().numpy() for a in (
             np.zeros((R, net.n_obs), np.float32), np.zeros((R, net.n_nodes), np.float32),
@@ -343,26 +434,43 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = algorithmic_bytes(net, v_live) * R
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "r01_sim_kernel_traffic.json")
-    if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+    traffic, issue = None, None
+    prof = None
+    for name in ("r02_sim_kernel_traffic.json", "r01_sim_kernel_traffic.json"):      # newest ncu capture of the kernel
+        tr_path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tr_path):
+            prof = json.load(open(tr_path))
+            break
+    if prof is not None and args.scenario == "large_grid" and prof.get("grid") == R:
+        traffic = prof.get("dram_bytes_per_launch")
+        if prof.get("warp_inst_per_launch"):
+            # second roofline of the same kernel: instruction issue (what actually bounds it).  Warp instructions per
+            # launch come from the committed ncu capture (smsp__inst_executed.sum); the rate uses the launch duration
+            # measured live here; peak = 148 SMs x 4 warp schedulers x 1 instruction / cycle x the sampled SM clock.
+            clk = (sampler.summary().get("sm_mhz") or 1965) * 1e6
+            issue_peak = 148 * 4 * clk
+            issue_rate = float(prof["warp_inst_per_launch"]) / (kern_ms * 1e-3)
+            issue = {"bound": "issue", "achieved": issue_rate / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
+                     "frac": issue_rate / issue_peak, "warp_inst_per_launch": prof["warp_inst_per_launch"],
+                     "source": prof.get("source")}
     roofline = {"bound": "hbm", "kernel": "tsc_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "mean_live_vehicles_per_replica": v_live,
                 "kernel_ms_per_launch": kern_ms, "share_of_step": kern_ms * args.steps / total_ms,
-                "note": "kernel is issue-bound, not HBM-bound: ~1.2k instructions per vehicle-second x5 "
-                        "fused sub-steps per 32 B of state traffic (DESIGN.md §5)"}
+                "issue": issue,
+                "note": "SURVEY 8(d) names HBM as the bound, so `frac` is against the measured copy bandwidth; the kernel is "
+                        "in fact instruction-issue-bound (five fused simulated seconds of Krauss updates per 24-32 B of "
+                        "state per vehicle) - see `issue` and DESIGN.md section 5"}
     cb = None
     if not args.no_cpu_baseline:
-        cb, _, _, _ = cpu_reference(net, par, args, cores, budget_s=args.cpu_budget)
+        cb, _, _, _ = cpu_reference(net, par, args, cores, n_step, mode, budget_s=args.cpu_budget)
     line = {"metric": "agent-env-steps/sec", "value": value, "unit": "agent-env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if mode == "sim" else "f32 (sim, LSTM cell, loss, optimizer) + bf16 tensor-core operands with f32 accumulation (learner GEMMs)",
             "data": "synthetic",
-            "config": {"workload": workload_name(R, mode, args.agent, args.policy), "replicas_per_gpu": R, "agents": net.n_nodes,
-                       "burnin_control_steps": args.burnin, "mode": mode, "n_step": N_STEP,
+            "config": {"workload": wl, "scenario": args.scenario, "replicas_per_gpu": R, "agents": net.n_nodes,
+                       "burnin_control_steps": args.burnin, "mode": mode, "n_step": n_step,
                        "updates_in_timed_region": n_updates_timed, "untimed_alignment_steps": align_steps,
                        "learner_gemm_library": "own tcgen05 kernels for the forward, BPTT and all weight gradients; cuBLAS "
                                                "bf16 only for dX = dZ.Wx^T (1 plain batched GEMM per update chunk)"
@@ -371,6 +479,7 @@ def main():
                              % (R * sim.info()["state_bytes_per_replica"] / 1e6),
                        "parallelism": "replica-dp%d" % world},
             "clocks": sampler.summary(),
+            "value_steady": value_steady,
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": e2e_api},
             "gpu_launches": timed_launches,

@@ -39,6 +39,7 @@ class BatchedTrainer:
         self.n_env_steps = 0
         self._uniform_fp = None
         self.sim_events = None        # list of (start, end) CUDA events around tsc_step when timing is on
+        self.update_events = None     # same around update() (bootstrap forward + backward)
         self.start_episode()
 
     def start_episode(self):
@@ -185,6 +186,16 @@ class BatchedTrainer:
             self.update()
 
     def update(self):
+        m = self.model
+        if self.update_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._update()
+        if self.update_events is not None:
+            e1.record()
+            self.update_events.append((e0, e1))
+
+    def _update(self):
         m = self.model
         boot = None
         if not self.done:

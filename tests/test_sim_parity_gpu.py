@@ -169,3 +169,48 @@ def test_single_replica_and_observe_only():
             np.testing.assert_array_equal(o1.view(np.uint32), ref.observe(fp).view(np.uint32))
             c1, v1 = gpu.dump_state(0)
             np.testing.assert_array_equal(c0, c1); np.testing.assert_array_equal(v0, v1)
+
+
+def test_many_waves_and_replica_ranges_bit_exact():
+    """R = 2304 replicas = several waves of resident CTAs (4 per SM x 148 SMs = 592): the oracle follows a SAMPLE of
+    replicas spread over all waves (each replica is independent, so stepping the sample alone is the same computation),
+    and the host-buffer range entry point (`tsc_step_host_range`, rep0 > 0) must agree with the device-resident step."""
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    from deeprl_signal_control_b200.sim import BatchedSim
+    from oracle.sim_ref import RefSim
+    net, par = build_large_grid(agent="ma2c"), EnvParams(agent="ma2c")
+    R = 2304
+    sample = np.array([0, 1, 591, 592, 593, 1183, 1184, 1500, 1776, 2047, 2048, 2302, 2303])
+    gpu, gpu2 = BatchedSim(net, par, R), BatchedSim(net, par, R)
+    ref = RefSim(net, par, len(sample))
+    seeds = np.arange(R, dtype=np.uint64) * np.uint64(31) + np.uint64(5)
+    gpu.reset(seeds); gpu2.reset(seeds); ref.reset(seeds[sample])
+    rng = np.random.default_rng(3)
+    r0, cnt = 1000, 700                                      # the range stepped through the host-buffer call
+    for step in range(150):
+        act = rng.integers(0, 5, size=(R, net.n_nodes), dtype=np.int32)
+        fp = rng.random((R, net.n_nodes, net.max_na), dtype=np.float32)
+        obs, rew, grew, done = gpu.step(torch.from_numpy(act).cuda(), torch.from_numpy(fp).cuda())
+        o2, r2, g2, d2 = ref.step(act[sample], fp[sample], threads=4)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(obs[sample].cpu().numpy().view(np.uint32), o2.view(np.uint32))
+        np.testing.assert_array_equal(rew[sample].cpu().numpy().view(np.uint32), r2.view(np.uint32))
+        np.testing.assert_array_equal(grew[sample].cpu().numpy().view(np.uint32), g2.view(np.uint32))
+        # second handle: replicas [r0, r0+cnt) through tsc_step_host_range, the rest through the device call on ranges
+        ho = np.zeros((cnt, net.n_obs), np.float32); hr = np.zeros((cnt, net.n_nodes), np.float32)
+        hg = np.zeros(cnt, np.float32); hd = np.zeros(cnt, np.uint8)
+        gpu2.step_host_range(r0, cnt, np.ascontiguousarray(act[r0:r0 + cnt]), np.ascontiguousarray(fp[r0:r0 + cnt]),
+                             ho, hr, hg, hd, sync=True)
+        np.testing.assert_array_equal(ho.view(np.uint32), obs[r0:r0 + cnt].cpu().numpy().view(np.uint32))
+        np.testing.assert_array_equal(hr.view(np.uint32), rew[r0:r0 + cnt].cpu().numpy().view(np.uint32))
+        np.testing.assert_array_equal(hg.view(np.uint32), grew[r0:r0 + cnt].cpu().numpy().view(np.uint32))
+    for k, r in enumerate(sample[[0, 3, 7, 12]]):
+        c1, v1 = gpu.dump_state(int(r))
+        c2, v2 = ref.dump_state([0, 3, 7, 12][k])
+        np.testing.assert_array_equal(c1, c2)
+        np.testing.assert_array_equal(v1, v2)
+    c1, v1 = gpu.dump_state(r0 + 5)
+    c2, v2 = gpu2.dump_state(r0 + 5)
+    np.testing.assert_array_equal(c1, c2); np.testing.assert_array_equal(v1, v2)
+    assert ref.misc(0)["live"] > 100

@@ -41,9 +41,26 @@
 #define F_ARRIVE 2
 
 typedef struct {
-  float pos, spd;
+  uint32_t xv; /* position : 16 (1/64 m) | speed : 16 (1/1024 m/s), see tsc.h "vehicle record" */
   uint32_t m0; /* wait:10 | hop:6 | route:8 | sfq:8 */
-} veh_t;   /* 12 bytes; trip statistics (depart, total wait) are not carried on the hot path */
+} veh_t;   /* 8 bytes; trip statistics (depart, total wait) are not carried on the hot path */
+
+/* fixed-point state: both scales are powers of two, so unpacking is exact */
+#define XQ_SCALE 64.0f
+#define XQ_INV 0.015625f
+#define VQ_SCALE 1024.0f
+#define VQ_INV 0.0009765625f
+static inline float veh_x(uint32_t xv) { return (float)(xv & 0xffffu) * XQ_INV; }
+static inline float veh_v(uint32_t xv) { return (float)(xv >> 16) * VQ_INV; }
+static inline uint32_t pack_xv(float x, float v) {
+  /* positions are truncated (a vehicle that stops 1 mm short of a stop line must stay short of it), speeds rounded */
+  int xq = (int)(x * XQ_SCALE), vq = (int)(v * VQ_SCALE + 0.5f);
+  if (xq < 0) xq = 0;
+  if (xq > 65535) xq = 65535;
+  if (vq < 0) vq = 0;
+  if (vq > 65535) vq = 65535;
+  return (uint32_t)xq | ((uint32_t)vq << 16);
+}
 
 typedef struct {
   veh_t* ring;          /* [n_slots] */
@@ -81,18 +98,23 @@ static inline uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
   return h;
 }
+/* key of one simulated second of one replica (two rounds), then ONE round per draw (entity b, index c) */
+static inline uint32_t rng_key(uint32_t s0, uint32_t s1, uint32_t a) {
+  return mix32(mix32(s0 ^ (a * 0x9E3779B1U)) ^ s1);
+}
+static inline uint32_t rng_draw(uint32_t key, uint32_t b, uint32_t c) {
+  return mix32(key ^ (b * 0x85EBCA77U + c * 0xC2B2AE3DU));
+}
 static inline uint32_t rng_u32(uint32_t s0, uint32_t s1, uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t h = mix32(s0 ^ (a * 0x9E3779B1U));
-  h = mix32(h ^ s1 ^ (b * 0x85EBCA77U));
-  h = mix32(h ^ (c * 0xC2B2AE3DU));
-  return h;
+  return rng_draw(rng_key(s0, s1, a), b, c);
 }
 static inline float u01(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* Krauss car-following, Euler update, dt = 1 s (SUMO MSCFModel.cpp, restated)                 */
-static inline float brake_gap(float v, float b) {
-  int steps = (int)(v / b);
+/* ib = 1 / b is formed once (float division) and multiplied: one IEEE division less per call, same on CPU and GPU */
+static inline float brake_gap(float v, float b, float ib) {
+  int steps = (int)(v * ib);
   float fs = (float)steps;
   float t1 = fs * v;
   float t2 = b * fs;
@@ -101,10 +123,10 @@ static inline float brake_gap(float v, float b) {
   float t5 = t4 * 0.5f;
   return t1 - t5;
 }
-static inline float stop_speed(float gap, float b, float tau) {
+static inline float stop_speed(float gap, float b, float ib, float tau) {
   float g = gap - 0.001f;
   if (g < 0.0f) return 0.0f;
-  float q = (2.0f * g) / b;
+  float q = (2.0f * g) * ib;
   q = q - tau;
   float tt = tau * tau;
   float disc = 1.0f + 4.0f * (q + tt);
@@ -119,8 +141,8 @@ static inline float stop_speed(float gap, float b, float tau) {
   float r = (g - h) / (n + tau);
   return n * b + r;
 }
-static inline float follow_speed(float gap, float v_lead, float b, float tau) {
-  return stop_speed(gap + brake_gap(v_lead, b), b, tau);
+static inline float follow_speed(float gap, float v_lead, float b, float ib, float tau) {
+  return stop_speed(gap + brake_gap(v_lead, b, ib), b, ib, tau);
 }
 static inline float free_speed(float dist, float target, float b) {
   if (dist < target) return target;
@@ -185,6 +207,8 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
   const tsc_cfg* c = &s->cfg;
   const int L = n->n_lanes;
   const uint32_t t_abs = (uint32_t)r->cur_sec;
+  const uint32_t key = rng_key(r->seed_lo, r->seed_hi, t_abs);
+  const float ib = 1.0f / c->decel;
   node_signal(s, r, yellow_phase, open, major, ymask);
 
   /* A1: which links have an approaching head vehicle with a green light */
@@ -197,8 +221,8 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
     int node = n->link_node[link];
     if (node < 0) continue;
     uint32_t bit = 1u << n->link_tlidx[link];
-    float d = n->lane_len[l] - h->pos;
-    if ((open[node] & bit) && d <= 3.0f * h->spd + 7.5f) approach[node] |= bit;
+    float d = n->lane_len[l] - veh_x(h->xv);
+    if ((open[node] & bit) && d <= 3.0f * veh_v(h->xv) + 7.5f) approach[node] |= bit;
   }
   /* A2: speed limit of each lane's head vehicle from the junction ahead */
   for (int l = 0; l < L; ++l) {
@@ -208,13 +232,13 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
     uint32_t route = M0_ROUTE(h->m0), hop = M0_HOP(h->m0);
     int link = n->route_link[route * n->max_hops + hop];
     if (link < 0) continue; /* arrival lane */
-    float d = n->lane_len[l] - h->pos;
+    float d = n->lane_len[l] - veh_x(h->xv);
     int node = n->link_node[link];
     int blocked = 0;
     if (node >= 0 && (int)M0_WAIT(h->m0) < c->teleport_sec) {
       uint32_t bit = 1u << n->link_tlidx[link];
       if (ymask[node] & bit) {
-        blocked = brake_gap(h->spd, c->decel) <= d;
+        blocked = brake_gap(veh_v(h->xv), c->decel, ib) <= d;
       } else if (!(open[node] & bit)) {
         blocked = 1;
       } else {
@@ -223,16 +247,16 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
         if (approach[node] & foes) blocked = 1;
       }
     }
-    if (blocked) { head_lim[l] = stop_speed(d, c->decel, c->tau); continue; }
+    if (blocked) { head_lim[l] = stop_speed(d, c->decel, ib, c->tau); continue; }
     float lim = INF_SPEED;
     float lv = n->link_vmax[link];
     if (lv < 1.0e8f) lim = free_speed(d, lv, c->decel);
     int nl = n->route_lane[route * n->max_hops + hop + 1];
     if (r->cnt[nl] > 0) {
       veh_t* t = veh_at(n, r, nl, r->cnt[nl] - 1);
-      float gap = d + (t->pos - c->veh_len);
+      float gap = d + (veh_x(t->xv) - c->veh_len);
       gap = gap - c->min_gap;
-      float fs = follow_speed(gap, t->spd, c->decel, c->tau);
+      float fs = follow_speed(gap, veh_v(t->xv), c->decel, ib, c->tau);
       if (fs < lim) lim = fs;
     }
     head_lim[l] = lim;
@@ -245,29 +269,30 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       veh_t* v = veh_at(n, r, l, k);
       int slot = (int)(v - r->ring);
       (void)base;
+      const float vx = veh_x(v->xv), vv = veh_v(v->xv);
       float sf = 0.5f + (float)M0_SFQ(v->m0) * (1.0f / 256.0f);
       float vmax = n->lane_vmax[l] * sf;
-      float vfree = v->spd + c->accel;
+      float vfree = vv + c->accel;
       if (vmax < vfree) vfree = vmax;
       float vsafe;
       if (k == 0) {
         vsafe = head_lim[l];
       } else {
         veh_t* ld = veh_at(n, r, l, k - 1);
-        float gap = ld->pos - c->veh_len;
-        gap = gap - v->pos;
+        float gap = veh_x(ld->xv) - c->veh_len;
+        gap = gap - vx;
         gap = gap - c->min_gap;
-        vsafe = follow_speed(gap, ld->spd, c->decel, c->tau);
+        vsafe = follow_speed(gap, veh_v(ld->xv), c->decel, ib, c->tau);
       }
       float vnm = vfree < vsafe ? vfree : vsafe;
-      float vmin = v->spd - c->decel;
+      float vmin = vv - c->decel;
       if (vmin < 0.0f) vmin = 0.0f;
       if (vnm < vmin) vmin = vnm;
-      float u = u01(rng_u32(r->seed_lo, r->seed_hi, t_abs, (uint32_t)l, (uint32_t)k));
+      float u = u01(rng_draw(key, (uint32_t)l, (uint32_t)k));
       float basev = vnm < c->accel ? vnm : c->accel;
       float vd = vnm - (c->sigma * basev) * u;
       float vn = vd > vmin ? vd : vmin;
-      float xn = v->pos + vn;
+      float xn = vx + vn;
       uint8_t f = 0;
       if (xn >= Ll) {
         if (k == 0) {
@@ -275,8 +300,8 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
           f = link < 0 ? F_ARRIVE : F_CROSS;
         } else { /* a lane discharges at most one vehicle per second */
           xn = Ll - 0.01f;
-          vn = xn - v->pos;
-          if (vn < 0.0f) { vn = 0.0f; xn = v->pos; }
+          vn = xn - vx;
+          if (vn < 0.0f) { vn = 0.0f; xn = vx; }
         }
       }
       vnew[slot] = vn; xnew[slot] = xn; flag[slot] = f;
@@ -287,17 +312,17 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
     for (int k = 0; k < r->cnt[l]; ++k) {
       veh_t* v = veh_at(n, r, l, k);
       int slot = (int)(v - r->ring);
-      v->pos = xnew[slot];
-      v->spd = vnew[slot];
+      const float vn = vnew[slot];      /* waiting is decided on the computed speed, the record stores it rounded */
+      v->xv = pack_xv(xnew[slot], vn);
       uint32_t w = M0_WAIT(v->m0);
-      if (r->trip && v->spd < 0.1f) { /* tripinfo waitingTime / waitingCount */
+      if (r->trip && vn < 0.1f) { /* tripinfo waitingTime / waitingCount */
         uint32_t t1 = r->trip[slot];
         uint32_t wt = T1_WAIT(t1), wc = T1_WCNT(t1);
         if (wt < 4095u) wt++;
         if (w == 0 && wc < 255u) wc++;
         r->trip[slot] = T1_DEPART(t1) | (wt << 12) | (wc << 24);
       }
-      if (v->spd < 0.1f) {
+      if (vn < 0.1f) {
         if (w < 1023u) w++;
       } else {
         w = 0;
@@ -310,7 +335,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
   for (int t = 0; t < L; ++t) {
     int cur = r->cnt[t];
     int have_tail = cur > 0;
-    float tail_x = have_tail ? veh_at(n, r, t, cur - 1)->pos : 0.0f;
+    float tail_x = have_tail ? veh_x(veh_at(n, r, t, cur - 1)->xv) : 0.0f;
     for (int q = n->lane_inl_off[t]; q < n->lane_inl_off[t + 1]; ++q) {
       int link = n->lane_inl[q];
       int src = n->link_from[link];
@@ -322,7 +347,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       if (n->route_link[route * n->max_hops + hop] != link) continue;
       if (n->route_lane[route * n->max_hops + hop + 1] != t) continue;
       if (cur >= n->lane_cap[t]) continue; /* refused: ring full */
-      float x = h->pos - n->lane_len[src];
+      float x = veh_x(h->xv) - n->lane_len[src];
       if (have_tail) {
         float lim = tail_x - c->veh_len;
         lim = lim - c->min_gap;
@@ -333,9 +358,9 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       int idx = r->head[t] + cur;
       if (idx >= cap) idx -= cap;
       veh_t* e = &r->ring[n->lane_slot0[t] + idx];
-      *e = *h;
-      e->pos = x;
+      e->xv = pack_xv(x, veh_v(h->xv));
       e->m0 = (h->m0 & ~(63u << 10)) | ((hop + 1) << 10);
+      x = veh_x(e->xv);                 /* the tail the next source sees is the stored (rounded) position */
       flag[n->lane_slot0[t] + idx] = 0;
       if (r->trip) r->trip[n->lane_slot0[t] + idx] = r->trip[hslot];
       cur++; tail_x = x; have_tail = 1;
@@ -363,7 +388,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       }
       else if (flag[hslot] == F_CROSS) {
         if (accepted[l]) pop = 1;
-        else { h->pos = n->lane_len[l] - 0.01f; h->spd = 0.0f; }
+        else { h->xv = pack_xv(n->lane_len[l] - 0.01f, 0.0f); }
       }
       if (pop) {
         r->head[l]++;
@@ -379,7 +404,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
     for (int q = 0; q < n->n_src; ++q) {
       int due = n->src_due[t_abs * n->n_src + q];
       if (n->src_group && n->n_pint > 0 && due > 0 && n->src_group[q] >= 0) { /* stochastic demand (tsc.h) */
-        float ug = u01(rng_u32(r->seed_lo, r->seed_hi, t_abs, 0x20000u + (uint32_t)n->src_group[q], 7u));
+        float ug = u01(rng_draw(key, 0x20000u + (uint32_t)n->src_group[q], 7u));
         int iv = (int)t_abs / n->pint_sec;
         if (iv >= n->n_pint) iv = n->n_pint - 1;
         if (!(ug >= n->src_plo[iv * n->n_src + q] && ug < n->src_phi[iv * n->n_src + q])) due = 0;
@@ -410,15 +435,15 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       if (cnt >= n->lane_cap[lane]) continue;
       float free_back = n->lane_len[lane];
       if (cnt > 0) {
-        free_back = veh_at(n, r, lane, cnt - 1)->pos - c->veh_len;
+        free_back = veh_x(veh_at(n, r, lane, cnt - 1)->xv) - c->veh_len;
         free_back = free_back - c->min_gap;
       }
       if (free_back < c->veh_len) continue;
       uint32_t qq = (uint32_t)q;
-      float u = u01(rng_u32(r->seed_lo, r->seed_hi, t_abs, qq, (1u << 16)));
+      float u = u01(rng_draw(key, qq, (1u << 16)));
       float pos = c->veh_len + u * (free_back - c->veh_len);
       float su = 0.0f;
-      for (uint32_t j = 1; j <= 4; ++j) su = su + u01(rng_u32(r->seed_lo, r->seed_hi, t_abs, qq, (1u << 16) | j));
+      for (uint32_t j = 1; j <= 4; ++j) su = su + u01(rng_draw(key, qq, (1u << 16) | j));
       /* speedFactor ~ N(1, speed_dev) via Irwin-Hall(4): std of sum = sqrt(1/3) */
       float sfr = 1.0f + (c->speed_dev * 1.7320508f) * (su - 2.0f);
       int sfq = (int)((sfr - 0.5f) * 256.0f);
@@ -428,7 +453,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       int idx = r->head[lane] + cnt;
       if (idx >= cap) idx -= cap;
       veh_t* e = &r->ring[n->lane_slot0[lane] + idx];
-      e->pos = pos; e->spd = 0.0f;
+      e->xv = pack_xv(pos, 0.0f);
       e->m0 = ((uint32_t)n->src_route[q] << 16) | ((uint32_t)sfq << 24);
       if (r->trip) r->trip[n->lane_slot0[lane] + idx] = t_abs & 4095u; /* depart second */
       r->cnt[lane] = cnt + 1;
@@ -449,10 +474,11 @@ static void measure(ref_sim* s, replica_t* r) {
     int veh = 0, halt = 0, wait = 0;
     for (int k = 0; k < r->cnt[l]; ++k) {
       veh_t* v = veh_at(n, r, l, k);
-      if (c->det_len > 0.0f && !(v->pos > Ll - c->det_len)) break;
+      const float vx = veh_x(v->xv);
+      if (c->det_len > 0.0f && !(vx > Ll - c->det_len)) break;
       veh++;
-      if (v->spd < c->halt_speed) halt++;
-      if (k == 0 && v->pos > 0.0f) wait = (int)M0_WAIT(v->m0);
+      if (veh_v(v->xv) < c->halt_speed) halt++;
+      if (k == 0 && vx > 0.0f) wait = (int)M0_WAIT(v->m0);
     }
     r->det_veh[d] = veh; r->det_halt[d] = halt; r->det_wait[d] = wait;
   }
@@ -733,8 +759,8 @@ void ref_traffic_stats(ref_sim* s, float* out) {
     for (int l = 0; l < n->n_lanes; ++l)
       for (int k = 0; k < r->cnt[l]; ++k) {
         veh_t* v = veh_at(n, r, l, k);
-        V++; wsum += (int)M0_WAIT(v->m0); sp = sp + v->spd;
-        if (v->spd < 0.1f) halt[l]++;
+        V++; wsum += (int)M0_WAIT(v->m0); sp = sp + veh_v(v->xv);
+        if (veh_v(v->xv) < 0.1f) halt[l]++;
       }
     float q = 0.0f, q2 = 0.0f;
     for (int d = 0; d < n->n_det; ++d) { float h = (float)halt[n->det_lane[d]]; q = q + h; q2 = q2 + h * h; }
@@ -820,7 +846,8 @@ void ref_dump_state(ref_sim* s, int32_t replica, int32_t* lane_cnt, uint32_t* ve
     lane_cnt[l] = r->cnt[l];
     for (int k = 0; k < r->cnt[l]; ++k) {
       veh_t* v = veh_at(n, r, l, k);
-      memcpy(veh + 3 * (size_t)w, v, 12);
+      float fx = veh_x(v->xv), fv = veh_v(v->xv);
+      memcpy(veh + 3 * (size_t)w, &fx, 4); memcpy(veh + 3 * (size_t)w + 1, &fv, 4); veh[3 * (size_t)w + 2] = v->m0;
       w++;
     }
   }
@@ -831,9 +858,9 @@ void ref_dump_state(ref_sim* s, int32_t replica, int32_t* lane_cnt, uint32_t* ve
  * 2 follow_speed(gap=a, v_lead=b, b=c, tau=d), 3 free_speed(dist=a, target=b, b=c) */
 float ref_probe_krauss(int32_t kind, float a, float b, float c, float d) {
   switch (kind) {
-    case 0: return brake_gap(a, b);
-    case 1: return stop_speed(a, b, c);
-    case 2: return follow_speed(a, b, c, d);
+    case 0: return brake_gap(a, b, 1.0f / b);
+    case 1: return stop_speed(a, b, 1.0f / b, c);
+    case 2: return follow_speed(a, b, c, 1.0f / c, d);
     default: return free_speed(a, b, c);
   }
 }

@@ -4,7 +4,7 @@
 // (reference envs/env.py:566-631: yellow phase, 2 x 1 s, green phase, 3 x 1 s, detector reads,
 // reward, observation) with the replica's entire vehicle state resident in shared memory:
 //
-//   HBM  (compact, lane-major, SoA 12 B/vehicle)  --coalesced loads-->  per-lane FIFO rings in smem
+//   HBM  (compact, lane-major, SoA 8 B/vehicle)   --coalesced loads-->  per-lane FIFO rings in smem
 //   5 x { A1 lane summaries + scan | A2 junction limits | B per-vehicle Krauss update |
 //         C junction transfers | D pops | E insertion }
 //   detector scan -> reward -> shaping -> observation gather -> compact store back to HBM
@@ -29,11 +29,12 @@
 #define TSC_THREADS 256
 #endif
 #ifndef TSC_MIN_BLOCKS
-#define TSC_MIN_BLOCKS 4   /* 4 CTAs/SM is the shared-memory limit for the 5x5 grid (54.8 KB each) */
+#define TSC_MIN_BLOCKS 5   /* 8-byte vehicle records: 38.7 KB of shared memory per 5x5-grid replica -> 5 CTAs/SM */
 #endif
 #define INF_SPEED 1.0e9f
 #define F_CROSS 1
 #define F_ARRIVE 2
+#define F_CLOSED 4 /* set by A2 on the lane's head flag: its stop line is closed (red / yellow-and-can-brake / yielding) */
 #define CTL_FIXED 8 /* cur_sec, seed_lo, seed_hi, n_departed, n_arrived, 3 spare */
 
 // ------------------------------------------------------------------------------------------------
@@ -73,7 +74,7 @@ struct StepArgs {
   DevNet net;
   tsc_cfg cfg;
   // state (HBM)
-  uint32_t* veh;      // [R][3][n_slots]  compact lane-major records, SoA: pos f32 | speed f32 | meta0
+  uint32_t* veh;      // [R][2][n_slots]  compact lane-major records, SoA: pos:16|speed:16 fixed point, meta0
   uint8_t* lane_cnt;  // [R][lpad]
   int32_t* ctl;       // [R][ctl_words]
   int32_t* meas;      // [R][3*n_det + n_nodes]  parity taps
@@ -102,17 +103,19 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
   return h;
 }
-__device__ __forceinline__ uint32_t rng_u32(uint32_t s0, uint32_t s1, uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t h = mix32(s0 ^ (a * 0x9E3779B1U));
-  h = mix32(h ^ s1 ^ (b * 0x85EBCA77U));
-  h = mix32(h ^ (c * 0xC2B2AE3DU));
-  return h;
+// key of one simulated second of one replica (two rounds, computed once per sub-step), then ONE round per draw
+__device__ __forceinline__ uint32_t rng_key(uint32_t s0, uint32_t s1, uint32_t a) {
+  return mix32(mix32(s0 ^ (a * 0x9E3779B1U)) ^ s1);
+}
+__device__ __forceinline__ uint32_t rng_draw(uint32_t key, uint32_t b, uint32_t c) {
+  return mix32(key ^ (b * 0x85EBCA77U + c * 0xC2B2AE3DU));
 }
 __device__ __forceinline__ float u01(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 
 // Krauss / Euler helpers (SUMO MSCFModel restated; same operation order as the oracle)
-__device__ __forceinline__ float brake_gap(float v, float b) {
-  int steps = (int)(v / b);
+// ib = 1 / b, formed once by a float division and multiplied here (same in the oracle)
+__device__ __forceinline__ float brake_gap(float v, float b, float ib) {
+  int steps = (int)(v * ib);
   float fs = (float)steps;
   float t1 = fs * v;
   float t2 = b * fs;
@@ -121,10 +124,10 @@ __device__ __forceinline__ float brake_gap(float v, float b) {
   float t5 = t4 * 0.5f;
   return t1 - t5;
 }
-__device__ __forceinline__ float stop_speed(float gap, float b, float tau) {
+__device__ __forceinline__ float stop_speed(float gap, float b, float ib, float tau) {
   float g = gap - 0.001f;
   if (g < 0.0f) return 0.0f;
-  float q = (2.0f * g) / b;
+  float q = (2.0f * g) * ib;
   q = q - tau;
   float tt = tau * tau;
   float disc = 1.0f + 4.0f * (q + tt);
@@ -139,8 +142,8 @@ __device__ __forceinline__ float stop_speed(float gap, float b, float tau) {
   float r = (g - h) / (n + tau);
   return n * b + r;
 }
-__device__ __forceinline__ float follow_speed(float gap, float v_lead, float b, float tau) {
-  return stop_speed(gap + brake_gap(v_lead, b), b, tau);
+__device__ __forceinline__ float follow_speed(float gap, float v_lead, float b, float ib, float tau) {
+  return stop_speed(gap + brake_gap(v_lead, b, ib), b, ib, tau);
 }
 __device__ __forceinline__ float free_speed(float dist, float target, float b) {
   if (dist < target) return target;
@@ -166,17 +169,23 @@ __device__ __forceinline__ float clipf(float x, float hi) {
   return x;
 }
 
-// Vehicle record = 12 bytes {pos f32, speed f32, meta0}; stored SoA both in HBM and in shared memory.
-struct Ring { float* x; float* v; uint32_t* m; uint32_t* t; };   // t: trip word (record mode only, else null)
+// Vehicle record = 8 bytes {pos:16 (1/64 m) | speed:16 (1/1024 m/s), meta0}; stored SoA both in HBM and in shared
+// memory.  Power-of-two scales: unpacking is exact; positions are truncated when packed (a vehicle that stops 1 mm
+// short of a stop line stays short of it), speeds rounded to nearest.  Same functions as in the oracle.
+struct Ring { uint32_t* xv; uint32_t* m; uint32_t* t; };   // t: trip word (record mode only, else null)
+__device__ __forceinline__ float veh_x(uint32_t xv) { return (float)(xv & 0xffffu) * 0.015625f; }
+__device__ __forceinline__ float veh_v(uint32_t xv) { return (float)(xv >> 16) * 0.0009765625f; }
+__device__ __forceinline__ uint32_t pack_xv(float x, float v) {
+  int xq = (int)(x * 64.0f), vq = (int)(v * 1024.0f + 0.5f);
+  xq = min(max(xq, 0), 65535);
+  vq = min(max(vq, 0), 65535);
+  return (uint32_t)xq | ((uint32_t)vq << 16);
+}
 #define T1_DEPART(t) ((t) & 4095u)
 #define T1_WAIT(t) (((t) >> 12) & 4095u)
 #define T1_WCNT(t) ((t) >> 24)
-__device__ __forceinline__ uint3 ld3(const Ring& r, int i) {
-  return make_uint3(__float_as_uint(r.x[i]), __float_as_uint(r.v[i]), r.m[i]);
-}
-__device__ __forceinline__ void st3(const Ring& r, int i, const uint3 e) {
-  r.x[i] = __uint_as_float(e.x); r.v[i] = __uint_as_float(e.y); r.m[i] = e.z;
-}
+__device__ __forceinline__ uint2 ld2(const Ring& r, int i) { return make_uint2(r.xv[i], r.m[i]); }
+__device__ __forceinline__ void st2(const Ring& r, int i, const uint2 e) { r.xv[i] = e.x; r.m[i] = e.y; }
 #define M0_WAIT(m) ((m) & 1023u)
 #define M0_HOP(m) (((m) >> 10) & 63u)
 #define M0_ROUTE(m) (((m) >> 16) & 255u)
@@ -295,9 +304,8 @@ tsc_step_kernel(const StepArgs A) {
 
   // ---- shared-memory carve-up ----
   Ring ring;
-  ring.x = reinterpret_cast<float*>(smem_raw);
-  ring.v = ring.x + n.n_slots;
-  ring.m = reinterpret_cast<uint32_t*>(ring.v + n.n_slots);
+  ring.xv = reinterpret_cast<uint32_t*>(smem_raw);
+  ring.m = ring.xv + n.n_slots;
   ring.t = REC ? ring.m + n.n_slots : nullptr;
   int32_t* s_cnt = reinterpret_cast<int32_t*>(ring.m + (REC ? 2 : 1) * n.n_slots);
   int32_t* s_head = s_cnt + L;
@@ -325,9 +333,8 @@ tsc_step_kernel(const StepArgs A) {
   // ---- load replica state -------------------------------------------------------------------
   const uint8_t* g_cnt = A.lane_cnt + (size_t)rep * n.lpad;
   int32_t* g_ctl = A.ctl + (size_t)rep * A.ctl_words;
-  uint32_t* g_x = A.veh + (size_t)rep * 3 * n.n_slots;
-  uint32_t* g_v = g_x + n.n_slots;
-  uint32_t* g_m = g_v + n.n_slots;
+  uint32_t* g_x = A.veh + (size_t)rep * 2 * n.n_slots;
+  uint32_t* g_m = g_x + n.n_slots;
   for (int l = tid; l < L; l += TSC_THREADS) { s_cnt[l] = g_cnt[l]; s_head[l] = 0; }
   if (tid < CTL_FIXED) s_misc[tid] = g_ctl[tid];
   for (int i = tid; i < N; i += TSC_THREADS) {
@@ -343,7 +350,7 @@ tsc_step_kernel(const StepArgs A) {
     for (int k = tid; k < V; k += TSC_THREADS) {
       int lane = find_lane(s_pre, L, k);
       int rank = k - s_pre[lane];
-      st3(ring, __ldg(&n.lane[lane].slot0) + rank, make_uint3(g_x[k], g_v[k], g_m[k]));
+      st2(ring, __ldg(&n.lane[lane].slot0) + rank, make_uint2(g_x[k], g_m[k]));
       if constexpr (REC) ring.t[__ldg(&n.lane[lane].slot0) + rank] = A.trip[(size_t)rep * n.n_slots + k];
     }
   }
@@ -354,6 +361,7 @@ tsc_step_kernel(const StepArgs A) {
   const uint32_t seed_lo = (uint32_t)s_misc[1], seed_hi = (uint32_t)s_misc[2];
   int cur_sec = s_misc[0];
   int n_dep_add = 0;  // per-thread partial (sources), reduced at the end via atomics
+  const float ib = 1.0f / c.decel;
 
   // ---- sub-steps: each is one traci.simulationStep() (envs/env.py:461-471) -------------------
   // Lane phases use BLOCKED ownership (thread tid owns lanes [tid*per, tid*per+per)), identical in every
@@ -363,20 +371,21 @@ tsc_step_kernel(const StepArgs A) {
   const int l_lo = tid * per, l_hi = min(L, l_lo + per);
   for (int sub = A.sub0; sub < A.sub0 + A.n_sub; ++sub) {
     const uint32_t t_abs = (uint32_t)cur_sec;
+    const uint32_t key = rng_key(seed_lo, seed_hi, t_abs);
     // A1: approach masks + reset of per-lane scratch (own lanes)
     for (int l = l_lo; l < l_hi; ++l) {
       s_hflag[l] = 0; s_acc[l] = 0; s_cntadd[l] = 0;
       if (s_cnt[l] > 0) {
         const LaneC lc = n.lane[l];
-        const uint3 h = ld3(ring, lc.slot0 + s_head[l]);
-        int link = __ldg(&n.route_link[M0_ROUTE(h.z) * n.max_hops + M0_HOP(h.z)]);
+        const uint2 h = ld2(ring, lc.slot0 + s_head[l]);
+        int link = __ldg(&n.route_link[M0_ROUTE(h.y) * n.max_hops + M0_HOP(h.y)]);
         if (link >= 0) {
           const LinkC* lk = &n.link[link];
           int node = __ldg(&lk->node);
           if (node >= 0) {
             uint32_t bit = 1u << __ldg(&lk->tlidx);
-            float d = lc.len - __uint_as_float(h.x);
-            if ((s_opn[node] & bit) && d <= 3.0f * __uint_as_float(h.y) + 7.5f) atomicOr(&s_appr[node], bit);
+            float d = lc.len - veh_x(h.x);
+            if ((s_opn[node] & bit) && d <= 3.0f * veh_v(h.x) + 7.5f) atomicOr(&s_appr[node], bit);
           }
         }
       }
@@ -393,18 +402,18 @@ tsc_step_kernel(const StepArgs A) {
       float lim = INF_SPEED;
       if (s_cnt[l] > 0) {
         const LaneC lc = n.lane[l];
-        const uint3 h = ld3(ring, lc.slot0 + s_head[l]);
-        const uint32_t route = M0_ROUTE(h.z), hop = M0_HOP(h.z);
+        const uint2 h = ld2(ring, lc.slot0 + s_head[l]);
+        const uint32_t route = M0_ROUTE(h.y), hop = M0_HOP(h.y);
         const int link = __ldg(&n.route_link[route * n.max_hops + hop]);
         if (link >= 0) {
           const LinkC lk = n.link[link];
-          const float hx = __uint_as_float(h.x), hv = __uint_as_float(h.y);
+          const float hx = veh_x(h.x), hv = veh_v(h.x);
           const float d = lc.len - hx;
           bool blocked = false;
-          if (lk.node >= 0 && (int)M0_WAIT(h.z) < c.teleport_sec) {
+          if (lk.node >= 0 && (int)M0_WAIT(h.y) < c.teleport_sec) {
             const uint32_t bit = 1u << lk.tlidx;
             if (s_yel[lk.node] & bit) {
-              blocked = brake_gap(hv, c.decel) <= d;
+              blocked = brake_gap(hv, c.decel, ib) <= d;
             } else if (!(s_opn[lk.node] & bit)) {
               blocked = true;
             } else {
@@ -414,7 +423,8 @@ tsc_step_kernel(const StepArgs A) {
             }
           }
           if (blocked) {
-            lim = stop_speed(d, c.decel, c.tau);
+            lim = stop_speed(d, c.decel, ib, c.tau);
+            s_hflag[l] = F_CLOSED;        // own lane; read by the lane's rank-0 vehicle thread in B after the barrier
           } else {
             if (lk.vmax < 1.0e8f) lim = free_speed(d, lk.vmax, c.decel);
             const int nl = __ldg(&n.route_lane[route * n.max_hops + hop + 1]);
@@ -423,10 +433,10 @@ tsc_step_kernel(const StepArgs A) {
               const LaneC nlc = n.lane[nl];
               int idx = s_head[nl] + nc - 1;
               if (idx >= nlc.cap) idx -= nlc.cap;
-              const uint3 t = ld3(ring, nlc.slot0 + idx);
-              float gap = d + (__uint_as_float(t.x) - c.veh_len);
+              const uint32_t txv = ring.xv[nlc.slot0 + idx];
+              float gap = d + (veh_x(txv) - c.veh_len);
               gap = gap - c.min_gap;
-              float fs = follow_speed(gap, __uint_as_float(t.y), c.decel, c.tau);
+              float fs = follow_speed(gap, veh_v(txv), c.decel, ib, c.tau);
               if (fs < lim) lim = fs;
             }
           }
@@ -444,7 +454,7 @@ tsc_step_kernel(const StepArgs A) {
         const int k = it * TSC_THREADS + tid;
         const bool act = k < V;
         int slot = 0, lane = 0, rank = 0;
-        uint3 me = make_uint3(0, 0, 0);
+        uint2 me = make_uint2(0, 0);
         uint8_t f = 0;
         {   // lane of compact index k: warp-cooperative search over the 32 lane boundaries that follow the lane of
             // the warp's first vehicle (33 possible outcomes -> 6 halvings); falls back to the block-wide search
@@ -467,9 +477,9 @@ tsc_step_kernel(const StepArgs A) {
           int idx = s_head[lane] + rank;
           if (idx >= lc.cap) idx -= lc.cap;
           slot = lc.slot0 + idx;
-          me = ld3(ring, slot);
-          const float x = __uint_as_float(me.x), v = __uint_as_float(me.y);
-          const float sf = 0.5f + (float)M0_SFQ(me.z) * (1.0f / 256.0f);
+          me = ld2(ring, slot);
+          const float x = veh_x(me.x), v = veh_v(me.x);
+          const float sf = 0.5f + (float)M0_SFQ(me.y) * (1.0f / 256.0f);
           const float vmax = lc.vmax * sf;
           float vfree = v + c.accel;
           if (vmax < vfree) vfree = vmax;
@@ -479,24 +489,26 @@ tsc_step_kernel(const StepArgs A) {
           } else {
             int lidx = idx - 1;
             if (lidx < 0) lidx += lc.cap;
-            const float2 ld = make_float2(ring.x[lc.slot0 + lidx], ring.v[lc.slot0 + lidx]);
-            float gap = ld.x - c.veh_len;
+            const uint32_t lxv = ring.xv[lc.slot0 + lidx];
+            float gap = veh_x(lxv) - c.veh_len;
             gap = gap - x;
             gap = gap - c.min_gap;
-            vsafe = follow_speed(gap, ld.y, c.decel, c.tau);
+            vsafe = follow_speed(gap, veh_v(lxv), c.decel, ib, c.tau);
           }
           const float vnm = vfree < vsafe ? vfree : vsafe;
           float vmin = v - c.decel;
           if (vmin < 0.0f) vmin = 0.0f;
           if (vnm < vmin) vmin = vnm;
-          const float u = u01(rng_u32(seed_lo, seed_hi, t_abs, (uint32_t)lane, (uint32_t)rank));
+          const float u = u01(rng_draw(key, (uint32_t)lane, (uint32_t)rank));
           const float basev = vnm < c.accel ? vnm : c.accel;
           const float vd = vnm - (c.sigma * basev) * u;
           float vn = vd > vmin ? vd : vmin;
           float xn = x + vn;
           if (xn >= lc.len) {
-            if (rank == 0) {
-              int link = __ldg(&n.route_link[M0_ROUTE(me.z) * n.max_hops + M0_HOP(me.z)]);
+            // a head vehicle whose stop line is closed never passes it (tau < 1 s makes the Euler stop speed
+            // overshoot: SUMO's "emergency stop at the end of the lane"); followers: one discharge per lane and second
+            if (rank == 0 && s_hflag[lane] != F_CLOSED) {
+              int link = __ldg(&n.route_link[M0_ROUTE(me.y) * n.max_hops + M0_HOP(me.y)]);
               f = link < 0 ? F_ARRIVE : F_CROSS;
             } else {
               xn = lc.len - 0.01f;
@@ -504,7 +516,7 @@ tsc_step_kernel(const StepArgs A) {
               if (vn < 0.0f) { vn = 0.0f; xn = x; }
             }
           }
-          uint32_t w = M0_WAIT(me.z);
+          uint32_t w = M0_WAIT(me.y);
           if constexpr (REC) {      // tripinfo waitingTime / waitingCount (envs/env.py:498-515)
             if (vn < 0.1f) {
               uint32_t t1 = ring.t[slot];
@@ -519,13 +531,12 @@ tsc_step_kernel(const StepArgs A) {
           } else {
             w = 0;
           }
-          me.x = __float_as_uint(xn);
-          me.y = __float_as_uint(vn);
-          me.z = (me.z & ~1023u) | w;
+          me.x = pack_xv(xn, vn);       // waiting was decided on the computed speed; the record stores it rounded
+          me.y = (me.y & ~1023u) | w;
         }
         __syncthreads();
         if (act) {
-          st3(ring, slot, me);
+          st2(ring, slot, me);
           if (rank == 0) s_hflag[lane] = f;
         }
       }
@@ -543,19 +554,19 @@ tsc_step_kernel(const StepArgs A) {
       if (have_tail) {
         int idx = s_head[t] + cur - 1;
         if (idx >= tc.cap) idx -= tc.cap;
-        tail_x = ring.x[tc.slot0 + idx];
+        tail_x = veh_x(ring.xv[tc.slot0 + idx]);
       }
       for (int q = q0; q < q1; ++q) {
         const int link = __ldg(&n.lane_inl[q]);
         const int src = __ldg(&n.link[link].from);
         if (s_cnt[src] == 0 || s_hflag[src] != F_CROSS) continue;
         const LaneC sc2 = n.lane[src];
-        const uint3 h = ld3(ring, sc2.slot0 + s_head[src]);
-        const uint32_t route = M0_ROUTE(h.z), hop = M0_HOP(h.z);
+        const uint2 h = ld2(ring, sc2.slot0 + s_head[src]);
+        const uint32_t route = M0_ROUTE(h.y), hop = M0_HOP(h.y);
         if (__ldg(&n.route_link[route * n.max_hops + hop]) != link) continue;
         if (__ldg(&n.route_lane[route * n.max_hops + hop + 1]) != t) continue;
         if (cur >= tc.cap) continue;
-        float x = __uint_as_float(h.x) - sc2.len;
+        float x = veh_x(h.x) - sc2.len;
         if (have_tail) {
           float lim = tail_x - c.veh_len;
           lim = lim - c.min_gap;
@@ -564,12 +575,12 @@ tsc_step_kernel(const StepArgs A) {
         if (x < 0.0f) continue;
         int idx = s_head[t] + cur;
         if (idx >= tc.cap) idx -= tc.cap;
-        uint3 e = h;
-        e.x = __float_as_uint(x);
-        e.z = (h.z & ~(63u << 10)) | ((hop + 1) << 10);
-        st3(ring, tc.slot0 + idx, e);
+        uint2 e;
+        e.x = pack_xv(x, veh_v(h.x));
+        e.y = (h.y & ~(63u << 10)) | ((hop + 1) << 10);
+        st2(ring, tc.slot0 + idx, e);
         if constexpr (REC) ring.t[tc.slot0 + idx] = ring.t[sc2.slot0 + s_head[src]];
-        cur++; tail_x = x; have_tail = true;
+        cur++; tail_x = veh_x(e.x); have_tail = true;   // the next source sees the stored (truncated) position
         s_acc[src] = 1;
       }
       s_cntadd[t] = cur - s_cnt[t];
@@ -605,8 +616,7 @@ tsc_step_kernel(const StepArgs A) {
         else if (f == F_CROSS) {
           if (s_acc[l]) pop = true;
           else {
-            ring.x[lc.slot0 + s_head[l]] = lc.len - 0.01f;
-            ring.v[lc.slot0 + s_head[l]] = 0.0f;
+            ring.xv[lc.slot0 + s_head[l]] = pack_xv(lc.len - 0.01f, 0.0f);
           }
         }
         if (pop) {
@@ -631,7 +641,7 @@ tsc_step_kernel(const StepArgs A) {
             int due = in_h ? (int)__ldg(&n.src_due[t_abs * n.n_src + q2]) : 0;
             const int gq = __ldg(&n.src_group[q2]);
             if (gq >= 0 && due > 0) {
-              const float ug = u01(rng_u32(seed_lo, seed_hi, t_abs, 0x20000u + (uint32_t)gq, 7u));
+              const float ug = u01(rng_draw(key, 0x20000u + (uint32_t)gq, 7u));
               int iv = (int)t_abs / n.pint_sec;
               if (iv >= n.n_pint) iv = n.n_pint - 1;
               if (!(ug >= __ldg(&n.src_plo[iv * n.n_src + q2]) && ug < __ldg(&n.src_phi[iv * n.n_src + q2]))) due = 0;
@@ -652,26 +662,25 @@ tsc_step_kernel(const StepArgs A) {
             if (ok && cl > 0) {
               int idx = s_head[l] + cl - 1;
               if (idx >= lc.cap) idx -= lc.cap;
-              free_back = ring.x[lc.slot0 + idx] - c.veh_len;
+              free_back = veh_x(ring.xv[lc.slot0 + idx]) - c.veh_len;
               free_back = free_back - c.min_gap;
             }
             if (ok && !(free_back < c.veh_len)) {
               const uint32_t qq = (uint32_t)q;
-              const float u = u01(rng_u32(seed_lo, seed_hi, t_abs, qq, (1u << 16)));
+              const float u = u01(rng_draw(key, qq, (1u << 16)));
               const float pos = c.veh_len + u * (free_back - c.veh_len);
               float su = 0.0f;
-              for (uint32_t j = 1; j <= 4; ++j) su = su + u01(rng_u32(seed_lo, seed_hi, t_abs, qq, (1u << 16) | j));
+              for (uint32_t j = 1; j <= 4; ++j) su = su + u01(rng_draw(key, qq, (1u << 16) | j));
               const float sfr = 1.0f + (c.speed_dev * 1.7320508f) * (su - 2.0f);
               int sfq = (int)((sfr - 0.5f) * 256.0f);
               if (sfq < 0) sfq = 0;
               if (sfq > 255) sfq = 255;
               int idx = s_head[l] + cl;
               if (idx >= lc.cap) idx -= lc.cap;
-              uint3 e;
-              e.x = __float_as_uint(pos);
-              e.y = __float_as_uint(0.0f);
-              e.z = ((uint32_t)__ldg(&n.src_route[q]) << 16) | ((uint32_t)sfq << 24);
-              st3(ring, lc.slot0 + idx, e);
+              uint2 e;
+              e.x = pack_xv(pos, 0.0f);
+              e.y = ((uint32_t)__ldg(&n.src_route[q]) << 16) | ((uint32_t)sfq << 24);
+              st2(ring, lc.slot0 + idx, e);
               if constexpr (REC) ring.t[lc.slot0 + idx] = (uint32_t)t_abs & 4095u;      // depart second
               cl++;
               b_new--;
@@ -696,12 +705,12 @@ tsc_step_kernel(const StepArgs A) {
     const int cl = s_cnt[l];
     int idx = s_head[l];
     for (int k = 0; k < cl; ++k) {
-      const uint3 v = ld3(ring, lc.slot0 + idx);
-      const float x = __uint_as_float(v.x);
+      const uint2 v = ld2(ring, lc.slot0 + idx);
+      const float x = veh_x(v.x);
       if (c.det_len > 0.0f && !(x > lc.len - c.det_len)) break;
       veh++;
-      if (__uint_as_float(v.y) < c.halt_speed) halt++;
-      if (k == 0 && x > 0.0f) wait = (int)M0_WAIT(v.z);
+      if (veh_v(v.x) < c.halt_speed) halt++;
+      if (k == 0 && x > 0.0f) wait = (int)M0_WAIT(v.y);
       if (++idx >= lc.cap) idx = 0;
     }
     s_det[d] = veh; s_det[n.n_det + d] = halt; s_det[2 * n.n_det + d] = wait;
@@ -779,8 +788,8 @@ tsc_step_kernel(const StepArgs A) {
       const LaneC lc = n.lane[lane];
       int idx = s_head[lane] + rank;
       if (idx >= lc.cap) idx -= lc.cap;
-      const uint3 e = ld3(ring, lc.slot0 + idx);
-      g_x[k] = e.x; g_v[k] = e.y; g_m[k] = e.z;
+      const uint2 e = ld2(ring, lc.slot0 + idx);
+      g_x[k] = e.x; g_m[k] = e.y;
       if constexpr (REC) A.trip[(size_t)rep * n.n_slots + k] = ring.t[lc.slot0 + idx];
     }
   }
@@ -838,8 +847,8 @@ __global__ void tsc_stats_kernel(const DevNet n, const uint32_t* __restrict__ ve
   const int V = s_pre[L];
   float w = 0.f, sp = 0.f;
   for (int k = tid; k < V; k += blockDim.x) {
-    const float vy = __uint_as_float(veh[((size_t)rep * 3 + 1) * n.n_slots + k]);
-    w += (float)(veh[((size_t)rep * 3 + 2) * n.n_slots + k] & 1023u);
+    const float vy = veh_v(veh[((size_t)rep * 2 + 0) * n.n_slots + k]);
+    w += (float)(veh[((size_t)rep * 2 + 1) * n.n_slots + k] & 1023u);
     sp += vy;
     if (vy < 0.1f) {
       int lo = 0, hi = L;
@@ -930,8 +939,13 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   if (net->n_nodes > TSC_THREADS - 1) return fail("tsc_create: too many nodes");
   if (net->n_src > TSC_THREADS) return fail("tsc_create: too many demand sources");
   if (net->max_hops > 63 || net->n_routes > 255) return fail("tsc_create: route table too large");
-  for (int l = 0; l < net->n_lanes; ++l)
+  for (int l = 0; l < net->n_lanes; ++l) {
     if (net->lane_cap[l] > 255) return fail("tsc_create: lane capacity > 255");
+    // fixed-point vehicle records: 16-bit position in 1/64 m (a crossing vehicle may overshoot by one step's travel),
+    // 16-bit speed in 1/1024 m/s; speedFactor <= 1.5
+    if (net->lane_len[l] + 64.0f > 1023.0f) return fail("tsc_create: lane longer than 959 m (16-bit position field)");
+    if (net->lane_vmax[l] * 1.5f > 63.9f) return fail("tsc_create: lane speed limit above 42 m/s (16-bit speed field)");
+  }
   CK(cudaSetDevice(device));
   tsc_handle* h = new tsc_handle();
   h->device = device; h->R = R;
@@ -991,7 +1005,7 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   h->args.ctl_words = (CTL_FIXED + N + net->n_src + 3) & ~3;
   h->meas_words = 3 * net->n_det + N;
   h->n_nodes = N; h->n_obs = net->n_obs; h->max_na = net->max_na; h->n_det = net->n_det;
-  rc |= dalloc(h, (size_t)R * 3 * net->n_slots, &h->args.veh);
+  rc |= dalloc(h, (size_t)R * 2 * net->n_slots, &h->args.veh);
   rc |= dalloc(h, (size_t)R * d.lpad, &h->args.lane_cnt);
   rc |= dalloc(h, (size_t)R * h->args.ctl_words, &h->args.ctl);
   rc |= dalloc(h, (size_t)R * h->meas_words, &h->args.meas);
@@ -1005,7 +1019,7 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   if (rc) { tsc_destroy(h); return -1; }
   h->args.train_mode = 1;
   // shared memory: must mirror the carve-up in the kernel
-  size_t sm = (size_t)net->n_slots * 12;
+  size_t sm = (size_t)net->n_slots * 8;
   sm += (size_t)L * 4 * 2 + ((size_t)L + 1) * 4 + (size_t)L * 4 * 2 + (size_t)L * 2;
   sm = (sm + 3) & ~(size_t)3;
   sm += (size_t)N * 4 * 6 + (size_t)net->n_src * 4 + (size_t)net->n_det * 12 + (size_t)N * 4 + (8 + TSC_THREADS / 32) * 4 +
@@ -1216,13 +1230,18 @@ extern "C" int tsc_dump_state(tsc_handle* h, int32_t replica, int32_t* lane_cnt_
   CK(cudaMemcpy(cnt.data(), h->args.lane_cnt + (size_t)replica * d.lpad, d.lpad, cudaMemcpyDeviceToHost));
   int V = 0;
   for (int l = 0; l < d.n_lanes; ++l) { lane_cnt_host[l] = cnt[l]; V += cnt[l]; }
-  if (V) {   // SoA on the device -> canonical [V][3] records on the host
-    std::vector<uint32_t> tmp((size_t)3 * V);
-    for (int a = 0; a < 3; ++a)
-      CK(cudaMemcpy(tmp.data() + (size_t)a * V, h->args.veh + ((size_t)replica * 3 + a) * d.n_slots, (size_t)V * 4,
+  if (V) {   // packed SoA on the device -> canonical [V][3] records {pos f32, speed f32, meta0} on the host
+    std::vector<uint32_t> tmp((size_t)2 * V);
+    for (int a = 0; a < 2; ++a)
+      CK(cudaMemcpy(tmp.data() + (size_t)a * V, h->args.veh + ((size_t)replica * 2 + a) * d.n_slots, (size_t)V * 4,
                     cudaMemcpyDeviceToHost));
-    for (int k = 0; k < V; ++k)
-      for (int a = 0; a < 3; ++a) veh_host[(size_t)k * 3 + a] = tmp[(size_t)a * V + k];
+    for (int k = 0; k < V; ++k) {
+      const uint32_t xv = tmp[k];
+      const float fx = (float)(xv & 0xffffu) * 0.015625f, fv = (float)(xv >> 16) * 0.0009765625f;
+      memcpy(&veh_host[(size_t)k * 3 + 0], &fx, 4);
+      memcpy(&veh_host[(size_t)k * 3 + 1], &fv, 4);
+      veh_host[(size_t)k * 3 + 2] = tmp[(size_t)V + k];
+    }
   }
   *n_veh = V;
   return 0;
@@ -1232,7 +1251,7 @@ extern "C" int tsc_info(tsc_handle* h, int64_t* state_bytes_per_replica, int32_t
   if (!h) return fail("tsc_info: null handle");
   const DevNet& d = h->args.net;
   if (state_bytes_per_replica)
-    *state_bytes_per_replica = (int64_t)d.n_slots * 12 + d.lpad + (int64_t)h->args.ctl_words * 4 + (int64_t)h->meas_words * 4;
+    *state_bytes_per_replica = (int64_t)d.n_slots * 8 + d.lpad + (int64_t)h->args.ctl_words * 4 + (int64_t)h->meas_words * 4;
   if (threads_per_block) *threads_per_block = TSC_THREADS;
   if (smem_bytes) *smem_bytes = h->smem;
   return 0;

@@ -214,6 +214,9 @@ class NetTables:
             setattr(self, name, arr)
         assert self.link_tlidx.max(initial=0) < 32
         assert self.n_lanes < 32767 and self.n_links < 32767
+        # vehicle positions are 16-bit fixed point in 1/64 m (include/tsc.h "vehicle record"): lane ends must lie on that
+        # grid, so that "crossed the end of the lane" means the same for the computed and for the stored position
+        self.lane_len = (np.round(self.lane_len.astype(np.float64) * 64.0) / 64.0).astype(np.float32)
         return self
 
     def as_c(self) -> CNet:

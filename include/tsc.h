@@ -197,7 +197,11 @@ int tsc_get_traffic_stats(tsc_handle* h, float* stats_dev, void* stream);
 /* Debug / parity: copy replica r's full vehicle state to the host in canonical form:
  * lane_cnt_host int32[n_lanes], veh_host uint32[3*n_slots] (lane-major, front vehicle first,
  * 12-byte records {pos f32, speed f32, meta0 = wait:10|hop:6|route:8|speedFactor:8}); *n_veh = vehicles written.
- * Synchronous. */
+ * Synchronous.
+ * "vehicle record": on the device (HBM and shared memory) a vehicle is 8 bytes — word 0 = position:16 (1/64 m) |
+ * speed:16 (1/1024 m/s), word 1 = meta0.  Both scales are powers of two, so this dump is the exact stored state;
+ * positions are truncated and speeds rounded when a record is written (once per simulated second).  Limits checked by
+ * tsc_create: lanes <= 959 m, speed limits <= 42 m/s. */
 int tsc_dump_state(tsc_handle* h, int32_t replica, int32_t* lane_cnt_host, uint32_t* veh_host,
                    int32_t* n_veh);
 

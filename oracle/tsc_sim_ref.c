@@ -201,7 +201,7 @@ static void node_signal(const ref_sim* s, const replica_t* r, int yellow_phase, 
 
 /* one simulated second of one replica == traci.simulationStep(), envs/env.py:464 */
 static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, float* xnew,
-                    uint8_t* flag, float* head_lim, uint32_t* approach, uint32_t* open,
+                    uint8_t* flag, uint8_t* hblk, float* head_lim, uint32_t* approach, uint32_t* open,
                     uint32_t* major, uint32_t* ymask, uint8_t* accepted, int32_t* cnt_add) {
   const tsc_net* n = &s->net;
   const tsc_cfg* c = &s->cfg;
@@ -227,6 +227,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
   /* A2: speed limit of each lane's head vehicle from the junction ahead */
   for (int l = 0; l < L; ++l) {
     head_lim[l] = INF_SPEED;
+    hblk[l] = 0;
     if (r->cnt[l] == 0) continue;
     veh_t* h = veh_at(n, r, l, 0);
     uint32_t route = M0_ROUTE(h->m0), hop = M0_HOP(h->m0);
@@ -247,7 +248,7 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
         if (approach[node] & foes) blocked = 1;
       }
     }
-    if (blocked) { head_lim[l] = stop_speed(d, c->decel, ib, c->tau); continue; }
+    if (blocked) { head_lim[l] = stop_speed(d, c->decel, ib, c->tau); hblk[l] = 1; continue; }
     float lim = INF_SPEED;
     float lv = n->link_vmax[link];
     if (lv < 1.0e8f) lim = free_speed(d, lv, c->decel);
@@ -295,10 +296,12 @@ static void substep(ref_sim* s, replica_t* r, int yellow_phase, float* vnew, flo
       float xn = vx + vn;
       uint8_t f = 0;
       if (xn >= Ll) {
-        if (k == 0) {
+        if (k == 0 && !hblk[l]) {
           int link = n->route_link[M0_ROUTE(v->m0) * n->max_hops + M0_HOP(v->m0)];
           f = link < 0 ? F_ARRIVE : F_CROSS;
-        } else { /* a lane discharges at most one vehicle per second */
+        } else { /* a lane discharges at most one vehicle per second; a head vehicle whose stop line is closed never
+                  * passes it (tau < 1 s makes the Euler stop speed overshoot: SUMO's "emergency stop at the end of
+                  * the lane") */
           xn = Ll - 0.01f;
           vn = xn - vx;
           if (vn < 0.0f) { vn = 0.0f; xn = vx; }
@@ -644,6 +647,7 @@ static void* step_range(void* arg) {
   float* vnew = (float*)malloc(4 * (size_t)n->n_slots);
   float* xnew = (float*)malloc(4 * (size_t)n->n_slots);
   uint8_t* flag = (uint8_t*)calloc((size_t)n->n_slots, 1);
+  uint8_t* hblk = (uint8_t*)calloc((size_t)n->n_lanes, 1);
   float* head_lim = (float*)malloc(4 * (size_t)n->n_lanes);
   uint32_t* approach = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
   uint32_t* open = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
@@ -655,7 +659,7 @@ static void* step_range(void* arg) {
     replica_t* r = &s->rep[i];
     for (int k = 0; k < n->n_nodes; ++k) r->cur_action[k] = j->action[(size_t)i * n->n_nodes + k];
     for (int t = 0; t < c->control_interval_sec; ++t)
-      substep(s, r, t < c->yellow_interval_sec, vnew, xnew, flag, head_lim, approach, open, major,
+      substep(s, r, t < c->yellow_interval_sec, vnew, xnew, flag, hblk, head_lim, approach, open, major,
               ymask, accepted, cnt_add);
     /* node.prev_action = action (set in the 'yellow' call, envs/env.py:134) */
     for (int k = 0; k < n->n_nodes; ++k) r->prev_action[k] = r->cur_action[k];
@@ -665,7 +669,7 @@ static void* step_range(void* arg) {
             j->reward ? j->reward + (size_t)i * n->n_nodes : 0,
             j->greward ? j->greward + i : 0, j->done ? j->done + i : 0);
   }
-  free(vnew); free(xnew); free(flag); free(head_lim); free(approach); free(open); free(major);
+  free(vnew); free(xnew); free(flag); free(hblk); free(head_lim); free(approach); free(open); free(major);
   free(ymask); free(accepted); free(cnt_add);
   return 0;
 }
@@ -786,6 +790,7 @@ void ref_step_record(ref_sim* s, const int32_t* action, const float* fp, float* 
   float* vnew = (float*)malloc(4 * (size_t)n->n_slots);
   float* xnew = (float*)malloc(4 * (size_t)n->n_slots);
   uint8_t* flag = (uint8_t*)calloc((size_t)n->n_slots, 1);
+  uint8_t* hblk = (uint8_t*)calloc((size_t)n->n_lanes, 1);
   float* head_lim = (float*)malloc(4 * (size_t)n->n_lanes);
   uint32_t* approach = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
   uint32_t* open = (uint32_t*)malloc(4 * (size_t)n->n_nodes);
@@ -799,7 +804,7 @@ void ref_step_record(ref_sim* s, const int32_t* action, const float* fp, float* 
     for (int k = 0; k < n->n_nodes; ++k) s->rep[i].cur_action[k] = action[(size_t)i * n->n_nodes + k];
   for (int t = 0; t < ci; ++t) {
     for (int i = 0; i < s->R; ++i)
-      substep(s, &s->rep[i], t < c->yellow_interval_sec, vnew, xnew, flag, head_lim, approach, open, major, ymask,
+      substep(s, &s->rep[i], t < c->yellow_interval_sec, vnew, xnew, flag, hblk, head_lim, approach, open, major, ymask,
               accepted, cnt_add);
     if (sub_stats) {
       ref_traffic_stats(s, st);
@@ -813,7 +818,7 @@ void ref_step_record(ref_sim* s, const int32_t* action, const float* fp, float* 
     outputs(s, r, fp ? fp + (size_t)i * n->n_nodes * n->max_na : 0, obs ? obs + (size_t)i * n->n_obs : 0,
             reward ? reward + (size_t)i * n->n_nodes : 0, greward ? greward + i : 0, done ? done + i : 0);
   }
-  free(vnew); free(xnew); free(flag); free(head_lim); free(approach); free(open); free(major);
+  free(vnew); free(xnew); free(flag); free(hblk); free(head_lim); free(approach); free(open); free(major);
   free(ymask); free(accepted); free(cnt_add); free(st);
 }
 

@@ -86,21 +86,25 @@ def test_real_net_greedy_controller_matches_reference():
         assert list(ctrl.forward(ob)) == list(z["greedy"][t])
 
 
-def test_recorded_ma2c_plans_reproduce_sumo_aggregates_at_paper_tau():
-    """Distribution-level check of the restated dynamics against SUMO: replay the signal plans the reference RECORDED for
-    its trained MA2C agent on Monaco (real_net_experimental_data/eva_data, 10 evaluation episodes; fixture cut by
-    tests/golden/replay_monaco_eval_traces.py) through the oracle, open loop.  The recordings date from the paper's vType
-    (tau = 0.5, reference README.md:63); with that tau the simulator reproduces what SUMO produced under the same plans,
-    averaged over the 10 episodes: trips completed and vehicles departed within 5 %, mean trip duration and mean speed
-    within 15 %, peak population within 20 %.  (With the current default tau = 1.0 the same demand exceeds the network's
-    capacity: DESIGN.md §2.)"""
+def test_recorded_ma2c_plans_replay_quantifies_the_gap_to_sumo():
+    """Distribution-level comparison of the restated dynamics with SUMO, at the vType that SHIPS (tau = 1.0, nothing
+    overridden): replay the signal plans the reference RECORDED for its trained MA2C agent on Monaco
+    (real_net_experimental_data/eva_data, 10 evaluation episodes; fixture cut by tests/golden/replay_monaco_eval_traces.py)
+    through the oracle, open loop, and compare with what SUMO produced under the same plans.
+
+    This is a CHARACTERISATION of a known gap, not a parity claim: the recordings were made with the
+    paper-era vType (tau = 0.5 on SUMO 0.32, reference README.md:63); with a 1-s Euler step the Krauss stop speed
+    overshoots for tau < 1 s (SUMO then makes "emergency stops" at the lane end, and the reference removed tau = 0.5
+    because of collisions), so that regime cannot be restated faithfully, and at tau = 1.0 the recorded plans meet 30-40 %
+    less junction capacity than they were made for: the network spills back.  The bounds below pin the size of that gap
+    (and the demand side, which must agree): a change of the model that moves them is a change of fidelity."""
     from deeprl_signal_control_b200.net.real_net import real_net_tables
     from oracle.sim_ref import RefSim
     z = np.load(os.path.join(GOLD, "monaco_ma2c_recorded_traces.npz"))
     want = json.loads(str(z["recorded"]))
     acts = z["actions"].astype(np.int32)                         # [episodes, 720, 28]
     net, par = real_net_tables("greedy"), real_params("greedy")
-    par.tau = 0.5
+    assert par.tau == 1.0
     R = acts.shape[0]
     sim = RefSim(net, par, R)
     sim.reset(np.arange(R, dtype=np.uint64) + np.uint64(10000))
@@ -113,9 +117,11 @@ def test_recorded_ma2c_plans_reproduce_sumo_aggregates_at_paper_tau():
         speed.append(st[..., 4].mean())
     trips = np.concatenate([sim.trips(r) for r in range(R)])
     departed = np.mean([sim.misc(r)["departed"] for r in range(R)])
-    rel = lambda got, key: abs(got - want[key]) / want[key]
-    assert rel(len(trips) / R, "trips_per_episode") < 0.05
-    assert rel(departed, "departed_per_episode") < 0.05
-    assert rel(float((trips[:, 1] - trips[:, 0]).mean()), "mean_trip_duration_sec") < 0.15
-    assert rel(float(np.mean(speed)), "avg_speed_mps") < 0.15
-    assert rel(float(peak.mean()), "peak_cars") < 0.20
+    backlog = np.mean([sim.misc(r)["backlog"] for r in range(R)])
+    ratio = lambda got, key: got / want[key]
+    # demand side: everything the flows generate is either in the network, arrived, or waiting to be inserted
+    assert abs((departed + backlog) - 2464.0) < 1.0 and want["departed_per_episode"] <= 2464.0
+    # supply side: the documented deficit (SUMO completed 2397 trips per episode under these plans)
+    assert 0.35 < ratio(len(trips) / R, "trips_per_episode") < 0.60
+    assert 0.30 < ratio(float(np.mean(speed)), "avg_speed_mps") < 0.60
+    assert 1.8 < ratio(float(peak.mean()), "peak_cars") < 3.2

@@ -113,10 +113,10 @@ def _mix32(h):
 
 
 def _rng_u32(s0, s1, a, b, c):
-    """Python mirror of rng_u32() (oracle/tsc_sim_ref.c, csrc/tsc_sim.cu)."""
-    h = _mix32(s0 ^ ((a * 0x9E3779B1) & 0xffffffff))
-    h = _mix32(h ^ s1 ^ ((b * 0x85EBCA77) & 0xffffffff))
-    return _mix32(h ^ ((c * 0xC2B2AE3D) & 0xffffffff))
+    """Python mirror of rng_draw(rng_key(s0, s1, a), b, c) (oracle/tsc_sim_ref.c, csrc/tsc_sim.cu): two rounds for the
+    key of (replica seed, second), one round per draw."""
+    key = _mix32(_mix32(s0 ^ ((a * 0x9E3779B1) & 0xffffffff)) ^ s1)
+    return _mix32(key ^ ((b * 0x85EBCA77 + c * 0xC2B2AE3D) & 0xffffffff))
 
 
 def test_stochastic_demand_accounting_is_exact():

@@ -251,6 +251,8 @@ def main():
         return
 
     # ---------------- our arm -----------------------------------------------------------------
+    from deeprl_signal_control_b200.dist import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local_rank)      # before torch allocates anything page-locked
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -477,7 +479,9 @@ def main():
                        if mode == "train" else None,
                        "l2": "inputs larger than L2: %.0f MB of replica state per GPU is streamed every step"
                              % (R * sim.info()["state_bytes_per_replica"] / 1e6),
-                       "parallelism": "replica-dp%d" % world},
+                       "parallelism": "replica-dp%d" % world,
+                       "host_binding": ("rank bound to the %d host cores of its GPU's NUMA node" % len(numa_cpus))
+                       if numa_cpus else "none (NVML affinity unavailable)"},
             "clocks": sampler.summary(),
             "value_steady": value_steady,
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": h2d,

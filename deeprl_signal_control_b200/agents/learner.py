@@ -97,6 +97,11 @@ class BatchedA2C:
         self.Wp = torch.zeros(U, ((L.dx + L.h) // 8) * 4 * L.h * 8 + 8 * L.dx * 8, dtype=torch.bfloat16,
                               device=self.dev)
         self.Wt = torch.zeros(U, 32, L.h, 8, dtype=torch.bfloat16, device=self.dev)    # Wh^T image for the BPTT MMA
+        self.Wxt = torch.zeros(U, 32, L.dx, 8, dtype=torch.bfloat16, device=self.dev)  # Wx^T image: dX fused into the BPTT
+        # measured (R = 8192, 1 x B200): fusing dX into the BPTT step lengthens the serial per-step chain (update 72.5 ->
+        # 92.5 ms), so the default keeps dX as a separate product; `dx_fused = True` selects the fused kernel (tested)
+        self.dx_fused = False
+        self.dx_fusable = self.use_tc and L.dx % 32 == 0 and L.dx <= 256
         self.bwd_tc = self.use_tc
         self.fc_bwd_tc = self.use_tc and layout.fc_bwd_tc_ok     # front-end weight gradients on the tensor cores
         self.wgrad_tc = self.use_tc and L.dx % 8 == 0 and L.dx <= 240   # LSTM weight gradients on the tensor cores
@@ -135,7 +140,9 @@ class BatchedA2C:
         if self.use_tc:
             _lib.check(_lib.lib().tscl_pack_weights(self._h, _p(self.P), _p(self.Wp), self._st()))
             _lib.check(_lib.lib().tscl_pack_wht(self._h, _p(self.P), _p(self.Wt), self._st()))
-            self.wx_b = self.pv["wx"].to(torch.bfloat16)       # operand of the bf16 library GEMM dX = dZ . Wx^T
+            if self.dx_fusable:
+                _lib.check(_lib.lib().tscl_pack_wxt(self._h, _p(self.P), _p(self.Wxt), self._st()))
+            self.wx_b = self.pv["wx"].to(torch.bfloat16)       # operand of the separate product dX = dZ . Wx^T
             self.kernel_launches += 3
 
     def _mm(self):
@@ -346,11 +353,13 @@ class BatchedA2C:
                 # head weight / bias gradients (plain batched GEMM + column sums)
                 self.gv["wo"].baddbmm_(H.transpose(1, 2), dlog)
                 self.gv["bo"].add_(dlog.sum(dim=1))
+            fuse_dx = all_tc and self.dx_fused and self.dx_fusable   # dX = dZ . Wx^T inside the BPTT kernel (second MMA per step)
             if self.bwd_tc:
                 gb = (_p(self.st_g[ci]), _p(self.st_c[ci])) if use_store else (None, None)
-                _lib.check(lib.tscl_lstm_seq_bwd_tc(self._h, _p(self.Wt), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
-                                                    C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), *gb,
-                                                    _p(dZb), st()))
+                _lib.check(lib.tscl_lstm_seq_bwd_tc_dx(self._h, _p(self.Wt), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw),
+                                                       _p(dpre), C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0),
+                                                       *gb, _p(dZb), _p(self.Wxt) if fuse_dx else None,
+                                                       _p(dXb) if fuse_dx else None, st()))
             else:
                 _lib.check(lib.tscl_lstm_seq_bwd(self._h, _p(self.P), _p(ZG), _p(Cc), _p(dH), _p(self.c_bw), _p(dpre),
                                                  C.c_int32(T), C.c_int64(rc), C.c_int64(R), C.c_int64(r0), st()))
@@ -367,10 +376,11 @@ class BatchedA2C:
                 self.gv["wx"].baddbmm_(X.transpose(1, 2), dZ)
                 self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)
                 self.gv["bl"].add_(dZ.sum(dim=1))
-            # dX = dZ . Wx^T: plain library GEMM (bf16 operands when dZ travels as bf16, else fp32 / TF32)
-            if all_tc:
+            # dX = dZ . Wx^T: fused into the BPTT kernel on the shipping path; a library GEMM only on the fp32 twin path
+            # (and for layouts whose dx is not a multiple of 32)
+            if all_tc and not fuse_dx:
                 torch.bmm(dZb, self.wx_b.transpose(1, 2), out=dXb)
-            else:
+            elif not all_tc:
                 torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)
             if self.fc_bwd_tc:
                 xb = _p(self.st_x[ci]) if use_store else None

@@ -856,7 +856,30 @@ __global__ void pack_wht_kernel(const DDimsTC d, const float* __restrict__ P, __
   }
 }
 
+// B operand of the fused dX = dZ . Wx^T product: element (kc, n, e) = Wx[n][kc * 8 + e], n = fc-output column (< dx)
+__global__ void pack_wxt_kernel(const DDimsTC d, const float* __restrict__ P, __nv_bfloat16* __restrict__ Wxt) {
+  const int u = blockIdx.y;
+  const float* Wx = P + d.off_wx + (int64_t)u * d.dx * TC_N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BW_KC * d.dx; i += gridDim.x * blockDim.x) {
+    const int kc = i / d.dx, n = i - kc * d.dx;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(Wx[(int64_t)n * TC_N + kc * 8 + e]);
+    *reinterpret_cast<uint4*>(Wxt + (((int64_t)u * BW_KC + kc) * d.dx + n) * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 struct BwdTC {
+  const __nv_bfloat16* Wxt;  // optional [2A][32][dx][8] (tscl_pack_wxt): with dXb, dX = dZ . Wx^T is fused into the step
+  __nv_bfloat16* dXb;        // optional [2A][T*Rc][dx] bf16
   const __nv_bfloat16* Wt;   // [2A][32][64][8]
   float* ZG;                 // [2A][T*Rc][256] gates in, dZ out
   const float* C;            // [2A][T*Rc][64]
@@ -881,13 +904,17 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
   constexpr int NSUB = HPT / 8;
   constexpr int NQ = NT / 128;              // hidden groups (threads per row)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool fuse_dx = a.dXb != nullptr;             // second product of the same dz tile: dX = dz . Wx^T (N = dx)
+  const int dx = d.dx;
   unsigned char* sB = tc_smem;                       // 32 * 1024  : Wh^T image
   unsigned char* sA = sB + BW_KC * 1024;             // 32 * 2048  : dz tile
   uint64_t* sBar = reinterpret_cast<uint64_t*>(sA + BW_KC * 2048);
   uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
+  unsigned char* sBx = sA + BW_KC * 2048 + 16;       // 32 * dx * 16 : Wx^T image (only when fuse_dx)
   const uint32_t bar = smem_u32(sBar);
+  const uint32_t tmem_cols = fuse_dx ? 512u : 64u;   // D1 (dh) in columns 0..63, D2 (dX) in columns 64..64+dx
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(64));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
@@ -899,7 +926,8 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *sTmem;
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_H >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+  const uint32_t idesc_x = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(dx >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB), aBx = smem_u32(sBx);
   const int64_t n_tiles = (a.Rc + TC_M - 1) / TC_M;
   const int64_t n_items = n_tiles * 2 * d.A;
   int cur_u = -1;
@@ -925,6 +953,11 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
       const uint4* src = reinterpret_cast<const uint4*>(a.Wt + (int64_t)u * BW_KC * TC_H * 8);
       uint4* dst = reinterpret_cast<uint4*>(sB);
       for (int i = tid; i < BW_KC * TC_H; i += NT) dst[i] = src[i];
+      if (fuse_dx) {
+        const uint4* sx = reinterpret_cast<const uint4*>(a.Wxt + (int64_t)u * BW_KC * dx * 8);
+        uint4* dxs = reinterpret_cast<uint4*>(sBx);
+        for (int i = tid; i < BW_KC * dx; i += NT) dxs[i] = sx[i];
+      }
     }
     float dc[HPT], dhc[HPT];
 #pragma unroll
@@ -1008,16 +1041,22 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
           if (valid && a.dZb) *reinterpret_cast<uint4*>(a.dZb + m * TC_N + g * 64 + jo) = *reinterpret_cast<const uint4*>(v);
         }
       }
-      if (keep != 0.f && t > 0) {
+      const bool need_dh = keep != 0.f && t > 0;
+      if (need_dh || fuse_dx) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (warp == 0) {
           if (lane == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int ks = 0; ks < 16; ++ks)
-              umma_bf16(tmem, make_desc(aA + ks * 2 * 2048, 2048, 128), make_desc(aB + ks * 2 * 1024, 1024, 128), idesc,
-                        ks > 0 ? 1u : 0u);
+            if (need_dh)
+              for (int ks = 0; ks < 16; ++ks)
+                umma_bf16(tmem, make_desc(aA + ks * 2 * 2048, 2048, 128), make_desc(aB + ks * 2 * 1024, 1024, 128), idesc,
+                          ks > 0 ? 1u : 0u);
+            if (fuse_dx)      // same A tile, B = Wx^T image: chunk stride dx * 16 B, 8-row groups 128 B apart
+              for (int ks = 0; ks < 16; ++ks)
+                umma_bf16(tmem + 64u, make_desc(aA + ks * 2 * 2048, 2048, 128),
+                          make_desc(aBx + (uint32_t)(ks * 2 * dx * 16), (uint32_t)(dx * 16), 128), idesc_x, ks > 0 ? 1u : 0u);
             umma_commit(bar);
           }
           __syncwarp();
@@ -1025,13 +1064,32 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
         mbar_wait(bar, parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float dhp[HPT];
+        if (need_dh) {
+          float dhp[HPT];
 #pragma unroll
-        for (int c16 = 0; c16 < HPT / 16; ++c16)
-          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(jq + c16 * 16), dhp + c16 * 16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int c16 = 0; c16 < HPT / 16; ++c16)
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(jq + c16 * 16), dhp + c16 * 16);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int e = 0; e < HPT; ++e) dhc[e] = dhp[e] * keep;
+          for (int e = 0; e < HPT; ++e) dhc[e] = dhp[e] * keep;
+        } else {
+#pragma unroll
+          for (int e = 0; e < HPT; ++e) dhc[e] = 0.f;
+        }
+        if (fuse_dx) {        // this thread's share of the row: dx / NQ columns, 8 at a time -> bf16 -> one 16-byte store
+          const int per = dx / NQ;
+          for (int c8 = 0; c8 < per; c8 += 8) {
+            float xv[8];
+            tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 + qt * per + c8), xv);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (valid) {
+              __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(xv[e]);
+              *reinterpret_cast<uint4*>(a.dXb + m * dx + qt * per + c8) = *reinterpret_cast<const uint4*>(v);
+            }
+          }
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < HPT; ++e) dhc[e] = 0.f;
@@ -1040,7 +1098,16 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+}
+
+extern "C" int tscl_pack_wxt(tscl_handle* h, const float* params, void* wxt_bf16, void* stream) {
+  if (!h || !params || !wxt_bf16) return tsc_set_error("tscl_pack_wxt: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  pack_wxt_kernel<<<dim3(8, 2 * d.A), 256, 0, (cudaStream_t)stream>>>(d, params, (__nv_bfloat16*)wxt_bf16);
+  PCK(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16, void* stream) {
@@ -1055,25 +1122,40 @@ extern "C" int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16,
 extern "C" int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH,
                                     const float* c0, const float* done, int32_t T, int64_t Rc, int64_t ld_state,
                                     int64_t r0, const void* gates_bf16, const void* c_bf16, void* dz_bf16, void* stream) {
+  return tscl_lstm_seq_bwd_tc_dx(h, wt_bf16, ZG, C, dH, c0, done, T, Rc, ld_state, r0, gates_bf16, c_bf16, dz_bf16, nullptr,
+                                 nullptr, stream);
+}
+
+extern "C" int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH,
+                                       const float* c0, const float* done, int32_t T, int64_t Rc, int64_t ld_state,
+                                       int64_t r0, const void* gates_bf16, const void* c_bf16, void* dz_bf16,
+                                       const void* wxt_bf16, void* dx_bf16, void* stream) {
   if (!h || !wt_bf16 || T <= 0 || Rc <= 0) return tsc_set_error("tscl_lstm_seq_bwd_tc: bad argument");
+  if ((wxt_bf16 == nullptr) != (dx_bf16 == nullptr)) return tsc_set_error("tscl_lstm_seq_bwd_tc_dx: wxt_bf16 and dx_bf16 go together");
   if (!ZG && !(gates_bf16 && c_bf16 && dz_bf16)) return tsc_set_error("tscl_lstm_seq_bwd_tc: ZG may be null only with gates_bf16, c_bf16 and dz_bf16");
   if ((gates_bf16 == nullptr) != (c_bf16 == nullptr)) return tsc_set_error("tscl_lstm_seq_bwd_tc: gates_bf16 and c_bf16 go together");
   PCK(cudaSetDevice(tscl_device_of(h)));
   const DDimsTC& d = *tscl_dims_of(h);
-  const size_t smem = BW_KC * 1024 + BW_KC * 2048 + 16;
+  if (dx_bf16 && (d.dx % 32 != 0 || d.dx > 256)) return tsc_set_error("tscl_lstm_seq_bwd_tc_dx: dx must be a multiple of 32, <= 256");
+  const size_t smem_max = BW_KC * 1024 + BW_KC * 2048 + 16 + (size_t)BW_KC * 256 * 16;
+  const size_t smem = BW_KC * 1024 + BW_KC * 2048 + 16 + (dx_bf16 ? (size_t)BW_KC * d.dx * 16 : 0);
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {
-    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    PCK(cudaFuncSetAttribute(lstm_bwd_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     attr_dev = tscl_device_of(h);
   }
   int n_sm = 0;
   PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
   const int64_t n_items = ((Rc + TC_M - 1) / TC_M) * 2 * d.A;
-  const int grid = (int)(n_items < 2 * n_sm ? n_items : 2 * n_sm);   // 96 KB smem: two 512-thread CTAs per SM when registers allow
+  // 96 KB smem: two 512-thread CTAs per SM when registers allow; the fused-dX variant (up to 211 KB, 512 TMEM columns) is
+  // one CTA per SM
+  const int64_t max_ctas = dx_bf16 ? n_sm : 2 * n_sm;
+  const int grid = (int)(n_items < max_ctas ? n_items : max_ctas);
   BwdTC a;
   a.Wt = (const __nv_bfloat16*)wt_bf16; a.ZG = ZG; a.C = C; a.dH = dH; a.c0 = c0; a.done = done; a.T = T; a.Rc = Rc;
   a.ld_state = ld_state; a.r0 = r0; a.Gb = (const __nv_bfloat16*)gates_bf16; a.Cb = (const __nv_bfloat16*)c_bf16; a.dZb = (__nv_bfloat16*)dz_bf16;
+  a.Wxt = (const __nv_bfloat16*)wxt_bf16; a.dXb = (__nv_bfloat16*)dx_bf16;
   // measured (R = 8192, 1 x B200): the one-CTA-per-SM 512-thread variant 2.097 ms per control step, the two-CTA 256-thread
   // variant 2.144 ms; TSC_BPTT_THREADS=256 selects the latter for experiments
   static const int bw_threads = []() { const char* e = getenv("TSC_BPTT_THREADS"); return e && atoi(e) == 256 ? 256 : 512; }();

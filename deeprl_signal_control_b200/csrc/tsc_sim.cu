@@ -59,6 +59,8 @@ struct DevNet {
   const int32_t* obs_kind;
   const int32_t* obs_idx;
   const float* obs_scale;
+  const uint32_t* obs_prog;   // packed gather program: kind:2 | scaled:1 | index:29 (scale is 1 or obs_scale_val)
+  float obs_scale_val;        // the one non-unit scale of the program (coop_gamma, envs/env.py:186-188)
   const int32_t* src_lane;
   const int32_t* src_route;
   const uint8_t* src_due;
@@ -274,6 +276,31 @@ __device__ __forceinline__ int find_lane(const int32_t* __restrict__ pre, int n,
   return lo;
 }
 
+// lane of compact vehicle index kk, warp-cooperatively: s_blk[j] = lane of compact index 32 j (written by the lane
+// owners after the scan); the 32 lane boundaries that follow the lane of the warp's first vehicle are searched with
+// shuffles (33 possible outcomes -> 6 halvings); falls back to the block-wide binary search when the warp spans more.
+__device__ __forceinline__ int find_lane_warp(const int32_t* __restrict__ pre, const int32_t* __restrict__ blk, int L, int kk) {
+  const int lane0 = blk[(kk & ~31) >> 5];
+  const int bi = lane0 + 1 + (threadIdx.x & 31);
+  const int bnd = pre[bi < L ? bi : L];
+  int lo = 0, hi = 32;
+#pragma unroll
+  for (int itb = 0; itb < 6; ++itb) {
+    const int mid = (lo + hi) >> 1;
+    const int vb = __shfl_sync(0xffffffffu, bnd, mid & 31);
+    if (lo < hi) { if (vb <= kk) lo = mid + 1; else hi = mid; }
+  }
+  return lo < 32 ? lane0 + lo : find_lane(pre, L, kk);
+}
+// s_blk for the current scan (own lanes of every thread)
+__device__ __forceinline__ void fill_blk(const int32_t* __restrict__ pre, const int32_t* __restrict__ cnt, int32_t* __restrict__ blk,
+                                         int l_lo, int l_hi) {
+  for (int l = l_lo; l < l_hi; ++l) {
+    const int p0 = pre[l], p1 = p0 + cnt[l];
+    for (int j = (p0 + 31) >> 5; (j << 5) < p1; ++j) blk[j] = l;
+  }
+}
+
 // signal state of node i for the yellow or the green part of the interval (envs/env.py:128-152)
 __device__ __forceinline__ void node_signal(const DevNet& n, int i, int a, int p, bool yellow_phase,
                                             uint32_t* open, uint32_t* major, uint32_t* ymask) {
@@ -329,13 +356,21 @@ tsc_step_kernel(const StepArgs A) {
   int32_t* s_wsum = s_misc + 8;
   int32_t* s_blk = s_wsum + TSC_THREADS / 32;                      // lane of compact vehicle 32*j
   float* s_obsv = reinterpret_cast<float*>(s_blk + (n.n_slots + 31) / 32 + 1);   // [2*n_det] normalised wave | wait
+  // static tables staged once per CTA (they sit on the dependent-load chains of every phase): lane constants and the
+  // route tables (hop -> lane, hop -> link)
+  LaneC* s_lane = reinterpret_cast<LaneC*>(smem_raw + ((reinterpret_cast<unsigned char*>(s_obsv + 2 * n.n_det) - smem_raw + 15) & ~15));
+  int16_t* s_rlane = reinterpret_cast<int16_t*>(s_lane + L);
+  int16_t* s_rlink = s_rlane + n.n_routes * n.max_hops;
 
   // ---- load replica state -------------------------------------------------------------------
   const uint8_t* g_cnt = A.lane_cnt + (size_t)rep * n.lpad;
   int32_t* g_ctl = A.ctl + (size_t)rep * A.ctl_words;
   uint32_t* g_x = A.veh + (size_t)rep * 2 * n.n_slots;
   uint32_t* g_m = g_x + n.n_slots;
-  for (int l = tid; l < L; l += TSC_THREADS) { s_cnt[l] = g_cnt[l]; s_head[l] = 0; }
+  for (int l = tid; l < L; l += TSC_THREADS) { s_cnt[l] = g_cnt[l]; s_head[l] = 0; s_lane[l] = n.lane[l]; }
+  for (int i = tid; i < n.n_routes * n.max_hops; i += TSC_THREADS) {
+    s_rlane[i] = __ldg(&n.route_lane[i]); s_rlink[i] = __ldg(&n.route_link[i]);
+  }
   if (tid < CTL_FIXED) s_misc[tid] = g_ctl[tid];
   for (int i = tid; i < N; i += TSC_THREADS) {
     s_prev[i] = g_ctl[CTL_FIXED + i];
@@ -346,12 +381,18 @@ tsc_step_kernel(const StepArgs A) {
   __syncthreads();
   block_scan(s_cnt, s_pre, s_wsum, L);
   {
+    const int per0 = (L + TSC_THREADS - 1) / TSC_THREADS;
+    fill_blk(s_pre, s_cnt, s_blk, tid * per0, min(L, tid * per0 + per0));
+    __syncthreads();
     const int V = s_pre[L];
-    for (int k = tid; k < V; k += TSC_THREADS) {
-      int lane = find_lane(s_pre, L, k);
-      int rank = k - s_pre[lane];
-      st2(ring, __ldg(&n.lane[lane].slot0) + rank, make_uint2(g_x[k], g_m[k]));
-      if constexpr (REC) ring.t[__ldg(&n.lane[lane].slot0) + rank] = A.trip[(size_t)rep * n.n_slots + k];
+    for (int k0 = 0; k0 < V; k0 += TSC_THREADS) {      // warp-uniform trip count: the lane lookup uses shuffles
+      const int k = k0 + tid;
+      const int lane = find_lane_warp(s_pre, s_blk, L, k < V ? k : V - 1);
+      if (k < V) {
+        const int rank = k - s_pre[lane];
+        st2(ring, s_lane[lane].slot0 + rank, make_uint2(g_x[k], g_m[k]));
+        if constexpr (REC) ring.t[s_lane[lane].slot0 + rank] = A.trip[(size_t)rep * n.n_slots + k];
+      }
     }
   }
   for (int i = tid; i < N; i += TSC_THREADS)
@@ -376,9 +417,9 @@ tsc_step_kernel(const StepArgs A) {
     for (int l = l_lo; l < l_hi; ++l) {
       s_hflag[l] = 0; s_acc[l] = 0; s_cntadd[l] = 0;
       if (s_cnt[l] > 0) {
-        const LaneC lc = n.lane[l];
+        const LaneC lc = s_lane[l];
         const uint2 h = ld2(ring, lc.slot0 + s_head[l]);
-        int link = __ldg(&n.route_link[M0_ROUTE(h.y) * n.max_hops + M0_HOP(h.y)]);
+        int link = (int)s_rlink[M0_ROUTE(h.y) * n.max_hops + M0_HOP(h.y)];
         if (link >= 0) {
           const LinkC* lk = &n.link[link];
           int node = __ldg(&lk->node);
@@ -393,18 +434,15 @@ tsc_step_kernel(const StepArgs A) {
     const ScanCarry sc = scan_part1(s_cnt, s_wsum, L);
     __syncthreads();
     scan_part2(sc, s_pre, s_wsum, L);
-    for (int l = l_lo; l < l_hi; ++l) {      // own lanes: which compact indices 32*j fall into lane l
-      const int p0 = s_pre[l], p1 = p0 + s_cnt[l];
-      for (int j = (p0 + 31) >> 5; (j << 5) < p1; ++j) s_blk[j] = l;
-    }
+    fill_blk(s_pre, s_cnt, s_blk, l_lo, l_hi);      // own lanes: which compact indices 32*j fall into lane l
     // A2: head-vehicle speed limit from the junction ahead (own lanes; reads other lanes' tails)
     for (int l = l_lo; l < l_hi; ++l) {
       float lim = INF_SPEED;
       if (s_cnt[l] > 0) {
-        const LaneC lc = n.lane[l];
+        const LaneC lc = s_lane[l];
         const uint2 h = ld2(ring, lc.slot0 + s_head[l]);
         const uint32_t route = M0_ROUTE(h.y), hop = M0_HOP(h.y);
-        const int link = __ldg(&n.route_link[route * n.max_hops + hop]);
+        const int link = (int)s_rlink[route * n.max_hops + hop];
         if (link >= 0) {
           const LinkC lk = n.link[link];
           const float hx = veh_x(h.x), hv = veh_v(h.x);
@@ -427,10 +465,10 @@ tsc_step_kernel(const StepArgs A) {
             s_hflag[l] = F_CLOSED;        // own lane; read by the lane's rank-0 vehicle thread in B after the barrier
           } else {
             if (lk.vmax < 1.0e8f) lim = free_speed(d, lk.vmax, c.decel);
-            const int nl = __ldg(&n.route_lane[route * n.max_hops + hop + 1]);
+            const int nl = (int)s_rlane[route * n.max_hops + hop + 1];
             const int nc = s_cnt[nl];
             if (nc > 0) {
-              const LaneC nlc = n.lane[nl];
+              const LaneC nlc = s_lane[nl];
               int idx = s_head[nl] + nc - 1;
               if (idx >= nlc.cap) idx -= nlc.cap;
               const uint32_t txv = ring.xv[nlc.slot0 + idx];
@@ -456,24 +494,10 @@ tsc_step_kernel(const StepArgs A) {
         int slot = 0, lane = 0, rank = 0;
         uint2 me = make_uint2(0, 0);
         uint8_t f = 0;
-        {   // lane of compact index k: warp-cooperative search over the 32 lane boundaries that follow the lane of
-            // the warp's first vehicle (33 possible outcomes -> 6 halvings); falls back to the block-wide search
-          const int kk = act ? k : V - 1;
-          const int lane0 = s_blk[(kk & ~31) >> 5];
-          const int bi = lane0 + 1 + (tid & 31);
-          const int bnd = s_pre[bi < L ? bi : L];
-          int lo = 0, hi = 32;
-#pragma unroll
-          for (int itb = 0; itb < 6; ++itb) {
-            const int mid = (lo + hi) >> 1;
-            const int vb = __shfl_sync(0xffffffffu, bnd, mid & 31);
-            if (lo < hi) { if (vb <= kk) lo = mid + 1; else hi = mid; }
-          }
-          lane = lo < 32 ? lane0 + lo : find_lane(s_pre, L, kk);
-        }
+        lane = find_lane_warp(s_pre, s_blk, L, act ? k : V - 1);
         if (act) {
           rank = k - s_pre[lane];
-          const LaneC lc = n.lane[lane];
+          const LaneC lc = s_lane[lane];
           int idx = s_head[lane] + rank;
           if (idx >= lc.cap) idx -= lc.cap;
           slot = lc.slot0 + idx;
@@ -508,7 +532,7 @@ tsc_step_kernel(const StepArgs A) {
             // a head vehicle whose stop line is closed never passes it (tau < 1 s makes the Euler stop speed
             // overshoot: SUMO's "emergency stop at the end of the lane"); followers: one discharge per lane and second
             if (rank == 0 && s_hflag[lane] != F_CLOSED) {
-              int link = __ldg(&n.route_link[M0_ROUTE(me.y) * n.max_hops + M0_HOP(me.y)]);
+              int link = (int)s_rlink[M0_ROUTE(me.y) * n.max_hops + M0_HOP(me.y)];
               f = link < 0 ? F_ARRIVE : F_CROSS;
             } else {
               xn = lc.len - 0.01f;
@@ -547,7 +571,7 @@ tsc_step_kernel(const StepArgs A) {
     for (int t = l_lo; t < l_hi; ++t) {
       const int q0 = __ldg(&n.lane_inl_off[t]), q1 = __ldg(&n.lane_inl_off[t + 1]);
       if (q0 == q1) continue;
-      const LaneC tc = n.lane[t];
+      const LaneC tc = s_lane[t];
       int cur = s_cnt[t];
       bool have_tail = cur > 0;
       float tail_x = 0.0f;
@@ -560,11 +584,11 @@ tsc_step_kernel(const StepArgs A) {
         const int link = __ldg(&n.lane_inl[q]);
         const int src = __ldg(&n.link[link].from);
         if (s_cnt[src] == 0 || s_hflag[src] != F_CROSS) continue;
-        const LaneC sc2 = n.lane[src];
+        const LaneC sc2 = s_lane[src];
         const uint2 h = ld2(ring, sc2.slot0 + s_head[src]);
         const uint32_t route = M0_ROUTE(h.y), hop = M0_HOP(h.y);
-        if (__ldg(&n.route_link[route * n.max_hops + hop]) != link) continue;
-        if (__ldg(&n.route_lane[route * n.max_hops + hop + 1]) != t) continue;
+        if ((int)s_rlink[route * n.max_hops + hop] != link) continue;
+        if ((int)s_rlane[route * n.max_hops + hop + 1] != t) continue;
         if (cur >= tc.cap) continue;
         float x = veh_x(h.x) - sc2.len;
         if (have_tail) {
@@ -596,7 +620,7 @@ tsc_step_kernel(const StepArgs A) {
     // tail segment; at most one insertion per lane per second, lowest source index first)
     for (int l = l_lo; l < l_hi; ++l) {
       int cl = s_cnt[l];
-      const LaneC lc = n.lane[l];
+      const LaneC lc = s_lane[l];
       if (cl > 0) {
         const uint8_t f = s_hflag[l];
         bool pop = false;
@@ -700,7 +724,7 @@ tsc_step_kernel(const StepArgs A) {
   // ---- detector reads (envs/env.py:325-407): one thread per detector lane ---------------------
   for (int d = tid; d < n.n_det; d += TSC_THREADS) {
     const int l = __ldg(&n.det_lane[d]);
-    const LaneC lc = n.lane[l];
+    const LaneC lc = s_lane[l];
     int veh = 0, halt = 0, wait = 0;
     const int cl = s_cnt[l];
     int idx = s_head[l];
@@ -768,12 +792,13 @@ tsc_step_kernel(const StepArgs A) {
     const float* fp = A.fp ? A.fp + (size_t)rep * N * n.max_na : nullptr;
     float* o = A.obs + (size_t)rep * n.n_obs;
     for (int k = tid; k < n.n_obs; k += TSC_THREADS) {
-      const int kind = __ldg(&n.obs_kind[k]), idx = __ldg(&n.obs_idx[k]);
+      const uint32_t pw = __ldg(&n.obs_prog[k]);
+      const int kind = (int)(pw & 3u), idx = (int)(pw >> 3);
       float v;
       if (kind == 0) v = s_obsv[idx];
       else if (kind == 1) v = s_obsv[n.n_det + idx];
       else v = fp ? fp[idx] : 0.0f;
-      o[k] = __ldg(&n.obs_scale[k]) * v;
+      o[k] = ((pw & 4u) ? n.obs_scale_val : 1.0f) * v;      // same product as obs_scale[k] * v
     }
   }
   if (A.n_sub == 0) return;  // observe only: state untouched
@@ -781,16 +806,21 @@ tsc_step_kernel(const StepArgs A) {
   // ---- store replica state (compact) + parity taps --------------------------------------------
   block_scan(s_cnt, s_pre, s_wsum, L);
   {
+    fill_blk(s_pre, s_cnt, s_blk, l_lo, l_hi);
+    __syncthreads();
     const int V = s_pre[L];
-    for (int k = tid; k < V; k += TSC_THREADS) {
-      int lane = find_lane(s_pre, L, k);
-      int rank = k - s_pre[lane];
-      const LaneC lc = n.lane[lane];
-      int idx = s_head[lane] + rank;
-      if (idx >= lc.cap) idx -= lc.cap;
-      const uint2 e = ld2(ring, lc.slot0 + idx);
-      g_x[k] = e.x; g_m[k] = e.y;
-      if constexpr (REC) A.trip[(size_t)rep * n.n_slots + k] = ring.t[lc.slot0 + idx];
+    for (int k0 = 0; k0 < V; k0 += TSC_THREADS) {
+      const int k = k0 + tid;
+      const int lane = find_lane_warp(s_pre, s_blk, L, k < V ? k : V - 1);
+      if (k < V) {
+        const int rank = k - s_pre[lane];
+        const LaneC lc = s_lane[lane];
+        int idx = s_head[lane] + rank;
+        if (idx >= lc.cap) idx -= lc.cap;
+        const uint2 e = ld2(ring, lc.slot0 + idx);
+        g_x[k] = e.x; g_m[k] = e.y;
+        if constexpr (REC) A.trip[(size_t)rep * n.n_slots + k] = ring.t[lc.slot0 + idx];
+      }
     }
   }
   uint8_t* g_cnt_w = A.lane_cnt + (size_t)rep * n.lpad;
@@ -982,6 +1012,19 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   rc |= upload(h, net->obs_kind, (size_t)net->n_obs, &d.obs_kind);
   rc |= upload(h, net->obs_idx, (size_t)net->n_obs, &d.obs_idx);
   rc |= upload(h, net->obs_scale, (size_t)net->n_obs, &d.obs_scale);
+  {
+    std::vector<uint32_t> prog(net->n_obs > 0 ? net->n_obs : 1, 0u);
+    float sv = 1.0f;
+    for (int k = 0; k < net->n_obs; ++k)
+      if (net->obs_scale[k] != 1.0f) sv = net->obs_scale[k];
+    for (int k = 0; k < net->n_obs; ++k) {
+      const float sc = net->obs_scale[k];
+      if (sc != 1.0f && sc != sv) { tsc_destroy(h); return fail("tsc_create: more than one non-unit observation scale"); }
+      prog[k] = (uint32_t)(net->obs_kind[k] & 3) | (sc != 1.0f ? 4u : 0u) | ((uint32_t)net->obs_idx[k] << 3);
+    }
+    d.obs_scale_val = sv;
+    rc |= upload(h, prog.data(), prog.size(), &d.obs_prog);
+  }
   rc |= upload(h, net->src_lane, (size_t)net->n_src, &d.src_lane);
   rc |= upload(h, net->src_route, (size_t)net->n_src, &d.src_route);
   rc |= upload(h, net->src_due, (size_t)net->horizon * net->n_src, &d.src_due);
@@ -1024,10 +1067,12 @@ extern "C" int tsc_create(const tsc_net* net, const tsc_cfg* cfg, int32_t R, int
   sm = (sm + 3) & ~(size_t)3;
   sm += (size_t)N * 4 * 6 + (size_t)net->n_src * 4 + (size_t)net->n_det * 12 + (size_t)N * 4 + (8 + TSC_THREADS / 32) * 4 +
         ((size_t)(net->n_slots + 31) / 32 + 1) * 4 + (size_t)net->n_det * 8;
-  h->smem = (int)sm;
+  sm = (sm + 15) & ~(size_t)15;
+  sm += (size_t)L * sizeof(LaneC) + (size_t)net->n_routes * net->max_hops * 2 * 2;
+  h->smem = (int)sm + 16;
   if (sm > 227 * 1024) { tsc_destroy(h); return fail("tsc_create: replica state exceeds 227 KB of shared memory"); }
   CK(cudaFuncSetAttribute(tsc_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
-  h->smem_rec = h->smem + (int)net->n_slots * 4;
+  h->smem_rec = h->smem + (int)net->n_slots * 4 + 16;   // + slack: the 16-byte alignment of the table block can shift
   if (h->smem_rec <= 232448)
     CK(cudaFuncSetAttribute(tsc_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_rec));
   std::vector<uint64_t> seeds(R, 0);

@@ -33,3 +33,26 @@ def allreduce_sum_(flat_grad, group=None):
     import torch.distributed as dist
     dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
     return flat_grad
+
+
+def bind_to_gpu_numa(device_index: int):
+    """Restrict this process to the host cores of the GPU's NUMA node (nvidia-smi topo 'CPU Affinity'), BEFORE any
+    page-locked buffer is allocated: pinned pages are then first-touched on the local node, so a rank's H2D / D2H
+    traffic does not cross the inter-socket link.  On an 8-GPU box GPUs 0-3 and 4-7 hang off different sockets; four
+    ranks sharing one socket's PCIe root is what limited the host-buffer (e2e) path at N = 4 in round 1.
+    Returns the cpu list it bound to, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None

@@ -129,6 +129,15 @@ int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16, void* stre
 int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH, const float* c0,
                          const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
                          const void* gates_bf16, const void* c_bf16, void* dz_bf16, void* stream);
+/* The same kernel with dX = dZ . Wx^T fused into every step (second tcgen05 product of the same dz tile, M=128, N=dx,
+ * K=256, accumulator in TMEM columns 64..64+dx): wxt_bf16 [2A][32][dx][8] from tscl_pack_wxt (refresh after every
+ * optimizer step), dx_bf16 [2A][T*Rc][dx] receives dX as bf16 — this replaces the last library GEMM of the update
+ * (reference: the tf.gradients chain through agents/utils.py:106, `tf.matmul(x, wx)`).  Both NULL = plain BPTT. */
+int tscl_pack_wxt(tscl_handle* h, const float* params, void* wxt_bf16, void* stream);
+int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH, const float* c0,
+                            const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
+                            const void* gates_bf16, const void* c_bf16, void* dz_bf16, const void* wxt_bf16, void* dx_bf16,
+                            void* stream);
 /* gates_bf16 / c_bf16 (both or neither): read gate activations and c_t straight from one chunk of the bf16
  * activation store instead of ZG / C (ZG is then write-only: it receives dZ).
  * dz_bf16 (optional): also write dZ as bf16 [2A][T*Rc][256]; with all three bf16 pointers ZG may be NULL. */

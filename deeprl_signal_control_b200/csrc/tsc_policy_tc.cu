@@ -86,6 +86,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // MUFU tanh (tanh.approx.f32, max rel. error ~2^-11: below the bf16 operand rounding of this path)
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -489,8 +498,14 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
 //        until the fc result is written / the h part is loaded), D0 = TMEM columns 256..256+dx;
 //   TMEM -> registers -> (+bias, relu, bf16) -> A tile chunks 0..dx/8, then h_prev -> last 8 chunks, then the
 //   gate MMA and the epilogue exactly as in v1.  Two tcgen05.commit per tile on one mbarrier.
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NT = 256: thread = (replica row, 32 hidden units); NT = 512: thread = (replica row, 16 hidden units) — twice the warps
+// per SM for the latency-bound staging / epilogue phases (one CTA per SM either way: the weight operand fills shared
+// memory), same arithmetic per element, so both variants produce identical bits.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
+  constexpr int NG = NT / 128;                 // hidden-unit groups per row (2 or 4)
+  constexpr int HPT = TC_H / NG;               // hidden units per thread (32 or 16)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = d.dx + TC_H, KC = K / 8, KS = K / 16, KCX = d.dx / 8;
   unsigned char* sB = tc_smem;                                  // KC * 4096
@@ -543,15 +558,15 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       cur_u = u;
       const uint4* src = reinterpret_cast<const uint4*>(Wu);
       uint4* dst = reinterpret_cast<uint4*>(sB);
-      for (int i = tid; i < KC * TC_N; i += TC_THREADS) dst[i] = src[i];
+      for (int i = tid; i < KC * TC_N; i += NT) dst[i] = src[i];
       nw = d.n_wave[ag]; nt = d.n_wait[ag]; nf = d.ff > 0 ? d.n_fp[ag] : 0;
       ooff = d.obs_off[ag]; na = d.n_a[ag];
-      for (int i = tid; i < TC_H * 8; i += TC_THREADS) {
+      for (int i = tid; i < TC_H * 8; i += NT) {
         const int k = i >> 3, j = i & 7;
         sWo[i] = j < d.max_na ? a.P[d.off_wo + ((int64_t)u * TC_H + k) * d.max_na + j] : 0.f;
       }
       if (tid < 8) sBo[tid] = tid < d.max_na ? a.P[d.off_bo + (int64_t)u * d.max_na + tid] : 0.f;
-      for (int i = tid; i < TC_N; i += TC_THREADS) {
+      for (int i = tid; i < TC_N; i += NT) {
         sBias[i] = a.P[d.off_bl + (int64_t)u * TC_N + i];
         float b0 = 0.f;
         if (i < d.fw) b0 = a.P[d.off_fcw_b[u] + i];
@@ -563,12 +578,12 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     // L2 prefetch of the NEXT work item's operands (observation slice, c, h): they are consumed ~one tile later
     if (it + 1 < it_hi) {
       const int un = (int)((it + 1) / n_tiles);
-      const int64_t rn = ((it + 1) - (int64_t)un * n_tiles) * TC_M + (tid >> 1);
-      if (rn < a.R) {
+      const int64_t rn = ((it + 1) - (int64_t)un * n_tiles) * TC_M + (tid / NG);
+      if (rn < a.R && (tid % NG) < 2) {
         const int an = un >> 1;
-        const float* op = a.obs + rn * d.n_obs + d.obs_off[an] + (tid & 1) * 32;
+        const float* op = a.obs + rn * d.n_obs + d.obs_off[an] + (tid % NG) * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(op));
-        const int64_t so = ((int64_t)un * ld + rn) * TC_H + (tid & 1) * 32;
+        const int64_t so = ((int64_t)un * ld + rn) * TC_H + (tid % NG) * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.c_in + so));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h_in + so));
       }
@@ -577,11 +592,11 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     {
       const uint4* src0 = reinterpret_cast<const uint4*>(Wu + (int64_t)KC * TC_N * 8);
       uint4* dst0 = reinterpret_cast<uint4*>(sA);
-      for (int i = tid; i < 8 * d.dx; i += TC_THREADS) dst0[i] = src0[i];
+      for (int i = tid; i < 8 * d.dx; i += NT) dst0[i] = src0[i];
       // thread = (row, 16-byte chunk) : 128 x 8 pairs, 4 per thread
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int pair = p * TC_THREADS + tid;
+      for (int p = 0; p < 1024 / NT; ++p) {
+        const int pair = p * NT + tid;
         const int row = pair & 127, ch = pair >> 7;          // consecutive threads -> consecutive rows
         const int64_t r = r0 + row;
         __align__(16) __nv_bfloat16 v[8];
@@ -621,36 +636,33 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     {
       const int q = warp & 3, hw = warp >> 2;
       const int row = q * 32 + lane;
-      const int ncol = d.dx >> 1;                      // columns per half (multiple of 16)
-      for (int c0 = hw * ncol; c0 < (hw + 1) * ncol; c0 += 16) {
-        float z[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
+      const int ncol = d.dx / NG;                      // columns per group (multiple of 8: dx % 32 == 0)
+      const bool st = a.st_x && r0 + row < a.R;
+      const int64_t m = st ? store_row(row) : 0;
+      for (int c0 = hw * ncol; c0 < (hw + 1) * ncol; c0 += 8) {
+        float z[8];
+        tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        __align__(16) __nv_bfloat16 v[16];
+        __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
+        for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
         *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
-        *reinterpret_cast<uint4*>(sA + (size_t)((c0 >> 3) + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
-        if (a.st_x && r0 + row < a.R) {
-          const int64_t m = store_row(row);
-          uint4* o = reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0));
-          o[0] = *reinterpret_cast<const uint4*>(v); o[1] = *reinterpret_cast<const uint4*>(v + 8);
-        }
+        if (st) *reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0)) = *reinterpret_cast<const uint4*>(v);
       }
     }
     {
-      const int row = tid >> 1, half = tid & 1;
+      const int row = tid / NG, half = tid % NG;      // `half` = hidden-unit group of HPT units
       const int64_t r = r0 + row;
       const bool live = r < a.R && !a.done;
-      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * ld + (r < a.R ? r : 0)) * TC_H + half * 32);
+      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * ld + (r < a.R ? r : 0)) * TC_H + half * HPT);
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
+      for (int c8 = 0; c8 < HPT / 8; ++c8) {
         __align__(16) __nv_bfloat16 v[8];
         float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
         if (live) { x0 = hp[2 * c8]; x1 = hp[2 * c8 + 1]; }
         v[0] = __float2bfloat16_rn(x0.x); v[1] = __float2bfloat16_rn(x0.y); v[2] = __float2bfloat16_rn(x0.z); v[3] = __float2bfloat16_rn(x0.w);
         v[4] = __float2bfloat16_rn(x1.x); v[5] = __float2bfloat16_rn(x1.y); v[6] = __float2bfloat16_rn(x1.z); v[7] = __float2bfloat16_rn(x1.w);
-        *reinterpret_cast<uint4*>(sA + (size_t)(KCX + half * 4 + c8) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+        *reinterpret_cast<uint4*>(sA + (size_t)(KCX + half * (HPT / 8) + c8) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -676,18 +688,18 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       const int row = q * 32 + lane;
       const int64_t r = r0 + row;
       const bool valid = r < a.R;
-      const int64_t srow = ((int64_t)u * ld + (valid ? r : 0)) * TC_H + half * 32;
+      const int64_t srow = ((int64_t)u * ld + (valid ? r : 0)) * TC_H + half * HPT;
       float lg[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) lg[j] = 0.f;
 #pragma unroll
-      for (int jb = 0; jb < 2; ++jb) {
+      for (int jb = 0; jb < HPT / 16; ++jb) {
         float zi[16], zf[16], zo[16], zu[16];
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + jb * 16);
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HPT + jb * 16);
         tmem_ld16(tbase, zi); tmem_ld16(tbase + 64, zf); tmem_ld16(tbase + 128, zo); tmem_ld16(tbase + 192, zu);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (a.zdbg && valid) {
-          float* z = a.zdbg + ((int64_t)u * ld + r) * TC_N + half * 32 + jb * 16;
+          float* z = a.zdbg + ((int64_t)u * ld + r) * TC_N + half * HPT + jb * 16;
 #pragma unroll
           for (int e = 0; e < 16; ++e) { z[e] = zi[e]; z[64 + e] = zf[e]; z[128 + e] = zo[e]; z[192 + e] = zu[e]; }
         }
@@ -707,7 +719,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         __align__(16) __nv_bfloat16 gbuf[4][16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int j = half * 32 + jb * 16 + e;
+          const int j = half * HPT + jb * 16 + e;
           const float gi = sigm(zi[e] + sBias[j]), gf = sigm(zf[e] + sBias[64 + j]);
           const float go = sigm(zo[e] + sBias[128 + j]), gu = tanh_fast(zu[e] + sBias[192 + j]);
           cn[e] = gf * cprev[e] + gi * gu;
@@ -719,7 +731,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         }
         if (valid && a.st_g) {
           const int64_t m = store_row((int)(r - r0));
-          const int jo = half * 32 + jb * 16;
+          const int jo = half * HPT + jb * 16;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4* o = reinterpret_cast<uint4*>(a.st_g + m * TC_N + g * 64 + jo);
@@ -744,14 +756,26 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      // partial head sums of groups 1..NG-1: group 1 in sRed, groups 2, 3 (NT = 512) in the A tile, which is dead once
+      // the gate MMA has been committed; group 0 adds them in a fixed order (deterministic bits)
+      float* sRed2 = reinterpret_cast<float*>(sA);
       if (half == 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
+      } else if (half > 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sRed2[((half - 2) * TC_M + row) * 8 + j] = lg[j];
       }
       __syncthreads();
       if (half == 0 && valid) {
+        if (NG == 2) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) lg[j] += sRed[row * 8 + j] + sBo[j];
+          for (int j = 0; j < 8; ++j) lg[j] += sRed[row * 8 + j] + sBo[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            lg[j] = ((lg[j] + sRed[row * 8 + j]) + (sRed2[row * 8 + j] + sRed2[(TC_M + row) * 8 + j])) + sBo[j];
+        }
         if ((u & 1) == 0) {
           float mx = -1e30f;
 #pragma unroll
@@ -809,7 +833,8 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
   if (smem > 232448) return tsc_set_error("tscl_policy_step_v2r: operand tiles exceed shared memory");
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {
-    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = tscl_device_of(h);
   }
   int n_sm = 0;
@@ -822,7 +847,10 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.step = (uint32_t)step; a.replica0 = replica0;
   a.st_x = (__nv_bfloat16*)st_x; a.st_g = (__nv_bfloat16*)st_g; a.st_c = (__nv_bfloat16*)st_c; a.st_h = (__nv_bfloat16*)st_h;
   a.t = t; a.T = T > 0 ? T : 1; a.rc = rc > 0 ? rc : R; a.ld = ld_state; a.row0 = ld_state > 0 ? row0 : 0;
-  policy_step_tc2_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  // TSC_POLICY_THREADS=256 selects the round-1 mapping (thread = row x 32 hidden units) for A/B measurements
+  static const int pol_threads = []() { const char* e = getenv("TSC_POLICY_THREADS"); return e && atoi(e) == 256 ? 256 : 512; }();
+  if (pol_threads == 512) policy_step_tc2_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
+  else policy_step_tc2_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
 }
@@ -868,15 +896,6 @@ __global__ void pack_wxt_kernel(const DDimsTC d, const float* __restrict__ P, __
     *reinterpret_cast<uint4*>(Wxt + (((int64_t)u * BW_KC + kc) * d.dx + n) * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 struct BwdTC {
   const __nv_bfloat16* Wxt;  // optional [2A][32][dx][8] (tscl_pack_wxt): with dXb, dX = dZ . Wx^T is fused into the step
   __nv_bfloat16* dXb;        // optional [2A][T*Rc][dx] bf16

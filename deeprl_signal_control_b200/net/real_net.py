@@ -145,10 +145,45 @@ def _fastest_path(adj, cost, src, dst):
     return path[::-1]
 
 
+def monaco_flow_list(flow_rate: int = 325):
+    """(route index, begin, end, vehsPerHour) of real_net/data/build_file.py:72-105."""
+    times = np.arange(0, 3301, 300)
+    flow_list = []
+    for i in range(len(times) - 1):
+        tb, te = int(times[i]), int(times[i + 1])
+        for j in (0, 1):
+            for ind in range(VOLS_A[i]):
+                flow_list.append((j * 4 + ind, tb, te, int(flow_rate)))
+        for j in (2, 3):
+            for ind in range(VOLS_B[i]):
+                flow_list.append((j * 4 + ind, tb, te, int(flow_rate)))
+    return flow_list
+
+
 def build_real_net(net_file: str, flow_rate: int = 325, agent: str = 'ma2c', coop_gamma: float = 0.9,
                    episode_length_sec: int = 3600, veh_len: float = 5.0, min_gap: float = 2.5) -> NetTables:
+    """The Monaco scenario of the reference: its hand-written NODES / PHASES / flows on most.net.xml."""
+    return build_from_sumo(net_file, tls_phases={n: PHASES[v[0]] for n, v in NODES.items()},
+                           neighbor_map={k: list(v[1]) for k, v in NODES.items()},
+                           flow_defs=[fl for grp in FLOWS for fl in grp], flow_list=monaco_flow_list(flow_rate),
+                           agent=agent, coop_gamma=coop_gamma, episode_length_sec=episode_length_sec,
+                           veh_len=veh_len, min_gap=min_gap, use_wait=False)     # STATE_NAMES = ['wave'] (:18)
+
+
+def build_from_sumo(net_file: str, tls_phases: Dict[str, List[str]], neighbor_map: Dict[str, List[str]],
+                    flow_defs: List[Tuple[str, str, str]], flow_list: List[Tuple[int, int, int, float]],
+                    agent: str = 'ma2c', coop_gamma: float = 0.9, episode_length_sec: int = 3600,
+                    veh_len: float = 5.0, min_gap: float = 2.5, use_wait: bool = False) -> NetTables:
+    """Any SUMO scenario -> NetTables.
+      tls_phases    signalised node -> its phase strings = the agent's action set (envs/real_net_env.py:49-68 for
+                    Monaco; net/sumo_ingest.py derives them from the <tlLogic> programs of a net file)
+      neighbor_map  node -> neighbour nodes in observation order (envs/real_net_env.py:20-47)
+      flow_defs     routes as (from edge, to edge, 'via edges'), routed as SUMO routes <flow from to via>
+      flow_list     (route index, begin s, end s, vehsPerHour)"""
     edges, cons, junctions, internal_len = parse_net(net_file)
-    node_names = sorted(NODES.keys())
+    NODES_ = {n: (n, list(neighbor_map.get(n, []))) for n in tls_phases}
+    PHASES_ = dict(tls_phases)
+    node_names = sorted(NODES_.keys())
     node_idx = {n: i for i, n in enumerate(node_names)}
 
     # ---- signalised links: lanes_in[node][linkIndex] (== traci getControlledLanes) -------------------
@@ -159,7 +194,7 @@ def build_real_net(net_file: str, flow_rate: int = 325, agent: str = 'ma2c', coo
             tl_con.setdefault(c['tl'], {})[int(c['linkIndex'])] = c
     for name in node_names:
         links = tl_con[name]
-        n_link = len(PHASES[NODES[name][0]][0])
+        n_link = len(PHASES_[name][0])
         assert sorted(links) == list(range(n_link)), (name, sorted(links), n_link)
         lanes_in[name] = ['%s_%s' % (links[i]['from'], links[i]['fromLane']) for i in range(n_link)]
     ilds_in = {n: list(dict.fromkeys(lanes_in[n])) for n in node_names}
@@ -176,7 +211,6 @@ def build_real_net(net_file: str, flow_rate: int = 325, agent: str = 'ma2c', coo
             con_of.setdefault((f, t), []).append(c)
     cost = {eid: edges[eid]['lanes'][0]['length'] / max(l['speed'] for l in edges[eid]['lanes'])
             for eid in usable}
-    flow_defs = [fl for grp in FLOWS for fl in grp]
     route_edges = []
     for (src, dst, via) in flow_defs:
         stops = [src] + via.split() + [dst]
@@ -300,12 +334,12 @@ def build_real_net(net_file: str, flow_rate: int = 325, agent: str = 'ma2c', coo
 
     # ---- per-node tables ---------------------------------------------------------------------------------------
     n_nodes = len(node_names)
-    max_phases = max(len(PHASES[NODES[n][0]]) for n in node_names)
+    max_phases = max(len(PHASES_[n]) for n in node_names)
     node_green = np.zeros((n_nodes, max_phases), np.uint32)
     node_major = np.zeros((n_nodes, max_phases), np.uint32)
     node_n_phases = np.zeros(n_nodes, np.int32)
     for i, name in enumerate(node_names):
-        ph = PHASES[NODES[name][0]]
+        ph = PHASES_[name]
         g, m = phase_masks(ph)
         node_green[i, :len(ph)] = g; node_major[i, :len(ph)] = m
         node_n_phases[i] = len(ph)
@@ -313,7 +347,7 @@ def build_real_net(net_file: str, flow_rate: int = 325, agent: str = 'ma2c', coo
     for name in node_names:
         det_lane += [lane_id[s] for s in ilds_in[name]]
         node_det_off.append(len(det_lane))
-    neighbor_map = {k: list(v[1]) for k, v in NODES.items()}
+    neighbor_map = {k: [n for n in v[1] if n in node_idx] for k, v in NODES_.items()}
     node_nbr, node_nbr_off = [], [0]
     for name in node_names:
         node_nbr += [node_idx[n] for n in neighbor_map[name]]
@@ -327,21 +361,12 @@ def build_real_net(net_file: str, flow_rate: int = 325, agent: str = 'ma2c', coo
         route_lane[r, :len(ls)] = ls; route_link[r, :len(ks)] = ks
     src_lane = [r[0] for r in routes_lane]
     src_route = list(range(len(routes_lane)))
-    times = np.arange(0, 3301, 300)
-    flow_list = []
-    for i in range(len(times) - 1):
-        tb, te = int(times[i]), int(times[i + 1])
-        for j in (0, 1):
-            for ind in range(VOLS_A[i]):
-                flow_list.append((j * 4 + ind, tb, te, int(flow_rate)))
-        for j in (2, 3):
-            for ind in range(VOLS_B[i]):
-                flow_list.append((j * 4 + ind, tb, te, int(flow_rate)))
+    flow_list = [(int(r), int(tb), int(te), rate) for r, tb, te, rate in flow_list]
     src_due = flow_due_table(flow_list, episode_length_sec, len(src_lane))
 
     net = NetTables(
         node_names=node_names, lane_names=lane_names, neighbor_map=neighbor_map,
-        phases={n: PHASES[NODES[n][0]] for n in node_names}, lanes_in=lanes_in, ilds_in=ilds_in,
+        phases={n: list(PHASES_[n]) for n in node_names}, lanes_in=lanes_in, ilds_in=ilds_in,
         max_hops=max_hops, horizon=episode_length_sec, max_phases=max_phases, max_na=max_phases,
         lane_len=lane_len, lane_vmax=lane_vmax, lane_cap=lane_cap, lane_slot0=lane_slot0,
         lane_inl_off=lane_inl_off, lane_inl=lane_inl,
@@ -358,7 +383,7 @@ def build_real_net(net_file: str, flow_rate: int = 325, agent: str = 'ma2c', coo
     )
     net.flow_list = flow_list
     net.route_edges = route_edges
-    build_obs_program(net, agent, coop_gamma, use_wait=False)      # STATE_NAMES = ['wave'], envs/real_net_env.py:18
+    build_obs_program(net, agent, coop_gamma, use_wait=use_wait)
     return net.finalize()
 
 

@@ -199,7 +199,9 @@ def cpu_reference(net, par, args, threads, n_step, mode, budget_s=12.0):
     el, learner_note = el_sim, "sim control step only (--mode sim)"
     if mode == "train":
         from oracle.learner_cpu import time_learner
-        R_upd = min(R_cpu, 1024)           # the whole sample when it fits (one agent's unroll at a time in memory)
+        # measured on the 16-core lease: the update costs 60 ms / replica at 128 replicas and 161 ms / replica at 784 (cache
+        # footprint of the autograd unroll), so the CPU arm is timed at its more efficient batch and scaled linearly
+        R_upd = min(R_cpu, 128)
         t_fwd, t_upd = time_learner(make_layout(net, args), R_cpu, 3, R_upd, n_step, threads)
         el_fwd = t_fwd * n_t                               # one policy forward per control step
         el_upd = t_upd * (R_cpu / R_upd) * (n_t / n_step)  # one n-step update per n_step control steps

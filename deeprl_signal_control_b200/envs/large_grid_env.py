@@ -45,9 +45,6 @@ class LargeGridEnv(TrafficSimulator):
         self.peak_flow1 = config.getint('peak_flow1')
         self.peak_flow2 = config.getint('peak_flow2')
         self.init_density = config.getfloat('init_density')
-        if self.init_density > 0:
-            raise NotImplementedError('init_density > 0 (large_grid/data/build_file.py:223-266) is not supported; '
-                                      'every shipped config uses 0')
         super().__init__(config, output_path, is_record, record_stat, port=port,
                          n_replicas=n_replicas, device=device)
 
@@ -62,4 +59,7 @@ class LargeGridEnv(TrafficSimulator):
     def _build_tables(self):
         return _grid.build_large_grid(self.peak_flow1, self.peak_flow2, agent=self.agent,
                                       coop_gamma=self.coop_gamma, use_wait='wait' in self.state_names,
-                                      episode_length_sec=self.episode_length_sec)
+                                      episode_length_sec=self.episode_length_sec,
+                                      init_density=self.init_density, seed=self.seed)
+        # init_density > 0 (large_grid/data/build_file.py:223-266): the destinations of the initial fleet are drawn once per
+        # environment from the config seed (the reference redraws them with every episode's seed)

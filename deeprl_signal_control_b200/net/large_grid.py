@@ -153,10 +153,39 @@ def _route_nodes(src_edge, dst_edge, turn: str) -> List[str]:
     return seq
 
 
+MAX_CAR_NUM = 30            # large_grid/data/build_file.py:19
+
+
+def init_fleet_specs(density: float, seed):
+    """The initial fleet of `init_routes` (large_grid/data/build_file.py:223-266): on every lane of every internal edge
+    `int(MAX_CAR_NUM * density)` vehicles at t = 0, each group bound for one boundary sink edge drawn with
+    `np.random.choice` from numpy's GLOBAL generator right after `np.random.seed(seed)` (build_file.py:275-282) — the
+    legacy `RandomState(seed).choice` reproduces those draws.  Returns [(from node, to node, lane, sink edge (nt, np), n)]."""
+    in_nodes = [5, 10, 15, 20, 25, 21, 16, 11, 6, 1, 1, 2, 3, 4, 5, 25, 24, 23, 22, 21]
+    out_nodes = [6, 7, 8, 9, 10, 16, 17, 18, 19, 20, 1, 2, 3, 4, 5, 11, 12, 13, 14, 15]
+    sinks = [(_nt(i), _np(j)) for i, j in zip(in_nodes, out_nodes)]
+    rs = np.random.RandomState(seed)
+    n = int(MAX_CAR_NUM * density)
+    out = []
+
+    def get(a, b, lane):
+        out.append((a, b, lane, sinks[int(rs.choice(len(sinks)))], n))
+    for i in range(1, 25, 5):                                   # streets: both directions, both lanes
+        for j in range(4):
+            a, b = _nt(i + j), _nt(i + j + 1)
+            get(a, b, 0); get(b, a, 0); get(a, b, 1); get(b, a, 1)
+    for i in range(1, 6):                                       # avenues
+        for j in range(0, 20, 5):
+            a, b = _nt(i + j), _nt(i + j + 5)
+            get(a, b, 0); get(b, a, 0)
+    return out
+
+
 def build_large_grid(peak_flow1: int = 1100, peak_flow2: int = 925, agent: str = "ma2c",
                      coop_gamma: float = 0.9, use_wait: bool = True,
                      episode_length_sec: int = 3600, veh_len: float = 5.0,
-                     min_gap: float = 2.5, route_turn: str = "early") -> NetTables:
+                     min_gap: float = 2.5, route_turn: str = "early",
+                     init_density: float = 0.0, seed=None) -> NetTables:
     edges = grid_edges()
     edge_id = {(a, b): k for k, (a, b, _) in enumerate(edges)}
     # ---- lanes -------------------------------------------------------------------------
@@ -295,6 +324,52 @@ def build_large_grid(peak_flow1: int = 1100, peak_flow2: int = 925, agent: str =
             gs.append(len(src_lane))
             src_lane.append(lanes_r[0]); src_route.append(rid)
         group_src.append(gs)
+    # ---- initial fleet (init_density > 0): fastest route from an internal edge to a drawn boundary sink -------------
+    init_flows = []
+    if init_density > 0 and int(MAX_CAR_NUM * init_density) > 0:
+        import heapq
+        n_edges = len(edges)
+        cost = [(L0 if (a.startswith("nt") and b.startswith("nt")) else L0_END) /
+                (SPEED_LIMIT_ST if typ == "a" else SPEED_LIMIT_AV) for a, b, typ in edges]
+        succ = {}
+        for l in range(n_links):
+            succ.setdefault(lane_edge[link_from[l]], set()).add(link_to_edge[l])
+
+        def fastest(e0, e1):                                    # Dijkstra over edges, ties -> lower edge id
+            dist, prev, pq = {e0: 0.0}, {}, [(0.0, e0)]
+            while pq:
+                dcur, u = heapq.heappop(pq)
+                if u == e1:
+                    break
+                if dcur > dist[u]:
+                    continue
+                for v in sorted(succ.get(u, ())):
+                    nd = dcur + cost[v]
+                    if nd < dist.get(v, 1e30) - 1e-9:
+                        dist[v], prev[v] = nd, u
+                        heapq.heappush(pq, (nd, v))
+            path = [e1]
+            while path[-1] != e0:
+                path.append(prev[path[-1]])
+            return path[::-1]
+        for (a, b, lane, sink, n_veh) in init_fleet_specs(init_density, seed):
+            hops_e = fastest(edge_id[(a, b)], edge_id[sink])
+            lanes_r, links_r = [], []
+            for h, e in enumerate(hops_e):
+                if h + 1 < len(hops_e):
+                    cand = [l for l in range(n_links)
+                            if lane_edge[link_from[l]] == e and link_to_edge[l] == hops_e[h + 1]]
+                    assert len(cand) == 1
+                    lanes_r.append(link_from[cand[0]]); links_r.append(cand[0])
+                else:
+                    lanes_r.append(edge_lane0[e]); links_r.append(-1)
+            # lanes are FIFO here (no mid-edge lane change): the group starts on the lane its first
+            # movement needs, which is `departLane` whenever that lane connects to the route
+            rid = len(routes_lane)
+            routes_lane.append(lanes_r); routes_link.append(links_r)
+            route_names.append("init %s_%s_%d->%s_%s" % (a, b, lane, sink[0], sink[1]))
+            init_flows.append((len(src_lane), n_veh))
+            src_lane.append(lanes_r[0]); src_route.append(rid)
     max_hops = max(len(r) for r in routes_lane)
     route_lane = np.full((len(routes_lane), max_hops), -1, np.int16)
     route_link = np.full((len(routes_lane), max_hops), -1, np.int16)
@@ -323,6 +398,8 @@ def build_large_grid(peak_flow1: int = 1100, peak_flow2: int = 925, agent: str =
                 for s in group_src[j]:
                     flow_list.append((s, tb, te, int(flows[j][i - id2])))
     src_due = flow_due_table(flow_list, episode_length_sec, len(src_lane))
+    for q, n_veh in init_flows:         # `begin="0" end="1" number=n`: all due in the first second (inserted one per lane
+        src_due[0, q] = n_veh           # and second on the free tail segment, like every other vehicle)
 
     net = NetTables(
         node_names=node_names, lane_names=lane_names, neighbor_map=neighbor_map,

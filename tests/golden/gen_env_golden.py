@@ -194,7 +194,13 @@ def grid_spec():
                        r'end="(\d+)" vehsPerHour="(\d+)"', ref_build.output_flows(1100, 925, 0, seed=12))
     nodes = re.findall(r'<node id="(\S+)" x="(\S+)" y="(\S+)" type="(\S+)"/>',
                        ref_build.output_nodes('  <node id="%s" x="%.2f" y="%.2f" type="%s"/>\n'))
-    return dict(edges=edges, connections=cons, ilds=ilds, flows=flows, nodes=nodes)
+    # initial fleet of init_density = 0.2 (init_routes, large_grid/data/build_file.py:223-266), seeds 12 and 31
+    init = {}
+    for seed in (12, 31):
+        xml = ref_build.output_flows(1100, 925, 0.2, seed=seed)
+        init[str(seed)] = re.findall(r'<flow id="i_(\d+)" departPos="random_free" from="(\S+)" to="(\S+)" begin="0" end="1" '
+                                     r'departLane="(\d)" departSpeed="0" number="(\d+)"', xml)
+    return dict(edges=edges, connections=cons, ilds=ilds, flows=flows, nodes=nodes, init_fleet=init)
 
 
 def buffers_golden():

@@ -136,3 +136,27 @@ def test_routes_are_connected_and_use_turn_lanes():
             b = net.lane_names[net.route_lane[r, h + 1]].rsplit("_", 1)[0]
             assert a == b
         assert net.route_link[r, n - 1] == -1
+
+
+def test_initial_fleet_matches_reference_generator():
+    """init_density > 0: the 120 (edge, departLane, sink, number) groups of `init_routes`
+    (large_grid/data/build_file.py:223-266), including the sink edges the reference draws from numpy's global generator
+    after np.random.seed(seed), and their effect on the tables (all due in second 0, routes end on the drawn sink)."""
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid, init_fleet_specs
+    spec = json.load(open(os.path.join(GOLD, "grid_spec.json")))
+    for seed in (12, 31):
+        ref = [(fr, to, int(lane), int(num)) for _, fr, to, lane, num in spec["init_fleet"][str(seed)]]
+        ours = [("%s_%s" % (a, b), "%s_%s" % sink, lane, n) for a, b, lane, sink, n in init_fleet_specs(0.2, seed)]
+        assert ours == ref and len(ref) == 120
+    net = build_large_grid(agent="ma2c", init_density=0.2, seed=12)
+    base = build_large_grid(agent="ma2c")
+    assert net.n_routes == base.n_routes + 120 and net.n_src == base.n_src + 120
+    assert int(net.src_due[0].sum()) - int(base.src_due[0].sum()) == 120 * 6        # int(30 * 0.2) per group
+    ref = spec["init_fleet"]["12"]
+    for k in range(120):
+        r = base.n_routes + k
+        first = net.lane_names[net.route_lane[r, 0]].rsplit("_", 1)[0]
+        last = net.lane_names[net.route_lane[r, net.route_len[r] - 1]].rsplit("_", 1)[0]
+        assert (first, last) == (ref[k][1], ref[k][2])
+        for h in range(int(net.route_len[r]) - 1):                                   # connected
+            assert net.link_from[net.route_link[r, h]] == net.route_lane[r, h]

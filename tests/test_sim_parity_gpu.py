@@ -214,3 +214,22 @@ def test_many_waves_and_replica_ranges_bit_exact():
     c2, v2 = gpu2.dump_state(r0 + 5)
     np.testing.assert_array_equal(c1, c2); np.testing.assert_array_equal(v1, v2)
     assert ref.misc(0)["live"] > 100
+
+
+def test_initial_fleet_bit_exact():
+    """init_density > 0 (large_grid/data/build_file.py:223-266): 120 extra demand sources on internal lanes, several
+    sources per lane, 132 routes — CUDA vs oracle for the first 10 minutes (the fleet drains through the junctions)."""
+    from deeprl_signal_control_b200.net.large_grid import build_large_grid
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    net, par = build_large_grid(agent="ma2c", init_density=0.4, seed=12), EnvParams(agent="ma2c")
+    R = 3
+    gpu, ref = _mk(net, par, R)
+    seeds = np.array([12, 13, 99], dtype=np.uint64)
+    gpu.reset(seeds); ref.reset(seeds)
+    rng = np.random.default_rng(5)
+    for step in range(120):
+        act = rng.integers(0, 5, size=(R, net.n_nodes), dtype=np.int32)
+        fp = rng.random((R, net.n_nodes, net.max_na), dtype=np.float32)
+        _compare_step(gpu, ref, act, fp, check_state_of=(0, 2) if step % 30 == 0 else ())
+    m = ref.misc(0)
+    assert m["departed"] > 120 * 12 * 0.9 and m["arrived"] > 200

@@ -6,8 +6,8 @@
 Same parameter vector layout as the LSTM learner with `PolicyLayout(recurrent=False)`: the LSTM block is replaced by
 `wx` [dx, 64] + `bl` [64]; the ragged fc front end and the heads are unchanged, so the hand-written kernels of
 csrc/tsc_learn.cu do the front end (tscl_fc_embed / tscl_fc_bwd_tc), the heads, sampling, loss and head gradients
-(tscl_heads, tscl_heads_loss), returns and clip + RMSProp; the one dense 160 x 64 layer in the middle is a plain
-batched library GEMM (torch.bmm).  There is no recurrent state: `done` is ignored by forward().
+(tscl_heads, tscl_heads_loss), returns and clip + RMSProp; the dense 160 x 64 layer in the middle runs on the
+register-tiled fp32 kernels tscl_fc_hidden_fwd / tscl_fc_hidden_bwd (no library GEMM on this path).  There is no recurrent state: `done` is ignored by forward().
 """
 from __future__ import annotations
 
@@ -38,12 +38,11 @@ class BatchedFcA2C(BatchedA2C):
         self._mm()
         _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs), C.c_int64(R), C.c_int64(R), C.c_int64(0),
                                      _p(self.X1), self._st()))
-        torch.baddbmm(self.pv["bl"].unsqueeze(1), self.X1, self.pv["wx"], out=self.H1)
-        self.H1.relu_()
+        _lib.check(lib.tscl_fc_hidden_fwd(self._h, _p(self.P), _p(self.X1), C.c_int64(R), _p(self.H1), self._st()))
         _lib.check(lib.tscl_heads(self._h, _p(self.P), _p(self.H1), C.c_int64(R), _p(self.pi), _p(self.val),
                                   _p(self.act) if want_act else None, C.c_uint64(self.seed),
                                   C.c_int64(self.n_forward), C.c_int64(self.replica0), self._st()))
-        self.kernel_launches += 2
+        self.kernel_launches += 3
         if commit:
             self.n_forward += 1
         return self.pi, self.val, (self.act if want_act else None)
@@ -75,23 +74,22 @@ class BatchedFcA2C(BatchedA2C):
             obs0 = self.obs_hist[0, r0:]
             _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs0), C.c_int64(M), C.c_int64(rc),
                                          C.c_int64(R * n_obs), _p(X), st()))
-            torch.baddbmm(self.pv["bl"].unsqueeze(1), X, self.pv["wx"], out=H)
-            H.relu_()
+            _lib.check(lib.tscl_fc_hidden_fwd(self._h, _p(self.P), _p(X), C.c_int64(M), _p(H), st()))
             _lib.check(lib.tscl_heads_loss(self._h, _p(self.P), _p(H), _p(self.act_hist[0, r0:]), _p(self.Rs[0, r0:]),
                                            _p(self.Adv[0, r0:]), C.c_int64(M), C.c_int64(rc), C.c_int64(R * A),
                                            C.c_float(self.v_coef), C.c_float(beta), C.c_float(scale), None, _p(dH),
                                            _p(self.stats), None, _p(self.G), st()))
-            dH.mul_(H > 0)                                           # relu'
-            self.gv["wx"].baddbmm_(X.transpose(1, 2), dH)
-            self.gv["bl"].add_(dH.sum(dim=1))
-            dX = torch.bmm(dH, self.pv["wx"].transpose(1, 2))
+            dX = torch.empty(U, M, L.dx, **f32)
+            # relu', dX = dH . W^T, dW += X^T dH, db += 1^T dH: own kernels (no library GEMM on this path)
+            _lib.check(lib.tscl_fc_hidden_bwd(self._h, _p(self.P), _p(X), _p(H), _p(dH), C.c_int64(M), _p(dX), _p(self.G),
+                                              st()))
             if self.fc_bwd_tc:
                 _lib.check(lib.tscl_fc_bwd_tc(self._h, _p(obs0), _p(X), None, _p(dX), None, C.c_int64(M), C.c_int64(rc),
                                               C.c_int64(R * n_obs), _p(self.G), C.c_int32(0), st()))
             else:
                 _lib.check(lib.tscl_fc_bwd(self._h, _p(obs0), _p(X), _p(dX), C.c_int64(M), C.c_int64(rc),
                                            C.c_int64(R * n_obs), _p(self.G), st()))
-            self.kernel_launches += 3
+            self.kernel_launches += 6
         if self.pg is not None:
             _dist.allreduce_sum_(self.G, self.pg)
         _lib.check(lib.tscl_clip_rmsprop(self._h, _p(self.P), _p(self.G), _p(self.MS), _p(self.agent_of),

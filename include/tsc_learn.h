@@ -61,6 +61,14 @@ int tscl_destroy(tscl_handle* h);
 int tscl_fc_embed(tscl_handle* h, const float* params, const float* obs, int64_t M, int64_t rows_per_t,
                   int64_t stride_t, float* X, void* stream);
 
+/* FcACPolicy hidden layer (agents/policies.py:236: `h = fc(h, out_type + '_fc', n_fc)`), own register-tiled fp32 GEMM
+ * kernels (PolicyLayout(recurrent=False): wx [2A][dx][h], bl [2A][h]):
+ *   fwd  H[u][m][:] = relu(X[u][m][:] . wx[u] + bl[u])                                  X [2A][M][dx], H [2A][M][h]
+ *   bwd  dH <- dH * (H > 0);  dX = dH . wx^T;  grads.wx += X^T dH;  grads.bl += 1^T dH   (tf.gradients through relu + matmul) */
+int tscl_fc_hidden_fwd(tscl_handle* h, const float* params, const float* X, int64_t M, float* H, void* stream);
+int tscl_fc_hidden_bwd(tscl_handle* h, const float* params, const float* X, const float* H, float* dH, int64_t M,
+                       float* dX, float* grads, void* stream);
+
 /* LSTM over T steps (agents/utils.py:88-116): recurrent GEMM h.Wh + fused cell.
  *   ZG   [2A][T*Rc][4h]  in: X.Wx + b (time-major rows m = t*Rc + r); out: gate activations i,f,o,u
  *   C,H  [2A][T*Rc][h]   out (may be NULL when T == 1 and only states are wanted)

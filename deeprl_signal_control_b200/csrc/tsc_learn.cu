@@ -749,98 +749,118 @@ __global__ void rmsprop_kernel(float* __restrict__ p, float* __restrict__ g, flo
 //   backward  dHm = dH * (H > 0) (written back),  dX = dHm . W^T,  g.bl += 1^T dHm     (one kernel)
 //             g.wx += X^T dHm                                                           (row-split kernel, atomics)
 // Tile = 64 rows x 64 columns per CTA of 256 threads (4 x 4 outputs per thread), K staged 32 at a time.
-#define FH_T 64
-#define FH_K 32
+#define FH_T 128           // rows per tile
+#define FH_K 32            // K staged per step of the forward
+// forward: W [dx][64] resident in shared memory for all the row tiles of a CTA; thread = 8 rows x 4 columns
 __global__ void __launch_bounds__(256)
 fc_hidden_fwd_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ X, int64_t M,
                      float* __restrict__ H) {
-  __shared__ float Xs[FH_T][FH_K + 1];
-  __shared__ float Ws[FH_K][FH_T + 4];
+  extern __shared__ float fh_sm[];
+  float* Ws = fh_sm;                               // [dx][64]
+  float* Xs = fh_sm + (size_t)d.dx * H64;          // [FH_T][FH_K + 1]
   const int u = blockIdx.y, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int64_t m0 = (int64_t)blockIdx.x * FH_T;
   const float* W = P + d.off_wx + (int64_t)u * d.dx * H64;
   const float* Xu = X + (int64_t)u * M * d.dx;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < d.dx; k0 += FH_K) {
-    for (int i = tid; i < FH_T * FH_K; i += 256) {
-      const int r = i / FH_K, k = i % FH_K;
-      Xs[r][k] = (m0 + r < M && k0 + k < d.dx) ? Xu[(m0 + r) * d.dx + k0 + k] : 0.f;
-      const int kk = i / FH_T, c = i % FH_T;
-      Ws[kk][c] = (k0 + kk < d.dx) ? W[(int64_t)(k0 + kk) * H64 + c] : 0.f;
+  for (int i = tid; i < d.dx * H64; i += 256) Ws[i] = W[i];
+  const float4 bias = *reinterpret_cast<const float4*>(P + d.off_bl + (int64_t)u * H64 + tx * 4);
+  const int64_t n_tiles = (M + FH_T - 1) / FH_T;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t m0 = tile * FH_T;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    for (int k0 = 0; k0 < d.dx; k0 += FH_K) {
+      __syncthreads();
+      for (int i = tid; i < FH_T * FH_K; i += 256) {
+        const int r = i / FH_K, k = i % FH_K;
+        Xs[r * (FH_K + 1) + k] = (m0 + r < M && k0 + k < d.dx) ? Xu[(m0 + r) * d.dx + k0 + k] : 0.f;
+      }
+      __syncthreads();
+      const int kmax = min(FH_K, d.dx - k0);
+      for (int k = 0; k < kmax; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(Ws + (size_t)(k0 + k) * H64 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = Xs[(ty * 8 + i) * (FH_K + 1) + k];
+          acc[i][0] = fmaf(x, b.x, acc[i][0]); acc[i][1] = fmaf(x, b.y, acc[i][1]);
+          acc[i][2] = fmaf(x, b.z, acc[i][2]); acc[i][3] = fmaf(x, b.w, acc[i][3]);
+        }
+      }
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < FH_K; ++k) {
-      float a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = Xs[ty * 4 + i][k]; b[i] = Ws[k][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-  const float* bias = P + d.off_bl + (int64_t)u * H64;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + ty * 4 + i;
-    if (m < M) {
-      float4 o;
-      o.x = fmaxf(acc[i][0] + bias[tx * 4 + 0], 0.f); o.y = fmaxf(acc[i][1] + bias[tx * 4 + 1], 0.f);
-      o.z = fmaxf(acc[i][2] + bias[tx * 4 + 2], 0.f); o.w = fmaxf(acc[i][3] + bias[tx * 4 + 3], 0.f);
-      *reinterpret_cast<float4*>(H + ((int64_t)u * M + m) * H64 + tx * 4) = o;
+    for (int i = 0; i < 8; ++i) {
+      const int64_t m = m0 + ty * 8 + i;
+      if (m < M)
+        *reinterpret_cast<float4*>(H + ((int64_t)u * M + m) * H64 + tx * 4) =
+            make_float4(fmaxf(acc[i][0] + bias.x, 0.f), fmaxf(acc[i][1] + bias.y, 0.f), fmaxf(acc[i][2] + bias.z, 0.f),
+                        fmaxf(acc[i][3] + bias.w, 0.f));
     }
   }
 }
 
-// dHm = dH * (H > 0) in place, dX[m][n-tile] = dHm[m][0:64] . W^T, bias gradient += column sums of dHm (n-tile 0 only)
+// dHm = dH * (H > 0) (written back), dX = dHm . W^T in column passes of 64, bias gradient += column sums of dHm;
+// W^T [64][dx] resident in shared memory for all the row tiles of a CTA
 __global__ void __launch_bounds__(256)
 fc_hidden_bwd_dx_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ H, float* __restrict__ dH,
                         int64_t M, float* __restrict__ dX, float* __restrict__ G) {
-  __shared__ float Ds[FH_T][H64 + 1];         // masked dH tile [64 rows][64]
-  __shared__ float Ws[FH_T][H64 + 1];         // W rows of this n-tile: Ws[n][k] = W[n0 + n][k]
+  extern __shared__ float fh_sm[];
+  float* Wt = fh_sm;                               // [64][dxp]   Wt[k][n] = W[n][k], dxp = dx rounded up to 64
+  const int dxp = (d.dx + 63) & ~63;
+  float* Ds = fh_sm + (size_t)H64 * dxp;           // [FH_T][65]
   const int u = blockIdx.y, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int n_tiles = (d.dx + FH_T - 1) / FH_T;
-  const int64_t m0 = (int64_t)(blockIdx.x / n_tiles) * FH_T;
-  const int n0 = (int)(blockIdx.x % n_tiles) * FH_T;
   const float* W = P + d.off_wx + (int64_t)u * d.dx * H64;
-  for (int i = tid; i < FH_T * H64; i += 256) {
-    const int r = i >> 6, k = i & 63;
-    float v = 0.f;
-    if (m0 + r < M) {
-      const int64_t o = ((int64_t)u * M + m0 + r) * H64 + k;
-      v = H[o] > 0.f ? dH[o] : 0.f;
-      if (n0 == 0) dH[o] = v;                 // the weight-gradient kernel reads the masked gradient
+  for (int i = tid; i < H64 * dxp; i += 256) {
+    const int k = i / dxp, n = i % dxp;
+    Wt[i] = n < d.dx ? W[(int64_t)n * H64 + k] : 0.f;
+  }
+  float bsum = 0.f;                                // threads 0..63: bias-gradient column sums over this CTA's tiles
+  const int64_t n_tiles = (M + FH_T - 1) / FH_T;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t m0 = tile * FH_T;
+    __syncthreads();
+    for (int i = tid; i < FH_T * H64; i += 256) {
+      const int r = i >> 6, k = i & 63;
+      float v = 0.f;
+      if (m0 + r < M) {
+        const int64_t o = ((int64_t)u * M + m0 + r) * H64 + k;
+        v = H[o] > 0.f ? dH[o] : 0.f;
+        dH[o] = v;                                 // the weight-gradient kernel reads the masked gradient
+      }
+      Ds[r * 65 + k] = v;
     }
-    Ds[r][k] = v;
-    Ws[r][k] = (n0 + r < d.dx) ? W[(int64_t)(n0 + r) * H64 + k] : 0.f;
+    __syncthreads();
+    if (tid < H64) {
+      float sum = 0.f;
+      for (int r = 0; r < FH_T; ++r) sum += Ds[r * 65 + tid];
+      bsum += sum;
+    }
+    for (int n0 = 0; n0 < d.dx; n0 += 64) {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+#pragma unroll 4
+      for (int k = 0; k < H64; ++k) {
+        const float4 b = *reinterpret_cast<const float4*>(Wt + (size_t)k * dxp + n0 + tx * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x = Ds[(ty * 8 + i) * 65 + k];
+          acc[i][0] = fmaf(x, b.x, acc[i][0]); acc[i][1] = fmaf(x, b.y, acc[i][1]);
+          acc[i][2] = fmaf(x, b.z, acc[i][2]); acc[i][3] = fmaf(x, b.w, acc[i][3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + ty * 8 + i;
+        if (m < M) {
+          float* o = dX + ((int64_t)u * M + m) * d.dx + n0 + tx * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n0 + tx * 4 + j < d.dx) o[j] = acc[i][j];
+        }
+      }
+    }
   }
-  __syncthreads();
-  float acc[4][4] = {};
-#pragma unroll 8
-  for (int k = 0; k < H64; ++k) {
-    float a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { a[i] = Ds[ty * 4 + i][k]; b[i] = Ws[tx * 4 + i][k]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + ty * 4 + i;
-    if (m < M)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (n0 + tx * 4 + j < d.dx) dX[((int64_t)u * M + m) * d.dx + n0 + tx * 4 + j] = acc[i][j];
-  }
-  if (n0 == 0 && tid < H64) {                 // bias gradient: one atomic per column and CTA
-    float sum = 0.f;
-    for (int r = 0; r < FH_T; ++r) sum += Ds[r][tid];
-    atomicAdd(G + d.off_bl + (int64_t)u * H64 + tid, sum);
-  }
+  if (tid < H64) atomicAdd(G + d.off_bl + (int64_t)u * H64 + tid, bsum);
 }
 
 // g.wx[u][k][c] += sum_m X[u][m][k] * dHm[u][m][c] over the CTA's row slice; thread = (k-group, 4 columns)
@@ -977,9 +997,18 @@ extern "C" int tscl_fc_embed(tscl_handle* h, const float* params, const float* o
 
 extern "C" int tscl_fc_hidden_fwd(tscl_handle* h, const float* params, const float* X, int64_t M, float* H, void* stream) {
   if (!h || !params || !X || !H || M <= 0) return tsc_set_error("tscl_fc_hidden_fwd: bad argument");
+  if (h->d.dx > 256) return tsc_set_error("tscl_fc_hidden_fwd: dx > 256");
   LCK(cudaSetDevice(h->device));
-  dim3 grid((unsigned)((M + FH_T - 1) / FH_T), 2 * h->d.A);
-  fc_hidden_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d, params, X, M, H);
+  static int attr_dev = -1;
+  if (attr_dev != h->device) {
+    LCK(cudaFuncSetAttribute(fc_hidden_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    LCK(cudaFuncSetAttribute(fc_hidden_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_dev = h->device;
+  }
+  const int64_t n_tiles = (M + FH_T - 1) / FH_T;
+  dim3 grid((unsigned)(n_tiles < 16 ? n_tiles : 16), 2 * h->d.A);      // 16 x 2A persistent CTAs: W is loaded once per CTA
+  const size_t smem = ((size_t)h->d.dx * H64 + (size_t)FH_T * (FH_K + 1)) * sizeof(float);
+  fc_hidden_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(h->d, params, X, M, H);
   LCK(cudaGetLastError());
   return 0;
 }
@@ -989,20 +1018,23 @@ extern "C" int tscl_fc_hidden_bwd(tscl_handle* h, const float* params, const flo
   if (!h || !params || !X || !H || !dH || !dX || !grads || M <= 0) return tsc_set_error("tscl_fc_hidden_bwd: bad argument");
   if (h->d.dx > 256) return tsc_set_error("tscl_fc_hidden_bwd: dx > 256");
   LCK(cudaSetDevice(h->device));
-  const int n_tiles = (h->d.dx + FH_T - 1) / FH_T;
-  dim3 g1((unsigned)(((M + FH_T - 1) / FH_T) * n_tiles), 2 * h->d.A);
-  fc_hidden_bwd_dx_kernel<<<g1, 256, 0, (cudaStream_t)stream>>>(h->d, params, H, dH, M, dX, grads);
+  static int attr_dev = -1;
+  if (attr_dev != h->device) {
+    LCK(cudaFuncSetAttribute(fc_hidden_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    LCK(cudaFuncSetAttribute(fc_hidden_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+    attr_dev = h->device;
+  }
+  const int64_t n_tiles = (M + FH_T - 1) / FH_T;
+  dim3 g1((unsigned)(n_tiles < 16 ? n_tiles : 16), 2 * h->d.A);
+  const int dxp = (h->d.dx + 63) & ~63;
+  const size_t smem1 = ((size_t)H64 * dxp + (size_t)FH_T * 65) * sizeof(float);
+  fc_hidden_bwd_dx_kernel<<<g1, 256, smem1, (cudaStream_t)stream>>>(h->d, params, H, dH, M, dX, grads);
   LCK(cudaGetLastError());
   int64_t splits = (M + 2047) / 2048;
   if (splits > 64) splits = 64;
   const int64_t rows_per = ((M + splits - 1) / splits + FH_WROWS - 1) / FH_WROWS * FH_WROWS;
   dim3 g2((unsigned)((M + rows_per - 1) / rows_per), 2 * h->d.A);
   const size_t smem = (size_t)FH_WROWS * (h->d.dx + H64) * sizeof(float);
-  static int attr_dev = -1;
-  if (attr_dev != h->device) {
-    LCK(cudaFuncSetAttribute(fc_hidden_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
-    attr_dev = h->device;
-  }
   fc_hidden_wgrad_kernel<<<g2, 256, smem, (cudaStream_t)stream>>>(h->d, X, dH, M, rows_per, grads);
   LCK(cudaGetLastError());
   return 0;

@@ -177,6 +177,7 @@ struct StepTC {
   // replica-range launches (v2 only): the per-unit state arrays have `ld` rows per unit (0: R) and the activation
   // store is indexed by the absolute replica row0 + r; every pointer is the base of the range's slice
   int64_t ld, row0;
+  unsigned long long* prof;   // optional: per-phase clock64 sums of thread 0 of every CTA (tools/profile only)
 };
 
 extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -485,7 +486,7 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
   a.h_out = h_out; a.pi = pi; a.val = val; a.act = act; a.zdbg = zdbg; a.R = R; a.done = done;
   a.swap_lbo_sbo = swap_lbo_sbo; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
   a.step = (uint32_t)step; a.replica0 = replica0;
-  a.st_x = a.st_g = a.st_c = a.st_h = nullptr; a.t = 0; a.T = 1; a.rc = R;
+  a.st_x = a.st_g = a.st_c = a.st_h = nullptr; a.t = 0; a.T = 1; a.rc = R; a.prof = nullptr;
   policy_step_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
@@ -501,7 +502,7 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
 // NT = 256: thread = (replica row, 32 hidden units); NT = 512: thread = (replica row, 16 hidden units) — twice the warps
 // per SM for the latency-bound staging / epilogue phases (one CTA per SM either way: the weight operand fills shared
 // memory), same arithmetic per element, so both variants produce identical bits.
-template <int NT>
+template <int NT, bool PROF>
 __global__ void __launch_bounds__(NT, 1)
 policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
   constexpr int NG = NT / 128;                 // hidden-unit groups per row (2 or 4)
@@ -541,6 +542,9 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
   int nw = 0, nt = 0, nf = 0, ooff = 0, na = 0;
   const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
 
+  long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
+#define PROF_MARK(i) do { if (PROF && tid == 0) { const long long c_ = clock64(); pt[i] += c_ - pc; pc = c_; } } while (0)
+  if (PROF && tid == 0) pc = clock64();
   for (int64_t it = it_lo; it < it_hi; ++it) {
     const int u = (int)(it / n_tiles);
     const int64_t r0 = (it - (int64_t)u * n_tiles) * TC_M;
@@ -575,6 +579,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         sBias0[i] = b0;
       }
     }
+    PROF_MARK(0);      // item-top sync + per-unit weight / constant (re)load
     // L2 prefetch of the NEXT work item's operands (observation slice, c, h): they are consumed ~one tile later
     if (it + 1 < it_hi) {
       const int un = (int)((it + 1) / n_tiles);
@@ -616,6 +621,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    PROF_MARK(1);      // staging: fc weights + observation slice
     // ---- 2. MMA0: D0[128 x dx] = A0[128 x 64] . B0[64 x dx]  (TMEM columns 256..) ----
     if (warp == 0) {
       if (lane == 0) {
@@ -632,6 +638,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    PROF_MARK(2);      // MMA0 issue + wait
     // ---- 3. X = relu(D0 + b) as bf16 -> A tile chunks 0..dx/8 ; h_prev -> last 8 chunks ----
     {
       const int q = warp & 3, hw = warp >> 2;
@@ -668,6 +675,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    PROF_MARK(3);      // relu epilogue of the fc GEMM (+ st_x) and h staging
     // ---- 4. MMA1: gates D1[128 x 256] = [X | h][128 x K] . [Wx;Wh][K x 256] ----
     if (warp == 0) {
       if (lane == 0) {
@@ -682,6 +690,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    PROF_MARK(4);      // gate MMA issue + wait
     // ---- 5. epilogue (identical to v1) ----
     {
       const int q = warp & 3, half = warp >> 2;
@@ -767,6 +776,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         for (int j = 0; j < 8; ++j) sRed2[((half - 2) * TC_M + row) * 8 + j] = lg[j];
       }
       __syncthreads();
+      PROF_MARK(5);    // cell + stores + head partial sums
       if (half == 0 && valid) {
         if (NG == 2) {
 #pragma unroll
@@ -806,14 +816,357 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       }
     }
   }
+  PROF_MARK(6);        // head softmax / sampling of the last item
+  if (PROF && tid == 0)
+    for (int i = 0; i < 7; ++i) atomicAdd(a.prof + i, (unsigned long long)pt[i]);
+#undef PROF_MARK
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ===================================================================================================
+// v3: the same fused step with the weight operand STREAMED instead of resident, so that TWO CTAs share an SM and
+// overlap each other's serial phases (v2 holds the 147 KB [Wx;Wh] image in shared memory: one CTA per SM, every
+// latency exposed).
+//   * [Wx;Wh] of the current unit stays in L2 (7.4 MB for all 50 units); its 18 K-slabs of 8 KB travel through a
+//     4-stage ring in shared memory by cp.async.bulk (TMA unit, mbarrier complete_tx), issued and consumed by ONE
+//     thread, which also issues the tcgen05.mma of each slab and commits it to the slab's "empty" barrier;
+//     the first slabs of the NEXT work item and its fc-weight block are prefetched while the current item is in its
+//     epilogue;
+//   * TMEM: 256 columns per CTA (two CTAs = 512): the fc accumulator D0 (dx columns) and the gate accumulator D1 (256)
+//     share them, D0 is dead once X has been written to the A tile;
+//   * shared memory 112 KB per CTA: A tile 72 KB | ring 32 KB | biases, head weights, partial head sums.
+// Arithmetic per element is identical to v2: the two kernels produce the same bits.
+#define V3_NSTG 4
+#define V3_SLAB 8192
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+policy_step_tc3_kernel(const DDimsTC d, const StepTC a) {
+  constexpr int NT = 256, NG = 2, HPT = 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = d.dx + TC_H, KC = K / 8, KS = K / 16, KCX = d.dx / 8;
+  unsigned char* sA = tc_smem;                                  // KC * 2048
+  unsigned char* sR = sA + (size_t)KC * 2048;                   // ring: V3_NSTG * 8192
+  float* sRed = reinterpret_cast<float*>(sR + V3_NSTG * V3_SLAB);   // [128][8]
+  float* sWo = sRed + TC_M * 8;                                 // [64][8]
+  float* sBo = sWo + TC_H * 8;                                  // [8]
+  float* sBias = sBo + 8;                                       // [256]  lstm bias
+  float* sBias0 = sBias + TC_N;                                 // [256]  fc biases
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sBias0 + TC_N);  // [0] mma done, [1] fc weights landed, [2..5] full, [6..9] empty
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2 + 2 * V3_NSTG);
+  const uint32_t bar_mma = smem_u32(sBar), bar_fc = smem_u32(sBar + 1);
+  const uint32_t bar_full = smem_u32(sBar + 2), bar_empty = smem_u32(sBar + 2 + V3_NSTG);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar_mma, 1); mbar_init(bar_fc, 1);
+    for (int s = 0; s < V3_NSTG; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.dx >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  const int64_t n_tiles = (a.R + TC_M - 1) / TC_M;
+  const int64_t ld = a.ld > 0 ? a.ld : a.R;
+  const int64_t n_items = n_tiles * 2 * d.A;
+  const int64_t it_lo = n_items * blockIdx.x / gridDim.x, it_hi = n_items * (blockIdx.x + 1) / gridDim.x;
+  int cur_u = -1;
+  uint32_t par_mma = 0, par_fc = 0;
+  uint32_t n_issue = 0, n_cons = 0;            // thread 0: slabs issued / consumed since the kernel started
+  int nw = 0, nt = 0, nf = 0, ooff = 0, na = 0;
+  const uint32_t aA = smem_u32(sA), aR = smem_u32(sR);
+  const uint32_t fc_bytes = (uint32_t)(8 * d.dx * 16);
+
+  // thread 0 only: stream slab `ks` of unit `u` into the next ring stage (waits until the MMA that last read it is done)
+  auto issue_slab = [&](int u, int ks) {
+    const uint32_t s = n_issue % V3_NSTG, k = n_issue / V3_NSTG;
+    if (k > 0) mbar_wait(bar_empty + 8 * s, (k - 1) & 1);
+    mbar_expect_tx(bar_full + 8 * s, V3_SLAB);
+    bulk_g2s(aR + s * V3_SLAB, reinterpret_cast<const unsigned char*>(a.Wp + (int64_t)u * wp_stride(d.dx)) + (size_t)ks * V3_SLAB,
+             V3_SLAB, bar_full + 8 * s);
+    ++n_issue;
+  };
+  const int n_pre = KS < V3_NSTG ? KS : V3_NSTG;
+  if (tid == 0 && it_lo < it_hi) {             // first work item: fc weights + the first slabs
+    const int u0 = (int)(it_lo / n_tiles);
+    mbar_expect_tx(bar_fc, fc_bytes);
+    bulk_g2s(aA, reinterpret_cast<const unsigned char*>(a.Wp + (int64_t)u0 * wp_stride(d.dx)) + (size_t)KC * 4096, fc_bytes, bar_fc);
+    for (int ks = 0; ks < n_pre; ++ks) issue_slab(u0, ks);
+  }
+
+  for (int64_t it = it_lo; it < it_hi; ++it) {
+    const int u = (int)(it / n_tiles);
+    const int64_t r0 = (it - (int64_t)u * n_tiles) * TC_M;
+    const int ag = u >> 1;
+    const int64_t st_c0 = (a.row0 + r0) / a.rc, st_rin0 = (a.row0 + r0) - st_c0 * a.rc;
+    auto store_row = [&](int row) -> int64_t {
+      int64_t c = st_c0, rin = st_rin0 + row;
+      while (rin >= a.rc) { rin -= a.rc; ++c; }
+      return ((c * (2 * d.A) + u) * a.T + a.t) * a.rc + rin;
+    };
+    if (u != cur_u) {      // per-unit constants (sRed / sWo / biases are not touched by the async copies in flight)
+      __syncthreads();     // previous item's epilogue has finished reading them
+      cur_u = u;
+      nw = d.n_wave[ag]; nt = d.n_wait[ag]; nf = d.ff > 0 ? d.n_fp[ag] : 0;
+      ooff = d.obs_off[ag]; na = d.n_a[ag];
+      for (int i = tid; i < TC_H * 8; i += NT) {
+        const int k = i >> 3, j = i & 7;
+        sWo[i] = j < d.max_na ? a.P[d.off_wo + ((int64_t)u * TC_H + k) * d.max_na + j] : 0.f;
+      }
+      if (tid < 8) sBo[tid] = tid < d.max_na ? a.P[d.off_bo + (int64_t)u * d.max_na + tid] : 0.f;
+      for (int i = tid; i < TC_N; i += NT) {
+        sBias[i] = a.P[d.off_bl + (int64_t)u * TC_N + i];
+        float b0 = 0.f;
+        if (i < d.fw) b0 = a.P[d.off_fcw_b[u] + i];
+        else if (i < d.fw + d.ff) b0 = a.P[d.off_fcf_b[u] + (i - d.fw)];
+        else if (i < d.dx) b0 = a.P[d.off_fct_b[u] + (i - d.fw - d.ff)];
+        sBias0[i] = b0;
+      }
+    }
+    if (it + 1 < it_hi) {      // L2 prefetch of the next item's observation slice and state rows
+      const int un = (int)((it + 1) / n_tiles);
+      const int64_t rn = ((it + 1) - (int64_t)un * n_tiles) * TC_M + (tid / NG);
+      if (rn < a.R) {
+        const int an = un >> 1;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.obs + rn * d.n_obs + d.obs_off[an] + (tid % NG) * 32));
+        const int64_t so = ((int64_t)un * ld + rn) * TC_H + (tid % NG) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.c_in + so));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.h_in + so));
+      }
+    }
+    // ---- 1. observation slice -> last 8 chunks of the A tile (the fc weights arrive by bulk copy in chunks 0..) ----
+#pragma unroll
+    for (int p = 0; p < 1024 / NT; ++p) {
+      const int pair = p * NT + tid;
+      const int row = pair & 127, ch = pair >> 7;
+      const int64_t r = r0 + row;
+      __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = ch * 8 + e;
+        int src = -1;
+        if (c < d.kw) { if (c < nw) src = c; }
+        else if (c < d.kw + TC_KF) { if (c - d.kw < nf) src = nw + nt + (c - d.kw); }
+        else { if (c - d.kw - TC_KF < nt) src = nw + (c - d.kw - TC_KF); }
+        float x = 0.f;
+        if (src >= 0 && r < a.R) x = __ldg(a.obs + r * d.n_obs + ooff + src);
+        v[e] = __float2bfloat16_rn(x);
+      }
+      *reinterpret_cast<uint4*>(sA + (size_t)(KC - 8 + ch) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 2. MMA0: D0[128 x dx] = A0[128 x 64] . B0[64 x dx]  (TMEM columns 0..dx) ----
+    if (tid == 0) {
+      mbar_wait(bar_fc, par_fc);               // fc weights of this item have landed in chunks 0..
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t da = make_desc(aA + (KC - 8 + 2 * ks) * 2048, 2048, 128);
+        const uint64_t db = make_desc(aA + ks * 2 * (d.dx * 16), d.dx * 16, 128);
+        umma_bf16(tmem, da, db, idesc0, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_mma);
+    }
+    par_fc ^= 1;
+    mbar_wait(bar_mma, par_mma);
+    par_mma ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- 3. X = relu(D0 + b) as bf16 -> A tile chunks 0..dx/8 ; h_prev -> the 8 chunks after them ----
+    {
+      const int q = warp & 3, hw = warp >> 2;
+      const int row = q * 32 + lane;
+      const int ncol = d.dx / NG;
+      const bool st = a.st_x && r0 + row < a.R;
+      const int64_t m = st ? store_row(row) : 0;
+      for (int c0 = hw * ncol; c0 < (hw + 1) * ncol; c0 += 8) {
+        float z[8];
+        tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, z);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
+        *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+        if (st) *reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0)) = *reinterpret_cast<const uint4*>(v);
+      }
+    }
+    {
+      const int row = tid / NG, half = tid % NG;
+      const int64_t r = r0 + row;
+      const bool live = r < a.R && !a.done;
+      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * ld + (r < a.R ? r : 0)) * TC_H + half * HPT);
+#pragma unroll
+      for (int c8 = 0; c8 < HPT / 8; ++c8) {
+        __align__(16) __nv_bfloat16 v[8];
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+        if (live) { x0 = hp[2 * c8]; x1 = hp[2 * c8 + 1]; }
+        v[0] = __float2bfloat16_rn(x0.x); v[1] = __float2bfloat16_rn(x0.y); v[2] = __float2bfloat16_rn(x0.z); v[3] = __float2bfloat16_rn(x0.w);
+        v[4] = __float2bfloat16_rn(x1.x); v[5] = __float2bfloat16_rn(x1.y); v[6] = __float2bfloat16_rn(x1.z); v[7] = __float2bfloat16_rn(x1.w);
+        *reinterpret_cast<uint4*>(sA + (size_t)(KCX + half * (HPT / 8) + c8) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 4. MMA1: gates D1[128 x 256] = [X | h][128 x K] . [Wx;Wh][K x 256], B slabs through the ring ----
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t s = n_cons % V3_NSTG, k = n_cons / V3_NSTG;
+        mbar_wait(bar_full + 8 * s, k & 1);
+        umma_bf16(tmem, make_desc(aA + ks * 2 * 2048, 2048, 128), make_desc(aR + s * V3_SLAB, 4096, 128), idesc1,
+                  ks > 0 ? 1u : 0u);
+        umma_commit(bar_empty + 8 * s);
+        ++n_cons;
+        if (ks >= 1 && ks - 1 + V3_NSTG < KS) issue_slab(u, ks - 1 + V3_NSTG);   // refill the stage MMA(ks-1) has left
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, par_mma);
+    par_mma ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && it + 1 < it_hi) {          // the A tile and the ring are free: start the next item's operands now
+      const int un = (int)((it + 1) / n_tiles);
+      mbar_expect_tx(bar_fc, fc_bytes);
+      bulk_g2s(aA, reinterpret_cast<const unsigned char*>(a.Wp + (int64_t)un * wp_stride(d.dx)) + (size_t)KC * 4096, fc_bytes, bar_fc);
+      for (int ks = 0; ks < n_pre; ++ks) issue_slab(un, ks);
+    }
+    // ---- 5. epilogue (as v2, NT = 256) ----
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int row = q * 32 + lane;
+      const int64_t r = r0 + row;
+      const bool valid = r < a.R;
+      const int64_t srow = ((int64_t)u * ld + (valid ? r : 0)) * TC_H + half * HPT;
+      float lg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) lg[j] = 0.f;
+#pragma unroll 1
+      for (int jb = 0; jb < HPT / 16; ++jb) {
+        float zi[16], zf[16], zo[16], zu[16];
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HPT + jb * 16);
+        tmem_ld16(tbase, zi); tmem_ld16(tbase + 64, zf); tmem_ld16(tbase + 128, zo); tmem_ld16(tbase + 192, zu);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float cprev[16];
+        if (valid && !a.done) {
+          const float4* cp = reinterpret_cast<const float4*>(a.c_in + srow + jb * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 x = cp[e4];
+            cprev[4 * e4] = x.x; cprev[4 * e4 + 1] = x.y; cprev[4 * e4 + 2] = x.z; cprev[4 * e4 + 3] = x.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cprev[e] = 0.f;
+        }
+        float cn[16], hn[16];
+        __align__(16) __nv_bfloat16 gbuf[4][16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int j = half * HPT + jb * 16 + e;
+          const float gi = sigm(zi[e] + sBias[j]), gf = sigm(zf[e] + sBias[64 + j]);
+          const float go = sigm(zo[e] + sBias[128 + j]), gu = tanh_fast(zu[e] + sBias[192 + j]);
+          cn[e] = gf * cprev[e] + gi * gu;
+          hn[e] = go * tanh_fast(cn[e]);
+          gbuf[0][e] = __float2bfloat16_rn(gi); gbuf[1][e] = __float2bfloat16_rn(gf);
+          gbuf[2][e] = __float2bfloat16_rn(go); gbuf[3][e] = __float2bfloat16_rn(gu);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
+        }
+        if (valid && a.st_g) {
+          const int64_t m = store_row((int)(r - r0));
+          const int jo = half * HPT + jb * 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4* o = reinterpret_cast<uint4*>(a.st_g + m * TC_N + g * 64 + jo);
+            o[0] = *reinterpret_cast<const uint4*>(&gbuf[g][0]); o[1] = *reinterpret_cast<const uint4*>(&gbuf[g][8]);
+          }
+          __align__(16) __nv_bfloat16 cb[16], hb[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { cb[e] = __float2bfloat16_rn(cn[e]); hb[e] = __float2bfloat16_rn(hn[e]); }
+          uint4* oc = reinterpret_cast<uint4*>(a.st_c + m * TC_H + jo);
+          uint4* oh = reinterpret_cast<uint4*>(a.st_h + m * TC_H + jo);
+          oc[0] = *reinterpret_cast<const uint4*>(cb); oc[1] = *reinterpret_cast<const uint4*>(cb + 8);
+          oh[0] = *reinterpret_cast<const uint4*>(hb); oh[1] = *reinterpret_cast<const uint4*>(hb + 8);
+        }
+        if (valid) {
+          float4* co = reinterpret_cast<float4*>(a.c_out + srow + jb * 16);
+          float4* ho = reinterpret_cast<float4*>(a.h_out + srow + jb * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            co[e4] = make_float4(cn[4 * e4], cn[4 * e4 + 1], cn[4 * e4 + 2], cn[4 * e4 + 3]);
+            ho[e4] = make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (half == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
+      }
+      __syncthreads();       // also: every thread is done with TMEM -> the next item's MMA0 may overwrite D
+      if (half == 0 && valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lg[j] += sRed[row * 8 + j] + sBo[j];
+        if ((u & 1) == 0) {
+          float mx = -1e30f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < na) mx = fmaxf(mx, lg[j]);
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lg[j] = j < na ? __expf(lg[j] - mx) : 0.f; s += lg[j]; }
+          const float inv = 1.0f / s;
+          float* po = a.pi + ((int64_t)r * d.A + ag) * d.max_na;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < d.max_na) po[j] = lg[j] * inv;
+          if (a.act) {
+            uint32_t hsh = pmix32(a.seed_lo ^ (a.step * 0x9E3779B1U));
+            hsh = pmix32(hsh ^ a.seed_hi ^ ((uint32_t)(a.replica0 + r) * 0x85EBCA77U));
+            hsh = pmix32(hsh ^ ((uint32_t)ag * 0xC2B2AE3DU));
+            const float uu = (float)(hsh >> 8) * (1.0f / 16777216.0f);
+            float cum = 0.f;
+            int pick = na - 1;
+            bool found = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < na) { cum += lg[j] * inv; if (!found && uu < cum) { pick = j; found = true; } }
+            a.act[(int64_t)r * d.A + ag] = pick;
+          }
+        } else {
+          a.val[(int64_t)r * d.A + ag] = lg[0];
+        }
+      }
+      __syncthreads();       // sRed is rewritten by the next item's epilogue only, but its head reads must finish first
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+static size_t tc3_smem_bytes(int K) {
+  const int KC = K / 8;
+  return (size_t)KC * 2048 + V3_NSTG * V3_SLAB + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + (2 + 2 * V3_NSTG) * 8 + 16;
 }
 
 static size_t tc2_smem_bytes(int K) {
   const int KC = K / 8;
   return (size_t)KC * 4096 + (size_t)KC * 2048 + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + 16;
 }
+
+static unsigned long long* g_policy_prof = nullptr;
+// tools only: device pointer to 8 uint64 counters that receive per-phase clock64 sums of the v2 kernel (NULL = off)
+extern "C" int tscl_debug_policy_prof(void* counters_dev) { g_policy_prof = (unsigned long long*)counters_dev; return 0; }
 
 extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs,
                                    int64_t R, const float* c_in, const float* h_in, float* c_out, float* h_out,
@@ -833,8 +1186,9 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
   if (smem > 232448) return tsc_set_error("tscl_policy_step_v2r: operand tiles exceed shared memory");
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {
-    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCK(cudaFuncSetAttribute(policy_step_tc2_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_dev = tscl_device_of(h);
   }
   int n_sm = 0;
@@ -847,10 +1201,24 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.step = (uint32_t)step; a.replica0 = replica0;
   a.st_x = (__nv_bfloat16*)st_x; a.st_g = (__nv_bfloat16*)st_g; a.st_c = (__nv_bfloat16*)st_c; a.st_h = (__nv_bfloat16*)st_h;
   a.t = t; a.T = T > 0 ? T : 1; a.rc = rc > 0 ? rc : R; a.ld = ld_state; a.row0 = ld_state > 0 ? row0 : 0;
-  // TSC_POLICY_THREADS=256 selects the round-1 mapping (thread = row x 32 hidden units) for A/B measurements
+  a.prof = g_policy_prof;
+  // default: the resident-weight kernel v2 (512 threads; TSC_POLICY_THREADS=256 = its round-1 thread mapping).
+  // TSC_POLICY_V3=1 selects the streamed-weight two-CTA-per-SM kernel: measured 1.404 vs 1.342 ms of rollout per control
+  // step at R = 8192 (policy kernel ~0.63 vs 0.57 ms), i.e. slower, so it is not the default
+  static const int pol_v3 = []() { const char* e = getenv("TSC_POLICY_V3"); return e ? atoi(e) : 0; }();
   static const int pol_threads = []() { const char* e = getenv("TSC_POLICY_THREADS"); return e && atoi(e) == 256 ? 256 : 512; }();
-  if (pol_threads == 512) policy_step_tc2_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
-  else policy_step_tc2_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
+  if (pol_v3 && !zdbg) {
+    const size_t smem3 = tc3_smem_bytes(K);
+    static int attr3_dev = -1;
+    if (attr3_dev != tscl_device_of(h)) {
+      PCK(cudaFuncSetAttribute(policy_step_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      attr3_dev = tscl_device_of(h);
+    }
+    const int grid3 = (int)(n_items < 2 * n_sm ? n_items : 2 * n_sm);       // two CTAs per SM
+    policy_step_tc3_kernel<<<grid3, 256, smem3, (cudaStream_t)stream>>>(d, a);
+  } else if (a.prof) policy_step_tc2_kernel<512, true><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
+  else if (pol_threads == 512) policy_step_tc2_kernel<512, false><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
+  else policy_step_tc2_kernel<256, false><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;
 }

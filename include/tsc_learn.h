@@ -157,6 +157,10 @@ int tscl_unpack_store(tscl_handle* h, const void* st_x, const void* st_g, const 
                       float* ZG, float* C, float* H, float* Hp, const float* h0, const float* done, int32_t T,
                       int64_t rc, int64_t ld_state, int64_t r0, void* stream);
 
+/* Tools only (scripts/profile_policy_phases.py): per-phase clock64 sums of tscl_policy_step_v2 are added to 8 uint64
+ * device counters while the pointer is set (NULL = off; a separate instantiation of the kernel, the hot one is unchanged). */
+int tscl_debug_policy_prof(void* counters_dev);
+
 /* Per-agent clip_by_global_norm(max_norm) + RMSProp step (TF1 semantics).  agent_of [n_params] u8.
  * norms [A] receives the pre-clip global norms. */
 int tscl_clip_rmsprop(tscl_handle* h, float* params, float* grads, float* ms, const uint8_t* agent_of,

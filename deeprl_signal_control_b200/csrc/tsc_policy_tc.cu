@@ -738,6 +738,75 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
         }
+        if constexpr (NT == 512) {
+          // Coalesced copy-out through the A tile (dead once the gate MMA has been committed): a thread owns a ROW, so
+          // its direct stores are 16-byte pieces 128-512 B apart (32 sectors per warp instruction: the phase profile
+          // showed stores as ~half of the kernel).  Each array is staged as [row][16-byte chunk ^ (row & mask)] (the XOR
+          // keeps both the row-owner writes and the chunk-per-lane reads free of bank conflicts) and written out with
+          // one warp instruction per contiguous 512 B of a row.
+          unsigned char* stg = sA;
+          const int sw = row & 31;
+          const bool do_store = a.st_g != nullptr;                       // uniform
+          if (do_store) {                                                // ---- gates [128][512 B]
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int c = g * 8 + half * 2;
+              *reinterpret_cast<uint4*>(stg + row * 512 + ((c ^ sw) << 4)) = *reinterpret_cast<const uint4*>(&gbuf[g][0]);
+              *reinterpret_cast<uint4*>(stg + row * 512 + (((c + 1) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(&gbuf[g][8]);
+            }
+          }
+          __syncthreads();
+          if (do_store) {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int rw = warp * 8 + rr;
+              if (r0 + rw < a.R) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rw * 512 + ((lane ^ (rw & 31)) << 4));
+                *reinterpret_cast<uint4*>(a.st_g + store_row(rw) * TC_N + lane * 8) = v;
+              }
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {                               // ---- c_out | h_out fp32 [128][256 B | 256 B]
+            const int c = half * 4 + e4;
+            *reinterpret_cast<float4*>(stg + row * 512 + ((c ^ sw) << 4)) =
+                make_float4(cn[4 * e4], cn[4 * e4 + 1], cn[4 * e4 + 2], cn[4 * e4 + 3]);
+            *reinterpret_cast<float4*>(stg + row * 512 + (((16 + c) ^ sw) << 4)) =
+                make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int rw = warp * 8 + rr;
+            if (r0 + rw < a.R) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + rw * 512 + ((lane ^ (rw & 31)) << 4));
+              float* dst = (lane < 16 ? a.c_out : a.h_out) + ((int64_t)u * ld + r0 + rw) * TC_H + (lane & 15) * 4;
+              *reinterpret_cast<float4*>(dst) = v;
+            }
+          }
+          if (do_store) {                                                // ---- c | h bf16 [128][128 B | 128 B]
+            __syncthreads();
+            __align__(16) __nv_bfloat16 cb[16], hb[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { cb[e] = __float2bfloat16_rn(cn[e]); hb[e] = __float2bfloat16_rn(hn[e]); }
+            const int s2 = row & 15, c = half * 2;
+            *reinterpret_cast<uint4*>(stg + row * 256 + ((c ^ s2) << 4)) = *reinterpret_cast<const uint4*>(cb);
+            *reinterpret_cast<uint4*>(stg + row * 256 + (((c + 1) ^ s2) << 4)) = *reinterpret_cast<const uint4*>(cb + 8);
+            *reinterpret_cast<uint4*>(stg + row * 256 + (((8 + c) ^ s2) << 4)) = *reinterpret_cast<const uint4*>(hb);
+            *reinterpret_cast<uint4*>(stg + row * 256 + (((9 + c) ^ s2) << 4)) = *reinterpret_cast<const uint4*>(hb + 8);
+            __syncthreads();
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const int rw = warp * 8 + rr * 2 + (lane >> 4), l = lane & 15;
+              if (r0 + rw < a.R) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rw * 256 + ((l ^ (rw & 15)) << 4));
+                __nv_bfloat16* dst = (l < 8 ? a.st_c : a.st_h) + store_row(rw) * TC_H + (l & 7) * 8;
+                *reinterpret_cast<uint4*>(dst) = v;
+              }
+            }
+          }
+        } else {
         if (valid && a.st_g) {
           const int64_t m = store_row((int)(r - r0));
           const int jo = half * HPT + jb * 16;
@@ -763,11 +832,12 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
             ho[e4] = make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
           }
         }
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       // partial head sums of groups 1..NG-1: group 1 in sRed, groups 2, 3 (NT = 512) in the A tile, which is dead once
       // the gate MMA has been committed; group 0 adds them in a fixed order (deterministic bits)
-      float* sRed2 = reinterpret_cast<float*>(sA);
+      float* sRed2 = reinterpret_cast<float*>(sA + 65536);      // behind the 64 KB copy-out staging (A tile = 72 KB)
       if (half == 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
@@ -1182,6 +1252,7 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
   if ((d.dx % 32) != 0 || d.dx > 256) return tsc_set_error("tscl_policy_step_v2r: dx must be a multiple of 32, <= 256");
   if (d.kw == 0) return tsc_set_error("tscl_policy_step_v2r: observation slice does not fit the 64-column input tile");
   if (8 * d.dx * 16 > (d.dx / 8) * 2048) return tsc_set_error("tscl_policy_step_v2r: fc operand does not fit its staging region");
+  const bool wide_tile = (size_t)(K / 8) * 2048 >= 65536 + 2 * TC_M * 8 * sizeof(float);   // copy-out staging + partial head sums
   const size_t smem = tc2_smem_bytes(K);
   if (smem > 232448) return tsc_set_error("tscl_policy_step_v2r: operand tiles exceed shared memory");
   static int attr_dev = -1;
@@ -1216,8 +1287,8 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
     }
     const int grid3 = (int)(n_items < 2 * n_sm ? n_items : 2 * n_sm);       // two CTAs per SM
     policy_step_tc3_kernel<<<grid3, 256, smem3, (cudaStream_t)stream>>>(d, a);
-  } else if (a.prof) policy_step_tc2_kernel<512, true><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
-  else if (pol_threads == 512) policy_step_tc2_kernel<512, false><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
+  } else if (a.prof && wide_tile) policy_step_tc2_kernel<512, true><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
+  else if (pol_threads == 512 && wide_tile) policy_step_tc2_kernel<512, false><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
   else policy_step_tc2_kernel<256, false><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;

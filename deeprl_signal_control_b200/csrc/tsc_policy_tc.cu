@@ -95,6 +95,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // MUFU tanh (tanh.approx.f32, max rel. error ~2^-11: below the bf16 operand rounding of this path)
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -517,14 +525,14 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
   float* sBias = sBo + 8;                                       // [256]  lstm bias
   float* sBias0 = sBias + TC_N;                                 // [256]  fc biases
   uint64_t* sBar = reinterpret_cast<uint64_t*>(sBias0 + TC_N);
-  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
-  const uint32_t bar = smem_u32(sBar);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2);
+  const uint32_t bar = smem_u32(sBar), bar_fc = smem_u32(sBar + 1);   // MMA completion; fc-weight bulk copy landed
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar, 1); mbar_init(bar_fc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -538,7 +546,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
   const int64_t n_items = n_tiles * 2 * d.A;
   const int64_t it_lo = n_items * blockIdx.x / gridDim.x, it_hi = n_items * (blockIdx.x + 1) / gridDim.x;
   int cur_u = -1;
-  uint32_t parity = 0;
+  uint32_t parity = 0, par_fc = 0;
   int nw = 0, nt = 0, nf = 0, ooff = 0, na = 0;
   const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
 
@@ -595,9 +603,13 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     }
     // ---- 1a. B0 (fc weights) -> first chunks of the A tile; 1b. observation slice -> last 8 chunks ----
     {
-      const uint4* src0 = reinterpret_cast<const uint4*>(Wu + (int64_t)KC * TC_N * 8);
-      uint4* dst0 = reinterpret_cast<uint4*>(sA);
-      for (int i = tid; i < 8 * d.dx; i += NT) dst0[i] = src0[i];
+      // fc weights (one contiguous 8 * dx * 16-byte block of the packed image) by ONE bulk copy (TMA unit, completion on
+      // bar_fc): it overlaps the observation staging below; only the MMA-issuing thread waits for it
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the epilogue's staging stores precede this async write
+        mbar_expect_tx(bar_fc, (uint32_t)(8 * d.dx * 16));
+        bulk_g2s(aA, reinterpret_cast<const unsigned char*>(Wu + (int64_t)KC * TC_N * 8), (uint32_t)(8 * d.dx * 16), bar_fc);
+      }
       // thread = (row, 16-byte chunk) : 128 x 8 pairs, 4 per thread
 #pragma unroll
       for (int p = 0; p < 1024 / NT; ++p) {
@@ -625,6 +637,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     // ---- 2. MMA0: D0[128 x dx] = A0[128 x 64] . B0[64 x dx]  (TMEM columns 256..) ----
     if (warp == 0) {
       if (lane == 0) {
+        mbar_wait(bar_fc, par_fc);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t da = make_desc(aA + (KC - 8 + 2 * ks) * 2048, 2048, 128);
@@ -635,6 +648,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       }
       __syncwarp();
     }
+    par_fc ^= 1;
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -644,7 +658,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       const int q = warp & 3, hw = warp >> 2;
       const int row = q * 32 + lane;
       const int ncol = d.dx / NG;                      // columns per group (multiple of 8: dx % 32 == 0)
-      const bool st = a.st_x && r0 + row < a.R;
+      const bool st = NT != 512 && a.st_x && r0 + row < a.R;     // NT = 512: X is copied out coalesced in the epilogue
       const int64_t m = st ? store_row(row) : 0;
       for (int c0 = hw * ncol; c0 < (hw + 1) * ncol; c0 += 8) {
         float z[8];
@@ -747,6 +761,31 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
           unsigned char* stg = sA;
           const int sw = row & 31;
           const bool do_store = a.st_g != nullptr;                       // uniform
+          if (do_store) {                                                // ---- X = relu(D0 + b) [128][dx bf16], pitch 512 B
+            // D0 (TMEM columns 256..256+dx) still holds the fc accumulators: recompute the bf16 X of phase 3 (same
+            // operations, same bits) instead of storing it row by row from there
+            const int ncol = d.dx / NG;
+            for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 8) {
+              float z[8];
+              tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
+              *reinterpret_cast<uint4*>(stg + row * 512 + (((c0 >> 3) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(v);
+            }
+            __syncthreads();
+            const int nch = d.dx >> 3;                                   // 16-byte chunks per row (28 for dx = 224)
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int rw = warp * 8 + rr;
+              if (r0 + rw < a.R && lane < nch) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rw * 512 + ((lane ^ (rw & 31)) << 4));
+                *reinterpret_cast<uint4*>(a.st_x + store_row(rw) * d.dx + lane * 8) = v;
+              }
+            }
+            __syncthreads();
+          }
           if (do_store) {                                                // ---- gates [128][512 B]
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -909,14 +948,6 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
 // Arithmetic per element is identical to v2: the two kernels produce the same bits.
 #define V3_NSTG 4
 #define V3_SLAB 8192
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 __global__ void __launch_bounds__(256, 2)
 policy_step_tc3_kernel(const DDimsTC d, const StepTC a) {
   constexpr int NT = 256, NG = 2, HPT = 32;
@@ -1231,7 +1262,7 @@ static size_t tc3_smem_bytes(int K) {
 
 static size_t tc2_smem_bytes(int K) {
   const int KC = K / 8;
-  return (size_t)KC * 4096 + (size_t)KC * 2048 + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + 16;
+  return (size_t)KC * 4096 + (size_t)KC * 2048 + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + 32;
 }
 
 static unsigned long long* g_policy_prof = nullptr;

@@ -1590,6 +1590,202 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// BPTT, staged variant (the activation-store path of the training loop: gates / c from the bf16 store, dZ written as
+// bf16).  Same arithmetic as lstm_bwd_tc_kernel<512>; what changes is how the operands reach the threads.  There a
+// thread owns (row, 16 hidden units) and loads its 16-byte pieces straight from global memory, 128-512 B apart between
+// the lanes of a warp (32 sectors per load instruction: lg_throttle 3.5 and long_scoreboard 10 warps per issue in
+// profiles/r02).  Here each step's tile — gates [128 x 512 B], c_{t-1} [128 x 128 B], dH [128 x 256 B] — is fetched by
+// coalesced 16-byte cp.async (one row segment per warp instruction) into XOR-swizzled shared memory one step AHEAD
+// (issued as soon as every thread has taken step t's operands into registers, landing while step t's cell math, MMA
+// and TMEM read-back run), and the threads pick their pieces from there without bank conflicts.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__global__ void __launch_bounds__(512, 1)
+lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
+  constexpr int NT = 512, HPT = 16, NSUB = 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned char* sB = tc_smem;                       // 32 KB : Wh^T image
+  unsigned char* sA = sB + BW_KC * 1024;             // 64 KB : dz tile (A operand)
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sA + BW_KC * 2048);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
+  unsigned char* sG = sA + BW_KC * 2048 + 16;        // 64 KB : gates [128][32 chunks ^ (row & 31)]
+  unsigned char* sC0 = sG + 128 * 512;               // 16 KB x 2 : c ring, [128][8 chunks ^ (row & 7)]
+  unsigned char* sD = sC0 + 2 * 128 * 128;           // 32 KB : dH fp32 [128][16 chunks ^ (row & 15)]
+  const uint32_t bar = smem_u32(sBar);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_H >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
+  const uint32_t aG = smem_u32(sG), aC = smem_u32(sC0), aD = smem_u32(sD);
+  const int64_t n_tiles = (a.Rc + TC_M - 1) / TC_M;
+  const int64_t n_items = n_tiles * 2 * d.A;
+  int cur_u = -1;
+  uint32_t parity = 0;
+  const int q = warp & 3, qt = warp >> 2;            // TMEM lane quadrant, hidden-unit group (16 units)
+  const int row = q * 32 + lane, jq = qt * HPT;
+  auto bf8 = [](const uint4 v, float* o) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  };
+  for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int u = (int)(it / n_tiles);
+    const int64_t rt0 = (it - (int64_t)u * n_tiles) * TC_M;       // first replica row of the tile
+    const int64_t r = rt0 + row;
+    const bool valid = r < a.Rc;
+    __syncthreads();
+    if (u != cur_u) {
+      cur_u = u;
+      const uint4* src = reinterpret_cast<const uint4*>(a.Wt + (int64_t)u * BW_KC * TC_H * 8);
+      uint4* dst = reinterpret_cast<uint4*>(sB);
+      for (int i = tid; i < BW_KC * TC_H; i += NT) dst[i] = src[i];
+    }
+    // coalesced fetch of one step's tile: rows beyond Rc are clamped to a valid row (their results are never stored)
+    auto fetch = [&](int t, bool with_c_t) {
+      const int64_t mb = ((int64_t)u * a.T + t) * a.Rc;            // row index of replica 0 at step t
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                                // gates: 128 rows x 32 chunks
+        const int id = i * NT + tid, rw = id >> 5, c = id & 31;
+        const int64_t rr = rt0 + rw < a.Rc ? rt0 + rw : a.Rc - 1;
+        cp_async16(aG + rw * 512 + ((c ^ (rw & 31)) << 4), a.Gb + (mb + rr) * TC_N + c * 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                                // dH fp32: 128 rows x 16 chunks
+        const int id = i * NT + tid, rw = id >> 4, c = id & 15;
+        const int64_t rr = rt0 + rw < a.Rc ? rt0 + rw : a.Rc - 1;
+        cp_async16(aD + rw * 256 + ((c ^ (rw & 15)) << 4), a.dH + (mb + rr) * TC_H + c * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {                                // c_{t-1} (and c_t for the first step): 128 rows x 8 chunks
+        const int id = i * NT + tid, rw = id >> 3, c = id & 7;
+        const int64_t rr = rt0 + rw < a.Rc ? rt0 + rw : a.Rc - 1;
+        const uint32_t off = rw * 128 + ((c ^ (rw & 7)) << 4);
+        if (with_c_t) cp_async16(aC + (t & 1) * 16384 + off, a.Cb + (mb + rr) * TC_H + c * 8);
+        if (t > 0) cp_async16(aC + ((t - 1) & 1) * 16384 + off, a.Cb + (mb - a.Rc + rr) * TC_H + c * 8);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(a.T - 1, true);
+    float dc[HPT], dhc[HPT];
+#pragma unroll
+    for (int e = 0; e < HPT; ++e) { dc[e] = 0.f; dhc[e] = 0.f; }
+    for (int t = a.T - 1; t >= 0; --t) {
+      const float keep = 1.0f - a.done[t];
+      const int64_t m = ((int64_t)u * a.T + t) * a.Rc + (valid ? r : 0);
+      if (t > 1) {      // pull step t-2's operands towards L2: they are fetched into shared memory during step t-1
+        const int64_t mp = ((int64_t)u * a.T + t - 2) * a.Rc + (valid ? r : 0);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Gb + mp * TC_N + qt * 64));
+        if (qt == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + mp * TC_H));
+        if (qt >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + (qt - 2) * 32));
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                              // step t's tile is in shared memory
+      const unsigned char* cT = sC0 + (t & 1) * 16384;
+      const unsigned char* cP = sC0 + ((t - 1) & 1) * 16384;
+#pragma unroll
+      for (int jb = 0; jb < NSUB; ++jb) {
+        const int jo = jq + jb * 8;
+        float gi[8], gf[8], go[8], gu[8], ct[8], cp[8], dh[8];
+        {
+          const int cg = jo >> 3, sw = row & 31;     // chunk of 8 hidden units inside each 64-wide gate block
+          bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((cg) ^ sw) << 4)), gi);
+          bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((8 + cg) ^ sw) << 4)), gf);
+          bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((16 + cg) ^ sw) << 4)), go);
+          bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((24 + cg) ^ sw) << 4)), gu);
+          bf8(*reinterpret_cast<const uint4*>(cT + row * 128 + ((cg ^ (row & 7)) << 4)), ct);
+          if (t > 0) bf8(*reinterpret_cast<const uint4*>(cP + row * 128 + ((cg ^ (row & 7)) << 4)), cp);
+          else if (valid) {
+            const float4 x = reinterpret_cast<const float4*>(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo)[0];
+            const float4 y = reinterpret_cast<const float4*>(a.c0 + ((int64_t)u * a.ld_state + a.r0 + r) * TC_H + jo)[1];
+            cp[0] = x.x; cp[1] = x.y; cp[2] = x.z; cp[3] = x.w; cp[4] = y.x; cp[5] = y.y; cp[6] = y.z; cp[7] = y.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cp[e] = 0.f;
+          }
+          const int cd = jo >> 2;                    // dH: 4 floats per chunk
+          const float4 d0 = *reinterpret_cast<const float4*>(sD + row * 256 + ((cd ^ (row & 15)) << 4));
+          const float4 d1 = *reinterpret_cast<const float4*>(sD + row * 256 + (((cd + 1) ^ (row & 15)) << 4));
+          dh[0] = d0.x; dh[1] = d0.y; dh[2] = d0.z; dh[3] = d0.w; dh[4] = d1.x; dh[5] = d1.y; dh[6] = d1.z; dh[7] = d1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cp[e] *= keep;
+          if (!valid) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { gi[e] = gf[e] = go[e] = gu[e] = ct[e] = cp[e] = dh[e] = 0.f; }
+          }
+        }
+        if (jb == NSUB - 1) {      // every thread holds its last operands: the staging buffers can take step t-1
+          __syncthreads();
+          if (t > 0) fetch(t - 1, false);
+        }
+        float dzi[8], dzf[8], dzo[8], dzu[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = jb * 8 + e;
+          const float dht = dh[e] + dhc[k];
+          const float tc = tanh_fast(ct[e]);
+          const float dcc = dc[k] + dht * go[e] * (1.0f - tc * tc);
+          dzi[e] = dcc * gu[e] * gi[e] * (1.0f - gi[e]);
+          dzf[e] = dcc * cp[e] * gf[e] * (1.0f - gf[e]);
+          dzo[e] = dht * tc * go[e] * (1.0f - go[e]);
+          dzu[e] = dcc * gi[e] * (1.0f - gu[e] * gu[e]);
+          dc[k] = dcc * gf[e] * keep;
+        }
+        const float* srcs[4] = {dzi, dzf, dzo, dzu};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(srcs[g][e]);
+          *reinterpret_cast<uint4*>(sA + (size_t)((g * 64 + jo) >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+          if (valid) *reinterpret_cast<uint4*>(a.dZb + m * TC_N + g * 64 + jo) = *reinterpret_cast<const uint4*>(v);
+        }
+      }
+      if (keep != 0.f && t > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+          if (lane == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int ks = 0; ks < 16; ++ks)
+              umma_bf16(tmem, make_desc(aA + ks * 2 * 2048, 2048, 128), make_desc(aB + ks * 2 * 1024, 1024, 128), idesc,
+                        ks > 0 ? 1u : 0u);
+            umma_commit(bar);
+          }
+          __syncwarp();
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float dhp[HPT];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)jq, dhp);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < HPT; ++e) dhc[e] = dhp[e] * keep;
+      } else {
+#pragma unroll
+        for (int e = 0; e < HPT; ++e) dhc[e] = 0.f;
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+}
+
 extern "C" int tscl_pack_wxt(tscl_handle* h, const float* params, void* wxt_bf16, void* stream) {
   if (!h || !params || !wxt_bf16) return tsc_set_error("tscl_pack_wxt: bad argument");
   PCK(cudaSetDevice(tscl_device_of(h)));
@@ -1648,7 +1844,18 @@ extern "C" int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, floa
   // measured (R = 8192, 1 x B200): the one-CTA-per-SM 512-thread variant 2.097 ms per control step, the two-CTA 256-thread
   // variant 2.144 ms; TSC_BPTT_THREADS=256 selects the latter for experiments
   static const int bw_threads = []() { const char* e = getenv("TSC_BPTT_THREADS"); return e && atoi(e) == 256 ? 256 : 512; }();
-  if (bw_threads == 512) lstm_bwd_tc_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
+  // staged variant (coalesced cp.async into swizzled shared memory one step ahead): store path without fused dX
+  static const int bw_staged = []() { const char* e = getenv("TSC_BPTT_STAGED"); return e ? atoi(e) : 1; }();
+  if (bw_staged && bw_threads == 512 && a.Gb && a.Cb && a.dZb && !a.ZG && !a.dXb) {
+    const size_t smem_s = BW_KC * 1024 + BW_KC * 2048 + 16 + 128 * 512 + 2 * 128 * 128 + 128 * 256;
+    static int attr_s = -1;
+    if (attr_s != tscl_device_of(h)) {
+      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      attr_s = tscl_device_of(h);
+    }
+    const int grid_s = (int)(n_items < n_sm ? n_items : n_sm);
+    lstm_bwd_tc_staged_kernel<<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a);
+  } else if (bw_threads == 512) lstm_bwd_tc_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
   else lstm_bwd_tc_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());
   return 0;

@@ -876,7 +876,8 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       // partial head sums of groups 1..NG-1: group 1 in sRed, groups 2, 3 (NT = 512) in the A tile, which is dead once
       // the gate MMA has been committed; group 0 adds them in a fixed order (deterministic bits)
-      float* sRed2 = reinterpret_cast<float*>(sA + 65536);      // behind the 64 KB copy-out staging (A tile = 72 KB)
+      // behind the 64 KB copy-out staging when the A tile has room (72 KB at K = 288), else in its own 8 KB after sTmem
+      float* sRed2 = KC * 2048 >= 65536 + 8192 ? reinterpret_cast<float*>(sA + 65536) : reinterpret_cast<float*>(sTmem + 4);
       if (half == 1) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
@@ -1283,8 +1284,8 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
   if ((d.dx % 32) != 0 || d.dx > 256) return tsc_set_error("tscl_policy_step_v2r: dx must be a multiple of 32, <= 256");
   if (d.kw == 0) return tsc_set_error("tscl_policy_step_v2r: observation slice does not fit the 64-column input tile");
   if (8 * d.dx * 16 > (d.dx / 8) * 2048) return tsc_set_error("tscl_policy_step_v2r: fc operand does not fit its staging region");
-  const bool wide_tile = (size_t)(K / 8) * 2048 >= 65536 + 2 * TC_M * 8 * sizeof(float);   // copy-out staging + partial head sums
-  const size_t smem = tc2_smem_bytes(K);
+  const bool wide_tile = (size_t)(K / 8) * 2048 >= 65536;   // the A tile doubles as the 64 KB copy-out staging of the epilogue
+  const size_t smem = tc2_smem_bytes(K) + ((size_t)(K / 8) * 2048 >= 65536 + 8192 ? 0 : 8192);
   if (smem > 232448) return tsc_set_error("tscl_policy_step_v2r: operand tiles exceed shared memory");
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {

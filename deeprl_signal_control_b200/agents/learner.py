@@ -18,6 +18,7 @@ batched GEMMs (X.Wx, dZ.Wx^T, [X|H]^T.dZ) go through cuBLAS (`torch.baddbmm/bmm`
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -102,6 +103,8 @@ class BatchedA2C:
         # 92.5 ms), so the default keeps dX as a separate product; `dx_fused = True` selects the fused kernel (tested)
         self.dx_fused = False
         self.dx_fusable = self.use_tc and L.dx % 32 == 0 and L.dx <= 256
+        # stand-alone dX = dZ . Wx^T kernel (tscl_dx_tc); False falls back to the library GEMM (A/B measurements only)
+        self.dx_own = self.use_tc and L.dx % 16 == 0 and L.dx <= 224 and os.environ.get("TSC_DX_LIBRARY", "0") != "1"
         self.bwd_tc = self.use_tc
         self.fc_bwd_tc = self.use_tc and layout.fc_bwd_tc_ok     # front-end weight gradients on the tensor cores
         self.wgrad_tc = self.use_tc and L.dx % 8 == 0 and L.dx <= 240   # LSTM weight gradients on the tensor cores
@@ -140,7 +143,7 @@ class BatchedA2C:
         if self.use_tc:
             _lib.check(_lib.lib().tscl_pack_weights(self._h, _p(self.P), _p(self.Wp), self._st()))
             _lib.check(_lib.lib().tscl_pack_wht(self._h, _p(self.P), _p(self.Wt), self._st()))
-            if self.dx_fusable:
+            if self.dx_fusable or self.dx_own:
                 _lib.check(_lib.lib().tscl_pack_wxt(self._h, _p(self.P), _p(self.Wxt), self._st()))
             self.wx_b = self.pv["wx"].to(torch.bfloat16)       # operand of the separate product dX = dZ . Wx^T
             self.kernel_launches += 3
@@ -378,7 +381,9 @@ class BatchedA2C:
                 self.gv["bl"].add_(dZ.sum(dim=1))
             # dX = dZ . Wx^T: fused into the BPTT kernel on the shipping path; a library GEMM only on the fp32 twin path
             # (and for layouts whose dx is not a multiple of 32)
-            if all_tc and not fuse_dx:
+            if all_tc and not fuse_dx and self.dx_own:
+                _lib.check(lib.tscl_dx_tc(self._h, _p(dZb), _p(self.Wxt), _p(dXb), C.c_int64(M), st()))
+            elif all_tc and not fuse_dx:
                 torch.bmm(dZb, self.wx_b.transpose(1, 2), out=dXb)
             elif not all_tc:
                 torch.bmm(dZ, self.pv["wx"].transpose(1, 2), out=dX)

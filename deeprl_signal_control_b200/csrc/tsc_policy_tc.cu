@@ -2596,3 +2596,204 @@ extern "C" int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const void* dz_bf1
   PCK(cudaGetLastError());
   return 0;
 }
+
+// ===================================================================================================
+// dX = dZ . Wx^T  (input gradient of the LSTM's x-projection, agents/utils.py:103-105 differentiated): a streaming GEMM
+// [M x 256] . [256 x dx] per unit, 960 B of HBM traffic per row.  Warp-specialised persistent kernel:
+//   warps 4-7  loaders : 16-byte cp.async of one swizzle atom (128 rows x 64 K, 16 KB) per stage, written in the
+//                        SWIZZLE_128B K-major pattern (chunk ^ (row & 7)); 3 stages, completion signalled two stages late
+//   warp  8    MMA     : 4 x tcgen05.mma (M = 128, N = dx, K = 16) per atom, B = the unit's Wx^T image resident in shared
+//                        memory (fetched by one cp.async.bulk per unit), accumulators double-buffered in TMEM (2 x 256 cols)
+//   warps 0-3  epilogue: tcgen05.ld -> bf16 -> padded row in shared memory -> one cp.async.bulk store per row (448 B),
+//                        drained by the copy engine while the next tile is converted
+// A CTA owns a contiguous range of the (unit, 128-row tile) list, so it changes unit at most twice.
+#define DXK_THREADS 288
+#define DXK_STAGES 3
+#define DXK_STAGE_BYTES 16384
+struct DxTC {
+  const __nv_bfloat16* dZb;    // [2A][M][256]
+  const __nv_bfloat16* Wxt;    // [2A][32][dx][8]  (tscl_pack_wxt)
+  __nv_bfloat16* dXb;          // [2A][M][dx]
+  int64_t M;
+};
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {      // K-major, 128-byte swizzle, 8-row groups 1024 B apart
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(DXK_THREADS, 1)
+dx_tc_kernel(const DDimsTC d, const DxTC a) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dx = d.dx, row_bytes = dx * 2, out_stride = row_bytes + 16;
+  unsigned char* sStage = tc_smem;
+  unsigned char* sB = sStage + DXK_STAGES * DXK_STAGE_BYTES;
+  unsigned char* sOut = sB + (size_t)BW_KC * dx * 16;
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sOut + (size_t)128 * out_stride);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 12);
+  const uint32_t bar_full = smem_u32(sBar), bar_empty = bar_full + 24, bar_accf = bar_full + 48, bar_acce = bar_full + 64,
+                 bar_b = bar_full + 80, bar_d = bar_full + 88;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < DXK_STAGES; ++s) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 128); }
+    mbar_init(bar_b, 1); mbar_init(bar_d, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *sTmem;
+  const int64_t tpu = (a.M + 127) / 128;
+  const int64_t NT = tpu * 2 * d.A;
+  const int64_t j0 = NT * blockIdx.x / gridDim.x, j1 = NT * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp >= 4 && warp < 8) {
+    // ---------------- loaders ----------------
+    const int lt = tid - 128;
+    const uint32_t aS = smem_u32(sStage);
+    int64_t it = 0;
+    for (int64_t j = j0; j < j1; ++j) {
+      const int u = (int)(j / tpu);
+      const int64_t m0 = (j - (int64_t)u * tpu) * 128;
+      const __nv_bfloat16* src0 = a.dZb + (int64_t)u * a.M * TC_N;
+      for (int at = 0; at < 4; ++at, ++it) {
+        const int s = (int)(it % DXK_STAGES);
+        const int64_t n = it / DXK_STAGES;
+        if (n > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)((n - 1) & 1));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int id = i * 128 + lt, rw = id >> 3, c = id & 7;
+          const int64_t rr = m0 + rw < a.M ? m0 + rw : a.M - 1;
+          cp_async16(aS + s * DXK_STAGE_BYTES + rw * 128 + ((c ^ (rw & 7)) << 4), src0 + rr * TC_N + at * 64 + c * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it >= 2) {
+          asm volatile("cp.async.wait_group 2;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(bar_full + 8 * (int)((it - 2) % DXK_STAGES));
+        }
+      }
+    }
+    if (it >= 2) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_full + 8 * (int)((it - 2) % DXK_STAGES));
+    }
+    if (it >= 1) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_full + 8 * (int)((it - 1) % DXK_STAGES));
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(dx >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      const uint32_t aS = smem_u32(sStage), aB = smem_u32(sB);
+      const uint32_t b_lbo = (uint32_t)dx * 16;
+      int64_t it = 0, tc = 0;
+      int cur_u = -1;
+      uint32_t bph = 0, dph = 0;
+      for (int64_t j = j0; j < j1; ++j, ++tc) {
+        const int u = (int)(j / tpu);
+        if (u != cur_u) {
+          if (cur_u >= 0) {                       // the MMAs in flight still read the previous unit's image
+            umma_commit(bar_d);
+            mbar_wait(bar_d, dph); dph ^= 1;
+          }
+          cur_u = u;
+          const uint32_t bytes = (uint32_t)BW_KC * dx * 16;
+          mbar_expect_tx(bar_b, bytes);
+          bulk_g2s(aB, a.Wxt + (int64_t)u * BW_KC * dx * 8, bytes, bar_b);
+          mbar_wait(bar_b, bph); bph ^= 1;
+        }
+        const int b = (int)(tc & 1);
+        const int64_t nb = tc >> 1;
+        if (nb > 0) mbar_wait(bar_acce + 8 * b, (uint32_t)((nb - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int at = 0; at < 4; ++at, ++it) {
+          const int s = (int)(it % DXK_STAGES);
+          mbar_wait(bar_full + 8 * s, (uint32_t)((it / DXK_STAGES) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + b * 256, make_desc_sw128(aS + s * DXK_STAGE_BYTES + k * 32),
+                      make_desc(aB + (uint32_t)((at * 4 + k) * 2) * b_lbo, b_lbo, 128), idesc, (at | k) ? 1u : 0u);
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_accf + 8 * b);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: thread = row (TMEM lane) ----------------
+    const int row = tid;
+    unsigned char* my = sOut + (size_t)row * out_stride;
+    const uint32_t my_s = smem_u32(my);
+    int64_t tc = 0;
+    for (int64_t j = j0; j < j1; ++j, ++tc) {
+      const int u = (int)(j / tpu);
+      const int64_t m0 = (j - (int64_t)u * tpu) * 128;
+      const int b = (int)(tc & 1);
+      mbar_wait(bar_accf + 8 * b, (uint32_t)((tc >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous store of this row has left shared memory
+      const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 256);
+      for (int c0 = 0; c0 < dx; c0 += 32) {
+        float v[32];
+        tmem_ld16(tb + c0, v);
+        if (c0 + 16 < dx) tmem_ld16(tb + c0 + 16, v + 16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int nq = (c0 + 16 < dx) ? 4 : 2;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          if (qd < nq) {
+            __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(v[qd * 8 + e]);
+            *reinterpret_cast<uint4*>(my + (c0 + qd * 8) * 2) = *reinterpret_cast<const uint4*>(o);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_acce + 8 * b);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (m0 + row < a.M) {
+        __nv_bfloat16* dst = a.dXb + ((int64_t)u * a.M + m0 + row) * dx;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(my_s), "r"(row_bytes) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+extern "C" int tscl_dx_tc(tscl_handle* h, const void* dz_bf16, const void* wxt_bf16, void* dx_bf16, int64_t M, void* stream) {
+  if (!h || !dz_bf16 || !wxt_bf16 || !dx_bf16 || M <= 0) return tsc_set_error("tscl_dx_tc: bad argument");
+  PCK(cudaSetDevice(tscl_device_of(h)));
+  const DDimsTC& d = *tscl_dims_of(h);
+  if (d.dx % 16 != 0 || d.dx > 256 || d.dx < 16) return tsc_set_error("tscl_dx_tc: dx must be a multiple of 16 in [16, 256]");
+  const size_t smem = (size_t)DXK_STAGES * DXK_STAGE_BYTES + (size_t)BW_KC * d.dx * 16 + (size_t)128 * (d.dx * 2 + 16) + 12 * 8 + 16;
+  if (smem > 232448) return tsc_set_error("tscl_dx_tc: shared memory budget exceeded");
+  static int attr_dev = -1;
+  if (attr_dev != tscl_device_of(h)) {
+    PCK(cudaFuncSetAttribute(dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_dev = tscl_device_of(h);
+  }
+  int n_sm = 0;
+  PCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, tscl_device_of(h)));
+  const int64_t NT = ((M + 127) / 128) * 2 * d.A;
+  const int grid = (int)(NT < n_sm ? NT : n_sm);
+  DxTC a;
+  a.dZb = (const __nv_bfloat16*)dz_bf16; a.Wxt = (const __nv_bfloat16*)wxt_bf16; a.dXb = (__nv_bfloat16*)dx_bf16; a.M = M;
+  dx_tc_kernel<<<grid, DXK_THREADS, smem, (cudaStream_t)stream>>>(d, a);
+  PCK(cudaGetLastError());
+  return 0;
+}

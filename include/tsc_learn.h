@@ -146,6 +146,11 @@ int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, float* ZG, cons
                             const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
                             const void* gates_bf16, const void* c_bf16, void* dz_bf16, const void* wxt_bf16, void* dx_bf16,
                             void* stream);
+/* dX = dZ . Wx^T as a stand-alone streaming product (the shipping path; reference: tf.gradients through
+ * `tf.matmul(x, wx)`, agents/utils.py:106): dz_bf16 [2A][M][256], wxt_bf16 from tscl_pack_wxt, dx_bf16 [2A][M][dx] out.
+ * Warp-specialised tcgen05 kernel (cp.async loaders -> 128B-swizzled operand stages, TMEM double buffer, bulk-copy stores).
+ * dx must be a multiple of 16, <= 224 for the shared-memory budget. */
+int tscl_dx_tc(tscl_handle* h, const void* dz_bf16, const void* wxt_bf16, void* dx_bf16, int64_t M, void* stream);
 /* gates_bf16 / c_bf16 (both or neither): read gate activations and c_t straight from one chunk of the bf16
  * activation store instead of ZG / C (ZG is then write-only: it receives dZ).
  * dz_bf16 (optional): also write dZ as bf16 [2A][T*Rc][256]; with all three bf16 pointers ZG may be NULL. */

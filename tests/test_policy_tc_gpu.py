@@ -339,3 +339,34 @@ def test_lstm_weight_gradients_tensor_core_kernel(ff, from_store):
     for k, v in gv.items():
         if k not in ("wx", "wh", "bl"):
             assert not bool(v.any()), k
+
+
+@pytest.mark.parametrize("ff,M", [(64, 128 * 5 + 37), (0, 300), ("monaco", 4096 + 1), (64, 128 * 400 + 3)])
+def test_dx_kernel_matches_bf16_matmul(ff, M):
+    """tscl_dx_tc (dX = dZ . Wx^T, warp-specialised tcgen05 kernel) vs the same product of the bf16-rounded operands in
+    fp32: products of bf16 values are exact in fp32, so only the summation order and the final bf16 rounding differ."""
+    import ctypes as C
+    from deeprl_signal_control_b200 import _lib
+    from deeprl_signal_control_b200.agents.learner import BatchedA2C
+    from tests.test_learner_gpu import _layout
+    lay = _layout(ff)
+    m = BatchedA2C(lay, 8, n_step=2, seed=5)
+    assert m.dx_own
+    U, dx = lay.U, lay.dx
+    g = torch.Generator(device="cuda").manual_seed(7)
+    dZ = (torch.randn(U, M, 256, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    dX = torch.full((U, M, dx), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pad = torch.full((1024,), 7.0, device="cuda", dtype=torch.bfloat16)        # canary right behind the output
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):          # second call: the persistent state (barriers, TMEM) is set up afresh every launch
+        _lib.check(_lib.lib().tscl_dx_tc(m._h, C.c_void_p(dZ.data_ptr()), C.c_void_p(m.Wxt.data_ptr()),
+                                         C.c_void_p(dX.data_ptr()), C.c_int64(M), st))
+    torch.cuda.synchronize()
+    wx = m.pv["wx"].to(torch.bfloat16).float()                 # [U][dx][256]
+    ref = torch.bmm(dZ.float(), wx.transpose(1, 2))
+    assert torch.isfinite(dX.float()).all()
+    err = (dX.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-6, err
+    # bf16 rounding of the exact result: at most one bf16 ulp of the value
+    assert ((dX.float() - ref).abs() <= ref.abs() * 2.0 ** -7 + 1e-3).all()
+    assert (pad == 7.0).all()

@@ -85,7 +85,7 @@ def parse():
     p.add_argument("--agent", default="ma2c", choices=["ma2c", "ia2c"],
                    help="ma2c = BASELINE configs[2] (the headline workload); ia2c with --policy fc = configs[1]")
     p.add_argument("--policy", default="lstm", choices=["lstm", "fc"], help="fc = FcACPolicy (agents/policies.py:214-256)")
-    p.add_argument("--e2e-parts", type=int, default=3,
+    p.add_argument("--e2e-parts", type=int, default=4,
                    help="replica ranges of the host-buffer (e2e) loop, one stream each (1: single blocking tsc_step_host)")
     return p.parse_args()
 
@@ -388,11 +388,20 @@ def main():
         for i in range(3):
             host_step()
         barrier()
+        wait_s = [0.0]
+        if os.environ.get("TSC_E2E_PROFILE"):          # how much of the host loop is spent blocked on the device
+            for cls in (torch.cuda.Event, torch.cuda.Stream):
+                def timed(self, _o=cls.synchronize):
+                    t_ = time.perf_counter(); _o(self); wait_s[0] += time.perf_counter() - t_
+                cls.synchronize = timed
         t0 = time.perf_counter()
         for i in range(e2e_steps):
             host_step()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        if os.environ.get("TSC_E2E_PROFILE"):
+            print("e2e host loop: %.3f ms/step, %.3f ms/step blocked in Event/Stream.synchronize" %
+                  (e2e_ms / e2e_steps, wait_s[0] * 1e3 / e2e_steps), file=sys.stderr)
         h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4
         d2h = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
         e2e_api = ("BatchedTrainer.control_step_host: policy forward on device, actions+fingerprints D2H, "

@@ -200,11 +200,13 @@ class BatchedA2C:
             self.n_forward += 1
         return self.pi, self.val, (self.act if want_act else None)
 
-    def forward_range(self, r0: int, n: int, done: bool, t: int, n_forward: int):
+    def forward_range(self, r0: int, n: int, done: bool, t: int, n_forward: int, stream=None, to_hist: bool = False):
         """forward() for the replica range [r0, r0 + n) only, on the current stream, for rollout slot `t` and decision
         counter `n_forward` (the caller may run ranges one step apart): reads obs_slot(t)[r0:r0+n], advances that
         range's recurrent state and writes its slices of pi / val / act (and of the activation store).  Ranges are
-        independent.  Tensor-core path only; bookkeeping of the step: end_forward_ranges()."""
+        independent.  Tensor-core path only; bookkeeping of the step: end_forward_ranges().
+        `stream`: raw CUDA stream handle (default: torch's current stream).  `to_hist`: actions / values go straight into
+        the rollout slots act_hist[t] / val_hist[t] (what add_transition would copy there) and those views are returned."""
         assert self.use_tc and self.tc_v2, "forward_range needs the fused tensor-core forward"
         L, R, A = self.lay, self.R, self.lay.A
         store = self.store_acts and t < self.T
@@ -213,13 +215,16 @@ class BatchedA2C:
         _lib.check(_lib.lib().tscl_policy_step_v2r(
             self._h, _p(self.P), _p(self.Wp), off(self.obs_hist[t], L.n_obs), C.c_int64(n),
             off(self.c_fw, L.h), off(self.h_fw, L.h), off(self.c_fw, L.h), off(self.h_fw, L.h),
-            off(self.pi, A * L.max_na), off(self.val, A), off(self.act, A), C.c_int32(1 if done else 0),
+            off(self.pi, A * L.max_na), off(self.val_hist[t] if to_hist else self.val, A),
+            off(self.act_hist[t] if to_hist else self.act, A), C.c_int32(1 if done else 0),
             C.c_uint64(self.seed), C.c_int64(n_forward), C.c_int64(self.replica0 + r0), None, *st,
             C.c_int32(t if store else 0), C.c_int32(self.T), C.c_int64(self.chunk), C.c_int64(R), C.c_int64(r0),
-            self._st()))
+            self._st() if stream is None else stream))
         self.kernel_launches += 1
         if t < self.T:
             self._acts_ok[t] = store
+        if to_hist:
+            return self.pi[r0:r0 + n], self.val_hist[t, r0:r0 + n], self.act_hist[t, r0:r0 + n]
         return self.pi[r0:r0 + n], self.val[r0:r0 + n], self.act[r0:r0 + n]
 
     def end_forward_ranges(self):

@@ -8,11 +8,13 @@ learner's rollout slot and reads actions / fingerprints from the learner's buffe
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
 
 import numpy as np
 import torch
 
+from .. import _lib
 from .. import dist as _dist
 from ..sim import BatchedSim
 from .learner import BatchedA2C
@@ -122,57 +124,66 @@ class BatchedTrainer:
         ranges are independent and the sampling RNG is keyed by the absolute replica.  The host still receives every
         range's observations / rewards in page-locked numpy buffers before the learner consumes them."""
         sim, m = self.sim, self.model
-        R, A = sim.R, m.lay.A
+        R, A, L = sim.R, m.lay.A, m.lay
+        lib = _lib.lib()
+        ma2c = self.agent == 'ma2c'
         if not hasattr(self, '_pp'):
             n_parts = max(1, min(n_parts, R))
             bounds = [R * k // n_parts for k in range(n_parts + 1)]
             pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
-            self._pp = dict(parts=[(bounds[k], bounds[k + 1] - bounds[k]) for k in range(n_parts)],
-                            streams=[torch.cuda.Stream(device=sim.device) for _ in range(n_parts)],
-                            ev=[torch.cuda.Event() for _ in range(n_parts)], primed=False,
-                            act=pin(R, A, dtype=torch.int32), pi=pin(R, A, m.lay.max_na), obs=pin(R, sim.net.n_obs),
-                            rew=pin(R, A), grew=pin(R), done=pin(R, dtype=torch.uint8))
+            pp = dict(primed=False, act=pin(R, A, dtype=torch.int32), pi=pin(R, A, L.max_na), obs=pin(R, sim.net.n_obs),
+                      rew=pin(R, A), grew=pin(R), done=pin(R, dtype=torch.uint8),
+                      rew_stage=torch.zeros(R, A, device=m.dev), grew_stage=torch.zeros(R, device=m.dev), parts=[])
+            at = lambda x, r0, per_row: C.c_void_p(x.data_ptr() + r0 * per_row * x.element_size())
+            for k in range(n_parts):        # raw pointers of every range's slices: the per-step loop is host-issue-bound
+                r0, n = bounds[k], bounds[k + 1] - bounds[k]
+                st = torch.cuda.Stream(device=sim.device)
+                pp['parts'].append(dict(
+                    r0=r0, n=n, stream=st, sth=C.c_void_p(st.cuda_stream), ev=torch.cuda.Event(),
+                    act_h=at(pp['act'], r0, A), pi_h=at(pp['pi'], r0, A * L.max_na) if ma2c else None,
+                    obs_h=at(pp['obs'], r0, sim.net.n_obs), rew_h=at(pp['rew'], r0, A), grew_h=at(pp['grew'], r0, 1),
+                    done_h=at(pp['done'], r0, 1), rew_stage=at(pp['rew_stage'], r0, A),
+                    grew_stage=at(pp['grew_stage'], r0, 1), rew_acc=at(self._rew_acc, r0, 1)))
+            self._pp = pp
         pp = self._pp
-        ma2c = self.agent == 'ma2c'
 
-        def issue_forward(k, t, nf, done):
-            r0, n = pp['parts'][k]
-            pi, val, act = m.forward_range(r0, n, done, t, nf)
-            pp['act'][r0:r0 + n].copy_(act, non_blocking=True)
+        def issue_forward(p, t, nf, done):
+            pi, val, act = m.forward_range(p['r0'], p['n'], done, t, nf, stream=p['sth'], to_hist=True)
+            _lib.check(lib.tscl_memcpy_async(m._h, p['act_h'], C.c_void_p(act.data_ptr()), C.c_int64(p['n'] * A * 4),
+                                             C.c_int32(2), p['sth']))
             if ma2c:
-                pp['pi'][r0:r0 + n].copy_(pi, non_blocking=True)
-            pp['ev'][k].record()
+                _lib.check(lib.tscl_memcpy_async(m._h, p['pi_h'], C.c_void_p(pi.data_ptr()),
+                                                 C.c_int64(p['n'] * A * L.max_na * 4), C.c_int32(2), p['sth']))
+            p['ev'].record(p['stream'])
 
         if not pp['primed']:
             cur = torch.cuda.current_stream(sim.device)
-            for k, st in enumerate(pp['streams']):
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
-                    issue_forward(k, m.t, m.n_forward, self.done)
+            for p in pp['parts']:
+                p['stream'].wait_stream(cur)
+                issue_forward(p, m.t, m.n_forward, self.done)
             m.end_forward_ranges()
             pp['primed'] = True
         t = m.t
         self.step_in_episode += 1
         new_done = self.step_in_episode >= self.T_episode
         boundary = (t + 1 == m.T)                       # an update (and possibly an episode end) follows this step
-        npv = lambda x, r0, n: x[r0:r0 + n].numpy()
-        for k, st in enumerate(pp['streams']):       # every range's env step is enqueued as soon as its actions are here
-            r0, n = pp['parts'][k]
-            pp['ev'][k].synchronize()                   # the host holds this range's actions / fingerprints
-            with torch.cuda.stream(st):
-                sim.step_host_range(r0, n, npv(pp['act'], r0, n), npv(pp['pi'], r0, n) if ma2c else None,
-                                    npv(pp['obs'], r0, n), npv(pp['rew'], r0, n), npv(pp['grew'], r0, n),
-                                    npv(pp['done'], r0, n), sync=False)
-        for k, st in enumerate(pp['streams']):
-            r0, n = pp['parts'][k]
-            st.synchronize()                            # the host holds this range's observations / rewards ...
-            with torch.cuda.stream(st):
-                # ... and hands them to the learner
-                m.obs_hist[t + 1, r0:r0 + n].copy_(pp['obs'][r0:r0 + n], non_blocking=True)
-                m.add_transition_range(r0, n, pp['rew'][r0:r0 + n].to(sim.device, non_blocking=True))
-                self._rew_acc[r0:r0 + n].add_(pp['grew'][r0:r0 + n].to(sim.device, non_blocking=True))
-                if not boundary:
-                    issue_forward(k, t + 1, m.n_forward, False)
+        n_obs = sim.net.n_obs
+        for p in pp['parts']:                           # every range's env step is enqueued as soon as its actions are here
+            p['ev'].synchronize()                       # the host holds this range's actions / fingerprints
+            _lib.check(lib.tsc_step_host_range_async(sim._h, C.c_int32(p['r0']), C.c_int32(p['n']), p['act_h'], p['pi_h'],
+                                                     p['obs_h'], p['rew_h'], p['grew_h'], p['done_h'], p['sth']))
+        obs_next, rew_t = m.obs_hist[t + 1], m.rew_hist[t]
+        for p in pp['parts']:
+            r0, n = p['r0'], p['n']
+            p['stream'].synchronize()                   # the host holds this range's observations / rewards ...
+            # ... and hands them to the learner: obs -> rollout slot t+1, reward -> normalised / clipped slot t, episode sum
+            _lib.check(lib.tscl_host_transition(
+                m._h, p['obs_h'], C.c_void_p(obs_next.data_ptr() + r0 * n_obs * 4), C.c_int64(n * n_obs), p['rew_h'],
+                p['rew_stage'], C.c_void_p(rew_t.data_ptr() + r0 * A * 4), C.c_int64(n * A),
+                C.c_float(m.reward_norm or 0.0), C.c_float(m.reward_clip or 0.0), p['grew_h'], p['grew_stage'],
+                p['rew_acc'], C.c_int64(n), p['sth']))
+            if not boundary:
+                issue_forward(p, t + 1, m.n_forward, False)
         m.end_transition_ranges(self.done, new_done)
         self.done = new_done
         self.n_env_steps += 1
@@ -180,8 +191,8 @@ class BatchedTrainer:
             m.end_forward_ranges()
         else:
             cur = torch.cuda.current_stream(sim.device)
-            for st in pp['streams']:
-                cur.wait_stream(st)
+            for p in pp['parts']:
+                cur.wait_stream(p['stream'])
             pp['primed'] = False
             self.update()
 

@@ -1147,3 +1147,51 @@ extern "C" int tscl_clip_rmsprop(tscl_handle* h, float* params, float* grads, fl
   LCK(cudaFreeAsync(norm2, st));
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer (e2e) loop helpers: one call per replica range and control step replaces a dozen framework-level
+// copies / elementwise launches (the host loop was issue-bound: 0.22 ms of Python per range and step).
+//   tscl_host_transition: observations host -> rollout slot, rewards host -> normalised / clipped rollout slot
+//   (envs/env.py reward hand-over + agents/models.py:222-229 `add_transition`, utils.py reward_norm / reward_clip),
+//   global rewards host -> running episode sum (utils.py:296-305).
+__global__ void host_transition_kernel(const float* __restrict__ rew_in, float* __restrict__ rew_hist, int64_t n_rew,
+                                       float inv_norm, float clip, const float* __restrict__ grew_in,
+                                       float* __restrict__ rew_acc, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_rew) {
+    float r = rew_in[i];
+    if (inv_norm != 0.f) r = r * inv_norm;
+    if (clip > 0.f) r = fminf(fmaxf(r, -clip), clip);
+    rew_hist[i] = r;
+  }
+  if (i < n) rew_acc[i] += grew_in[i];
+}
+
+extern "C" int tscl_host_transition(tscl_handle* h, const float* obs_host, float* obs_dev, int64_t obs_floats,
+                                    const float* rew_host, float* rew_stage_dev, float* rew_hist_dev, int64_t rew_floats,
+                                    float reward_norm, float reward_clip, const float* grew_host, float* grew_stage_dev,
+                                    float* rew_acc_dev, int64_t n, void* stream) {
+  if (!h || !obs_host || !obs_dev || !rew_host || !rew_stage_dev || !rew_hist_dev || !grew_host || !grew_stage_dev ||
+      !rew_acc_dev || obs_floats <= 0 || rew_floats <= 0 || n <= 0 || n > rew_floats)
+    return tsc_set_error("tscl_host_transition: bad argument");
+  LCK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  LCK(cudaMemcpyAsync(obs_dev, obs_host, (size_t)obs_floats * 4, cudaMemcpyHostToDevice, st));
+  LCK(cudaMemcpyAsync(rew_stage_dev, rew_host, (size_t)rew_floats * 4, cudaMemcpyHostToDevice, st));
+  LCK(cudaMemcpyAsync(grew_stage_dev, grew_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  host_transition_kernel<<<(unsigned)((rew_floats + 255) / 256), 256, 0, st>>>(
+      rew_stage_dev, rew_hist_dev, rew_floats, reward_norm != 0.f ? 1.0f / reward_norm : 0.f, reward_clip, grew_stage_dev,
+      rew_acc_dev, n);
+  LCK(cudaGetLastError());
+  return 0;
+}
+
+// plain asynchronous copy on a caller-supplied stream (kind: 1 host->device, 2 device->host, 3 device->device)
+extern "C" int tscl_memcpy_async(tscl_handle* h, void* dst, const void* src, int64_t bytes, int32_t kind, void* stream) {
+  if (!h || !dst || !src || bytes <= 0 || kind < 1 || kind > 3) return tsc_set_error("tscl_memcpy_async: bad argument");
+  LCK(cudaSetDevice(h->device));
+  LCK(cudaMemcpyAsync(dst, src, (size_t)bytes, kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost
+                                                                                              : cudaMemcpyDeviceToDevice,
+                      (cudaStream_t)stream));
+  return 0;
+}

@@ -146,6 +146,16 @@ int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, float* ZG, cons
                             const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
                             const void* gates_bf16, const void* c_bf16, void* dz_bf16, const void* wxt_bf16, void* dx_bf16,
                             void* stream);
+/* Host-buffer loop, one call per replica range and control step (replaces the reference's per-step numpy hand-over of
+ * ob / reward into `model.add_transition`, agents/models.py:222-229, main.py / utils.py:272-286): observations
+ * host -> obs_dev (the rollout slot), rewards host -> rew_hist_dev = clip(reward / reward_norm) (0 = off for either),
+ * global rewards host -> rew_acc_dev += (episode sum, utils.py:296-305).  *_stage_dev are device scratch of the same
+ * size as the host arrays.  Host arrays should be page-locked; everything is enqueued on `stream`. */
+int tscl_host_transition(tscl_handle* h, const float* obs_host, float* obs_dev, int64_t obs_floats, const float* rew_host,
+                         float* rew_stage_dev, float* rew_hist_dev, int64_t rew_floats, float reward_norm, float reward_clip,
+                         const float* grew_host, float* grew_stage_dev, float* rew_acc_dev, int64_t n, void* stream);
+/* cudaMemcpyAsync on a caller-supplied stream; kind 1 = host->device, 2 = device->host, 3 = device->device */
+int tscl_memcpy_async(tscl_handle* h, void* dst, const void* src, int64_t bytes, int32_t kind, void* stream);
 /* dX = dZ . Wx^T as a stand-alone streaming product (the shipping path; reference: tf.gradients through
  * `tf.matmul(x, wx)`, agents/utils.py:106): dz_bf16 [2A][M][256], wxt_bf16 from tscl_pack_wxt, dx_bf16 [2A][M][dx] out.
  * Warp-specialised tcgen05 kernel (cp.async loaders -> 128B-swizzled operand stages, TMEM double buffer, bulk-copy stores).

@@ -394,14 +394,20 @@ def main():
                 def timed(self, _o=cls.synchronize):
                     t_ = time.perf_counter(); _o(self); wait_s[0] += time.perf_counter() - t_
                 cls.synchronize = timed
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            host_step()
-        barrier()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
+        # three back-to-back windows of one rollout + one update each; the MEDIAN window is reported (the host side of
+        # this loop is sensitive to whatever else the lease's cores are doing; all three are listed in the JSON line)
+        e2e_windows = []
+        for w in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                host_step()
+            barrier()
+            e2e_windows.append((time.perf_counter() - t0) * 1e3)
+        e2e_ms = sorted(e2e_windows)[1]
         if os.environ.get("TSC_E2E_PROFILE"):
             print("e2e host loop: %.3f ms/step, %.3f ms/step blocked in Event/Stream.synchronize" %
-                  (e2e_ms / e2e_steps, wait_s[0] * 1e3 / e2e_steps), file=sys.stderr)
+                  (e2e_ms / e2e_steps, wait_s[0] * 1e3 / (3 * e2e_steps)), file=sys.stderr)
         h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4
         d2h = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
         e2e_api = ("BatchedTrainer.control_step_host: policy forward on device, actions+fingerprints D2H, "
@@ -409,7 +415,8 @@ def main():
         if args.e2e_parts > 1:
             e2e_api = ("BatchedTrainer.control_step_host_pipelined: %d replica ranges, one stream each; per range: policy "
                        "forward (tscl_policy_step_v2r), actions+fingerprints D2H to pinned host buffers, "
-                       "tsc_step_host_range (H2D, kernel, D2H, host sync), obs+reward H2D into the learner; update "
+                       "tsc_step_host_range (H2D, kernel, D2H, host sync), obs+reward H2D into the learner (tscl_host_transition); "
+                       "median of three windows; update "
                        "every %d steps" % (args.e2e_parts, n_step))
     else:
         e2e_steps = max(3, min(args.steps, 20))
@@ -433,6 +440,7 @@ def main():
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_windows_all = [round(x, 3) for x in e2e_windows] if trainer is not None else None
     e2e_value = world * R * net.n_nodes * e2e_steps / (float(t.item()) * 1e-3)
 
     if rank != 0:
@@ -496,7 +504,8 @@ def main():
             "clocks": sampler.summary(),
             "value_steady": value_steady,
             "e2e": {"value": e2e_value, "unit": "agent-env-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": e2e_api},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": e2e_api,
+                    "windows_ms": e2e_windows_all},
             "gpu_launches": timed_launches,
             "roofline": roofline, "cpu_baseline": cb}
     print(json.dumps(line))

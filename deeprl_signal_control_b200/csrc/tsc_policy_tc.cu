@@ -510,6 +510,12 @@ extern "C" int tscl_policy_step(tscl_handle* h, const float* params, const void*
 // NT = 256: thread = (replica row, 32 hidden units); NT = 512: thread = (replica row, 16 hidden units) — twice the warps
 // per SM for the latency-bound staging / epilogue phases (one CTA per SM either way: the weight operand fills shared
 // memory), same arithmetic per element, so both variants produce identical bits.
+// A-tile region of the v2 kernel: the operand tile, or the largest copy-out staging pass (128 rows x 528 B + the parked
+// head partial sums behind the X pass), whichever is larger
+__host__ __device__ inline size_t tc2_a_bytes(int K) {
+  const size_t a = (size_t)(K / 8) * 2048;
+  return a > 69632 ? a : 69632;
+}
 template <int NT, bool PROF>
 __global__ void __launch_bounds__(NT, 1)
 policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
@@ -519,7 +525,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
   const int K = d.dx + TC_H, KC = K / 8, KS = K / 16, KCX = d.dx / 8;
   unsigned char* sB = tc_smem;                                  // KC * 4096
   unsigned char* sA = sB + (size_t)KC * 4096;                   // KC * 2048
-  float* sRed = reinterpret_cast<float*>(sA + (size_t)KC * 2048);   // [128][8]
+  float* sRed = reinterpret_cast<float*>(sA + tc2_a_bytes(K));      // [128][8]
   float* sWo = sRed + TC_M * 8;                                 // [64][8]
   float* sBo = sWo + TC_H * 8;                                  // [8]
   float* sBias = sBo + 8;                                       // [256]  lstm bias
@@ -547,10 +553,10 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
   const int64_t it_lo = n_items * blockIdx.x / gridDim.x, it_hi = n_items * (blockIdx.x + 1) / gridDim.x;
   int cur_u = -1;
   uint32_t parity = 0, par_fc = 0;
-  int nw = 0, nt = 0, nf = 0, ooff = 0, na = 0;
+  int nw = 0, nt = 0, nf = 0, ooff = 0, na = 0, src_a = -1, src_b = -1;
   const uint32_t aA = smem_u32(sA), aB = smem_u32(sB);
 
-  long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
+  long long pt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
 #define PROF_MARK(i) do { if (PROF && tid == 0) { const long long c_ = clock64(); pt[i] += c_ - pc; pc = c_; } } while (0)
   if (PROF && tid == 0) pc = clock64();
   for (int64_t it = it_lo; it < it_hi; ++it) {
@@ -573,6 +579,14 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       for (int i = tid; i < KC * TC_N; i += NT) dst[i] = src[i];
       nw = d.n_wave[ag]; nt = d.n_wait[ag]; nf = d.ff > 0 ? d.n_fp[ag] : 0;
       ooff = d.obs_off[ag]; na = d.n_a[ag];
+      {      // observation index of this lane's two input slots (-1: unused slot)
+        auto slot_src = [&](int c) -> int {
+          if (c < d.kw) return c < nw ? c : -1;
+          if (c < d.kw + TC_KF) return c - d.kw < nf ? nw + nt + (c - d.kw) : -1;
+          return c - d.kw - TC_KF < nt ? nw + (c - d.kw - TC_KF) : -1;
+        };
+        src_a = slot_src(2 * lane); src_b = slot_src(2 * lane + 1);
+      }
       for (int i = tid; i < TC_H * 8; i += NT) {
         const int k = i >> 3, j = i & 7;
         sWo[i] = j < d.max_na ? a.P[d.off_wo + ((int64_t)u * TC_H + k) * d.max_na + j] : 0.f;
@@ -610,25 +624,46 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         mbar_expect_tx(bar_fc, (uint32_t)(8 * d.dx * 16));
         bulk_g2s(aA, reinterpret_cast<const unsigned char*>(Wu + (int64_t)KC * TC_N * 8), (uint32_t)(8 * d.dx * 16), bar_fc);
       }
-      // thread = (row, 16-byte chunk) : 128 x 8 pairs, 4 per thread
+      if constexpr (NT == 512) {
+        // a warp takes 8 rows; lane l owns input slots 2l, 2l + 1 of every row (their observation indices src_a / src_b were
+        // resolved when the unit changed).  The slice of a row is one contiguous <= 256 B run of the observation vector, so
+        // a warp load touches 2-3 sectors of ONE row (the former thread = (row, chunk) mapping touched 32 rows per
+        // instruction: 8 k sector requests per tile, the whole staging phase); the two values leave as one packed store.
+        float xa[8], xb[8];
 #pragma unroll
-      for (int p = 0; p < 1024 / NT; ++p) {
-        const int pair = p * NT + tid;
-        const int row = pair & 127, ch = pair >> 7;          // consecutive threads -> consecutive rows
-        const int64_t r = r0 + row;
-        __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = ch * 8 + e;
-          int src = -1;
-          if (c < d.kw) { if (c < nw) src = c; }
-          else if (c < d.kw + TC_KF) { if (c - d.kw < nf) src = nw + nt + (c - d.kw); }
-          else { if (c - d.kw - TC_KF < nt) src = nw + (c - d.kw - TC_KF); }
-          float x = 0.f;
-          if (src >= 0 && r < a.R) x = __ldg(a.obs + r * d.n_obs + ooff + src);
-          v[e] = __float2bfloat16_rn(x);
+        for (int rr = 0; rr < 8; ++rr) {
+          const int64_t r = r0 + warp * 8 + rr;
+          const float* op = a.obs + (r < a.R ? r : 0) * d.n_obs + ooff;
+          xa[rr] = (src_a >= 0 && r < a.R) ? __ldg(op + src_a) : 0.f;
+          xb[rr] = (src_b >= 0 && r < a.R) ? __ldg(op + src_b) : 0.f;
         }
-        *reinterpret_cast<uint4*>(sA + (size_t)(KC - 8 + ch) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int row = warp * 8 + rr;
+          const __nv_bfloat162 v = __floats2bfloat162_rn(xa[rr], xb[rr]);
+          *reinterpret_cast<__nv_bfloat162*>(sA + (size_t)(KC - 8 + (lane >> 2)) * 2048 + row * 16 + (lane & 3) * 4) = v;
+        }
+      } else {
+        // thread = (row, 16-byte chunk) : 128 x 8 pairs, 4 per thread
+#pragma unroll
+        for (int p = 0; p < 1024 / NT; ++p) {
+          const int pair = p * NT + tid;
+          const int row = pair & 127, ch = pair >> 7;          // consecutive threads -> consecutive rows
+          const int64_t r = r0 + row;
+          __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+            int src = -1;
+            if (c < d.kw) { if (c < nw) src = c; }
+            else if (c < d.kw + TC_KF) { if (c - d.kw < nf) src = nw + nt + (c - d.kw); }
+            else { if (c - d.kw - TC_KF < nt) src = nw + (c - d.kw - TC_KF); }
+            float x = 0.f;
+            if (src >= 0 && r < a.R) x = __ldg(a.obs + r * d.n_obs + ooff + src);
+            v[e] = __float2bfloat16_rn(x);
+          }
+          *reinterpret_cast<uint4*>(sA + (size_t)(KC - 8 + ch) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+        }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -658,17 +693,36 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       const int q = warp & 3, hw = warp >> 2;
       const int row = q * 32 + lane;
       const int ncol = d.dx / NG;                      // columns per group (multiple of 8: dx % 32 == 0)
-      const bool st = NT != 512 && a.st_x && r0 + row < a.R;     // NT = 512: X is copied out coalesced in the epilogue
+      const bool st = a.st_x && r0 + row < a.R;
       const int64_t m = st ? store_row(row) : 0;
-      for (int c0 = hw * ncol; c0 < (hw + 1) * ncol; c0 += 8) {
-        float z[8];
-        tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        __align__(16) __nv_bfloat16 v[8];
+      const int cend = (hw + 1) * ncol;
+      for (int c0 = hw * ncol; c0 < cend;) {
+        if (NT == 512 && (c0 & 15) == 0 && c0 + 16 <= cend) {      // 16 columns: one 256-bit store of the activation row
+          float z[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __align__(32) __nv_bfloat16 v[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
-        *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
-        if (st) *reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0)) = *reinterpret_cast<const uint4*>(v);
+          for (int e = 0; e < 16; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
+          *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+          *reinterpret_cast<uint4*>(sA + (size_t)((c0 >> 3) + 1) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v + 8);
+          if (st) {
+            const uint4 x = reinterpret_cast<const uint4*>(v)[0], y = reinterpret_cast<const uint4*>(v)[1];
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(a.st_x + (m * d.dx + c0)), "r"(x.x), "r"(x.y),
+                         "r"(x.z), "r"(x.w), "r"(y.x), "r"(y.y), "r"(y.z), "r"(y.w) : "memory");
+          }
+          c0 += 16;
+        } else {
+          float z[8];
+          tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
+          *reinterpret_cast<uint4*>(sA + (size_t)(c0 >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
+          if (st) *reinterpret_cast<uint4*>(a.st_x + (m * d.dx + c0)) = *reinterpret_cast<const uint4*>(v);
+          c0 += 8;
+        }
       }
     }
     {
@@ -715,179 +769,10 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       float lg[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) lg[j] = 0.f;
-#pragma unroll
-      for (int jb = 0; jb < HPT / 16; ++jb) {
-        float zi[16], zf[16], zo[16], zu[16];
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HPT + jb * 16);
-        tmem_ld16(tbase, zi); tmem_ld16(tbase + 64, zf); tmem_ld16(tbase + 128, zo); tmem_ld16(tbase + 192, zu);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (a.zdbg && valid) {
-          float* z = a.zdbg + ((int64_t)u * ld + r) * TC_N + half * HPT + jb * 16;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) { z[e] = zi[e]; z[64 + e] = zf[e]; z[128 + e] = zo[e]; z[192 + e] = zu[e]; }
-        }
-        float cprev[16];
-        if (valid && !a.done) {
-          const float4* cp = reinterpret_cast<const float4*>(a.c_in + srow + jb * 16);
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 x = cp[e4];
-            cprev[4 * e4] = x.x; cprev[4 * e4 + 1] = x.y; cprev[4 * e4 + 2] = x.z; cprev[4 * e4 + 3] = x.w;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) cprev[e] = 0.f;
-        }
-        float cn[16], hn[16];
-        __align__(16) __nv_bfloat16 gbuf[4][16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int j = half * HPT + jb * 16 + e;
-          const float gi = sigm(zi[e] + sBias[j]), gf = sigm(zf[e] + sBias[64 + j]);
-          const float go = sigm(zo[e] + sBias[128 + j]), gu = tanh_fast(zu[e] + sBias[192 + j]);
-          cn[e] = gf * cprev[e] + gi * gu;
-          hn[e] = go * tanh_fast(cn[e]);
-          gbuf[0][e] = __float2bfloat16_rn(gi); gbuf[1][e] = __float2bfloat16_rn(gf);
-          gbuf[2][e] = __float2bfloat16_rn(go); gbuf[3][e] = __float2bfloat16_rn(gu);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
-        }
-        if constexpr (NT == 512) {
-          // Coalesced copy-out through the A tile (dead once the gate MMA has been committed): a thread owns a ROW, so
-          // its direct stores are 16-byte pieces 128-512 B apart (32 sectors per warp instruction: the phase profile
-          // showed stores as ~half of the kernel).  Each array is staged as [row][16-byte chunk ^ (row & mask)] (the XOR
-          // keeps both the row-owner writes and the chunk-per-lane reads free of bank conflicts) and written out with
-          // one warp instruction per contiguous 512 B of a row.
-          unsigned char* stg = sA;
-          const int sw = row & 31;
-          const bool do_store = a.st_g != nullptr;                       // uniform
-          if (do_store) {                                                // ---- X = relu(D0 + b) [128][dx bf16], pitch 512 B
-            // D0 (TMEM columns 256..256+dx) still holds the fc accumulators: recompute the bf16 X of phase 3 (same
-            // operations, same bits) instead of storing it row by row from there
-            const int ncol = d.dx / NG;
-            for (int c0 = half * ncol; c0 < (half + 1) * ncol; c0 += 8) {
-              float z[8];
-              tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)c0, z);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-              __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(fmaxf(z[e] + sBias0[c0 + e], 0.f));
-              *reinterpret_cast<uint4*>(stg + row * 512 + (((c0 >> 3) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(v);
-            }
-            __syncthreads();
-            const int nch = d.dx >> 3;                                   // 16-byte chunks per row (28 for dx = 224)
-#pragma unroll
-            for (int rr = 0; rr < 8; ++rr) {
-              const int rw = warp * 8 + rr;
-              if (r0 + rw < a.R && lane < nch) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stg + rw * 512 + ((lane ^ (rw & 31)) << 4));
-                *reinterpret_cast<uint4*>(a.st_x + store_row(rw) * d.dx + lane * 8) = v;
-              }
-            }
-            __syncthreads();
-          }
-          if (do_store) {                                                // ---- gates [128][512 B]
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int c = g * 8 + half * 2;
-              *reinterpret_cast<uint4*>(stg + row * 512 + ((c ^ sw) << 4)) = *reinterpret_cast<const uint4*>(&gbuf[g][0]);
-              *reinterpret_cast<uint4*>(stg + row * 512 + (((c + 1) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(&gbuf[g][8]);
-            }
-          }
-          __syncthreads();
-          if (do_store) {
-#pragma unroll
-            for (int rr = 0; rr < 8; ++rr) {
-              const int rw = warp * 8 + rr;
-              if (r0 + rw < a.R) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stg + rw * 512 + ((lane ^ (rw & 31)) << 4));
-                *reinterpret_cast<uint4*>(a.st_g + store_row(rw) * TC_N + lane * 8) = v;
-              }
-            }
-          }
-          __syncthreads();
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {                               // ---- c_out | h_out fp32 [128][256 B | 256 B]
-            const int c = half * 4 + e4;
-            *reinterpret_cast<float4*>(stg + row * 512 + ((c ^ sw) << 4)) =
-                make_float4(cn[4 * e4], cn[4 * e4 + 1], cn[4 * e4 + 2], cn[4 * e4 + 3]);
-            *reinterpret_cast<float4*>(stg + row * 512 + (((16 + c) ^ sw) << 4)) =
-                make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
-          }
-          __syncthreads();
-#pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const int rw = warp * 8 + rr;
-            if (r0 + rw < a.R) {
-              const float4 v = *reinterpret_cast<const float4*>(stg + rw * 512 + ((lane ^ (rw & 31)) << 4));
-              float* dst = (lane < 16 ? a.c_out : a.h_out) + ((int64_t)u * ld + r0 + rw) * TC_H + (lane & 15) * 4;
-              *reinterpret_cast<float4*>(dst) = v;
-            }
-          }
-          if (do_store) {                                                // ---- c | h bf16 [128][128 B | 128 B]
-            __syncthreads();
-            __align__(16) __nv_bfloat16 cb[16], hb[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { cb[e] = __float2bfloat16_rn(cn[e]); hb[e] = __float2bfloat16_rn(hn[e]); }
-            const int s2 = row & 15, c = half * 2;
-            *reinterpret_cast<uint4*>(stg + row * 256 + ((c ^ s2) << 4)) = *reinterpret_cast<const uint4*>(cb);
-            *reinterpret_cast<uint4*>(stg + row * 256 + (((c + 1) ^ s2) << 4)) = *reinterpret_cast<const uint4*>(cb + 8);
-            *reinterpret_cast<uint4*>(stg + row * 256 + (((8 + c) ^ s2) << 4)) = *reinterpret_cast<const uint4*>(hb);
-            *reinterpret_cast<uint4*>(stg + row * 256 + (((9 + c) ^ s2) << 4)) = *reinterpret_cast<const uint4*>(hb + 8);
-            __syncthreads();
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const int rw = warp * 8 + rr * 2 + (lane >> 4), l = lane & 15;
-              if (r0 + rw < a.R) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stg + rw * 256 + ((l ^ (rw & 15)) << 4));
-                __nv_bfloat16* dst = (l < 8 ? a.st_c : a.st_h) + store_row(rw) * TC_H + (l & 7) * 8;
-                *reinterpret_cast<uint4*>(dst) = v;
-              }
-            }
-          }
-        } else {
-        if (valid && a.st_g) {
-          const int64_t m = store_row((int)(r - r0));
-          const int jo = half * HPT + jb * 16;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4* o = reinterpret_cast<uint4*>(a.st_g + m * TC_N + g * 64 + jo);
-            o[0] = *reinterpret_cast<const uint4*>(&gbuf[g][0]); o[1] = *reinterpret_cast<const uint4*>(&gbuf[g][8]);
-          }
-          __align__(16) __nv_bfloat16 cb[16], hb[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) { cb[e] = __float2bfloat16_rn(cn[e]); hb[e] = __float2bfloat16_rn(hn[e]); }
-          uint4* oc = reinterpret_cast<uint4*>(a.st_c + m * TC_H + jo);
-          uint4* oh = reinterpret_cast<uint4*>(a.st_h + m * TC_H + jo);
-          oc[0] = *reinterpret_cast<const uint4*>(cb); oc[1] = *reinterpret_cast<const uint4*>(cb + 8);
-          oh[0] = *reinterpret_cast<const uint4*>(hb); oh[1] = *reinterpret_cast<const uint4*>(hb + 8);
-        }
-        if (valid) {
-          float4* co = reinterpret_cast<float4*>(a.c_out + srow + jb * 16);
-          float4* ho = reinterpret_cast<float4*>(a.h_out + srow + jb * 16);
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            co[e4] = make_float4(cn[4 * e4], cn[4 * e4 + 1], cn[4 * e4 + 2], cn[4 * e4 + 3]);
-            ho[e4] = make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
-          }
-        }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      // partial head sums of groups 1..NG-1: group 1 in sRed, groups 2, 3 (NT = 512) in the A tile, which is dead once
-      // the gate MMA has been committed; group 0 adds them in a fixed order (deterministic bits)
-      // behind the 64 KB copy-out staging when the A tile has room (72 KB at K = 288), else in its own 8 KB after sTmem
-      float* sRed2 = KC * 2048 >= 65536 + 8192 ? reinterpret_cast<float*>(sA + 65536) : reinterpret_cast<float*>(sTmem + 4);
-      if (half == 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
-      } else if (half > 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sRed2[((half - 2) * TC_M + row) * 8 + j] = lg[j];
-      }
-      __syncthreads();
-      PROF_MARK(5);    // cell + stores + head partial sums
-      if (half == 0 && valid) {
+      // partial head sums of groups 1..NG-1: group 1 in sRed, groups 2, 3 (NT = 512) in the A tile, which is dead once the
+      // gate MMA has been committed; group 0 adds them in a fixed order (deterministic bits)
+      float* sRed2 = reinterpret_cast<float*>(sA);
+      auto finish_heads = [&]() {
         if (NG == 2) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) lg[j] += sRed[row * 8 + j] + sBo[j];
@@ -923,12 +808,120 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         } else {
           a.val[(int64_t)r * d.A + ag] = lg[0];
         }
+      };
+#pragma unroll
+      for (int jb = 0; jb < HPT / 16; ++jb) {
+        float zi[16], zf[16], zo[16], zu[16];
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HPT + jb * 16);
+        tmem_ld16(tbase, zi); tmem_ld16(tbase + 64, zf); tmem_ld16(tbase + 128, zo); tmem_ld16(tbase + 192, zu);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a.zdbg && valid) {
+          float* z = a.zdbg + ((int64_t)u * ld + r) * TC_N + half * HPT + jb * 16;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { z[e] = zi[e]; z[64 + e] = zf[e]; z[128 + e] = zo[e]; z[192 + e] = zu[e]; }
+        }
+        float cprev[16];
+        if (valid && !a.done) {
+          const float* cp = a.c_in + srow + jb * 16;
+#pragma unroll
+          for (int e8 = 0; e8 < 2; ++e8) {      // 256-bit loads: one full sector per thread and instruction
+            uint32_t w[8];
+            asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                         : "l"(cp + 8 * e8));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cprev[8 * e8 + e] = __uint_as_float(w[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) cprev[e] = 0.f;
+        }
+        float cn[16], hn[16];
+        __align__(16) __nv_bfloat16 gbuf[4][16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int j = half * HPT + jb * 16 + e;
+          const float gi = sigm(zi[e] + sBias[j]), gf = sigm(zf[e] + sBias[64 + j]);
+          const float go = sigm(zo[e] + sBias[128 + j]), gu = tanh_fast(zu[e] + sBias[192 + j]);
+          cn[e] = gf * cprev[e] + gi * gu;
+          hn[e] = go * tanh_fast(cn[e]);
+          gbuf[0][e] = __float2bfloat16_rn(gi); gbuf[1][e] = __float2bfloat16_rn(gf);
+          gbuf[2][e] = __float2bfloat16_rn(go); gbuf[3][e] = __float2bfloat16_rn(gu);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) lg[jj] = fmaf(hn[e], sWo[j * 8 + jj], lg[jj]);
+        }
+        if constexpr (NT == 512) {
+          // Stores: a thread owns (row, 16 hidden units), i.e. 32-byte pieces of its row.  They leave as 256-bit stores
+          // (STG.256: one full 32-byte sector per thread and instruction, 14 instructions per thread and tile) straight
+          // from the registers, interleaved with the other warps' cell math.  Measured alternatives: 16-byte row-owner
+          // stores (28 half-sector instructions: the LSU was ~half of the kernel), a SIMT copy-out through XOR-swizzled
+          // shared memory (coalesced, but 4 staging passes with 8 block-wide barriers: 16 k cycles per tile) and the same
+          // passes handed to the copy engine row by row (cp.async.bulk, 128-512 B each: slower still).
+          auto st32 = [](void* p, const void* v) {
+            const uint4 x = reinterpret_cast<const uint4*>(v)[0], y = reinterpret_cast<const uint4*>(v)[1];
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w),
+                         "r"(y.x), "r"(y.y), "r"(y.z), "r"(y.w) : "memory");
+          };
+          if (valid) {
+            if (a.st_g) {
+              const int64_t m = store_row(row);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) st32(a.st_g + m * TC_N + g * 64 + half * HPT, &gbuf[g][0]);
+              __align__(32) __nv_bfloat16 cb[16], hb[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { cb[e] = __float2bfloat16_rn(cn[e]); hb[e] = __float2bfloat16_rn(hn[e]); }
+              st32(a.st_c + m * TC_H + half * HPT, cb);
+              st32(a.st_h + m * TC_H + half * HPT, hb);
+            }
+            float* co = a.c_out + srow;
+            float* ho = a.h_out + srow;
+            st32(co, cn); st32(co + 8, cn + 8);
+            st32(ho, hn); st32(ho + 8, hn + 8);
+          }
+        } else {
+        if (valid && a.st_g) {
+          const int64_t m = store_row((int)(r - r0));
+          const int jo = half * HPT + jb * 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4* o = reinterpret_cast<uint4*>(a.st_g + m * TC_N + g * 64 + jo);
+            o[0] = *reinterpret_cast<const uint4*>(&gbuf[g][0]); o[1] = *reinterpret_cast<const uint4*>(&gbuf[g][8]);
+          }
+          __align__(16) __nv_bfloat16 cb[16], hb[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { cb[e] = __float2bfloat16_rn(cn[e]); hb[e] = __float2bfloat16_rn(hn[e]); }
+          uint4* oc = reinterpret_cast<uint4*>(a.st_c + m * TC_H + jo);
+          uint4* oh = reinterpret_cast<uint4*>(a.st_h + m * TC_H + jo);
+          oc[0] = *reinterpret_cast<const uint4*>(cb); oc[1] = *reinterpret_cast<const uint4*>(cb + 8);
+          oh[0] = *reinterpret_cast<const uint4*>(hb); oh[1] = *reinterpret_cast<const uint4*>(hb + 8);
+        }
+        if (valid) {
+          float4* co = reinterpret_cast<float4*>(a.c_out + srow + jb * 16);
+          float4* ho = reinterpret_cast<float4*>(a.h_out + srow + jb * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            co[e4] = make_float4(cn[4 * e4], cn[4 * e4 + 1], cn[4 * e4 + 2], cn[4 * e4 + 3]);
+            ho[e4] = make_float4(hn[4 * e4], hn[4 * e4 + 1], hn[4 * e4 + 2], hn[4 * e4 + 3]);
+          }
+        }
+        }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (half == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sRed[row * 8 + j] = lg[j];
+      } else if (half > 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sRed2[((half - 2) * TC_M + row) * 8 + j] = lg[j];
+      }
+      __syncthreads();
+      PROF_MARK(5);    // cell + stores + head partial sums
+      if (half == 0 && valid) finish_heads();
     }
   }
   PROF_MARK(6);        // head softmax / sampling of the last item
   if (PROF && tid == 0)
-    for (int i = 0; i < 7; ++i) atomicAdd(a.prof + i, (unsigned long long)pt[i]);
+    for (int i = 0; i < 16; ++i) atomicAdd(a.prof + i, (unsigned long long)pt[i]);
 #undef PROF_MARK
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -1263,7 +1256,7 @@ static size_t tc3_smem_bytes(int K) {
 
 static size_t tc2_smem_bytes(int K) {
   const int KC = K / 8;
-  return (size_t)KC * 4096 + (size_t)KC * 2048 + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + 32;
+  return (size_t)KC * 4096 + tc2_a_bytes(K) + (TC_M * 8 + TC_H * 8 + 8 + TC_N + TC_N) * 4 + 32;
 }
 
 static unsigned long long* g_policy_prof = nullptr;
@@ -1284,8 +1277,8 @@ extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const v
   if ((d.dx % 32) != 0 || d.dx > 256) return tsc_set_error("tscl_policy_step_v2r: dx must be a multiple of 32, <= 256");
   if (d.kw == 0) return tsc_set_error("tscl_policy_step_v2r: observation slice does not fit the 64-column input tile");
   if (8 * d.dx * 16 > (d.dx / 8) * 2048) return tsc_set_error("tscl_policy_step_v2r: fc operand does not fit its staging region");
-  const bool wide_tile = (size_t)(K / 8) * 2048 >= 65536;   // the A tile doubles as the 64 KB copy-out staging of the epilogue
-  const size_t smem = tc2_smem_bytes(K) + ((size_t)(K / 8) * 2048 >= 65536 + 8192 ? 0 : 8192);
+  const bool wide_tile = d.dx <= 224;   // NT = 512: the A-tile region doubles as the copy-out staging (X pitch dx * 2 + 16 <= 464 B)
+  const size_t smem = tc2_smem_bytes(K);
   if (smem > 232448) return tsc_set_error("tscl_policy_step_v2r: operand tiles exceed shared memory");
   static int attr_dev = -1;
   if (attr_dev != tscl_device_of(h)) {

@@ -571,7 +571,10 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       return ((c * (2 * d.A) + u) * a.T + a.t) * a.rc + rin;
     };
     const __nv_bfloat16* Wu = a.Wp + (int64_t)u * wp_stride(d.dx);
-    __syncthreads();      // previous tile fully retired (sRed, sA, TMEM readers)
+    // NT = 512: no block-wide barrier here.  Warps 0-3 may still be in the previous tile's head softmax / sampling (they read
+    // sRed, sRed2 = sA + 32 KB, sBo) while warps 4-15 already fetch and stage this tile's observation slice (last 8 chunks
+    // of sA) and the fc-weight block (first 28 KB of sA); the barrier after the staging retires the previous tile.
+    if (NT != 512 || u != cur_u) __syncthreads();      // previous tile fully retired (sRed, sA, sBo, TMEM readers)
     if (u != cur_u) {
       cur_u = u;
       const uint4* src = reinterpret_cast<const uint4*>(Wu);
@@ -619,8 +622,10 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     {
       // fc weights (one contiguous 8 * dx * 16-byte block of the packed image) by ONE bulk copy (TMA unit, completion on
       // bar_fc): it overlaps the observation staging below; only the MMA-issuing thread waits for it
-      if (tid == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the epilogue's staging stores precede this async write
+      // NT = 512: the copy for every tile but the CTA's first was issued right after the previous tile's gate MMA had
+      // completed (the whole epilogue hides its ~3 k cycles)
+      if (tid == NT - 1 && (NT != 512 || it == it_lo)) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy stores to the A tile precede this async write
         mbar_expect_tx(bar_fc, (uint32_t)(8 * d.dx * 16));
         bulk_g2s(aA, reinterpret_cast<const unsigned char*>(Wu + (int64_t)KC * TC_N * 8), (uint32_t)(8 * d.dx * 16), bar_fc);
       }
@@ -629,19 +634,26 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
         // resolved when the unit changed).  The slice of a row is one contiguous <= 256 B run of the observation vector, so
         // a warp load touches 2-3 sectors of ONE row (the former thread = (row, chunk) mapping touched 32 rows per
         // instruction: 8 k sector requests per tile, the whole staging phase); the two values leave as one packed store.
-        float xa[8], xb[8];
+        // warps 4-15 share the 128 rows (11 each); warps 0-3 finish the previous tile's heads meanwhile
+        if (warp >= 4) {
+          const int rb = (warp - 4) * 11;
+          float xa[11], xb[11];
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int64_t r = r0 + warp * 8 + rr;
-          const float* op = a.obs + (r < a.R ? r : 0) * d.n_obs + ooff;
-          xa[rr] = (src_a >= 0 && r < a.R) ? __ldg(op + src_a) : 0.f;
-          xb[rr] = (src_b >= 0 && r < a.R) ? __ldg(op + src_b) : 0.f;
-        }
+          for (int rr = 0; rr < 11; ++rr) {
+            const int64_t r = r0 + rb + rr;
+            const bool ok = rb + rr < TC_M && r < a.R;
+            const float* op = a.obs + (ok ? r : 0) * d.n_obs + ooff;
+            xa[rr] = (src_a >= 0 && ok) ? __ldg(op + src_a) : 0.f;
+            xb[rr] = (src_b >= 0 && ok) ? __ldg(op + src_b) : 0.f;
+          }
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int row = warp * 8 + rr;
-          const __nv_bfloat162 v = __floats2bfloat162_rn(xa[rr], xb[rr]);
-          *reinterpret_cast<__nv_bfloat162*>(sA + (size_t)(KC - 8 + (lane >> 2)) * 2048 + row * 16 + (lane & 3) * 4) = v;
+          for (int rr = 0; rr < 11; ++rr) {
+            const int row = rb + rr;
+            if (row < TC_M) {
+              const __nv_bfloat162 v = __floats2bfloat162_rn(xa[rr], xb[rr]);
+              *reinterpret_cast<__nv_bfloat162*>(sA + (size_t)(KC - 8 + (lane >> 2)) * 2048 + row * 16 + (lane & 3) * 4) = v;
+            }
+          }
         }
       } else {
         // thread = (row, 16-byte chunk) : 128 x 8 pairs, 4 per thread
@@ -684,6 +696,15 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       __syncwarp();
     }
     par_fc ^= 1;
+    // h_{t-1} of this thread's (row, hidden-unit group): requested before the MMA wait, staged after the relu epilogue
+    float4 hpre[HPT / 4];
+    {
+      const int64_t r = r0 + tid / NG;
+      const bool live = r < a.R && !a.done;
+      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * ld + (r < a.R ? r : 0)) * TC_H + (tid % NG) * HPT);
+#pragma unroll
+      for (int i = 0; i < HPT / 4; ++i) hpre[i] = live ? hp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -727,14 +748,10 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
     }
     {
       const int row = tid / NG, half = tid % NG;      // `half` = hidden-unit group of HPT units
-      const int64_t r = r0 + row;
-      const bool live = r < a.R && !a.done;
-      const float4* hp = reinterpret_cast<const float4*>(a.h_in + ((int64_t)u * ld + (r < a.R ? r : 0)) * TC_H + half * HPT);
 #pragma unroll
       for (int c8 = 0; c8 < HPT / 8; ++c8) {
         __align__(16) __nv_bfloat16 v[8];
-        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-        if (live) { x0 = hp[2 * c8]; x1 = hp[2 * c8 + 1]; }
+        const float4 x0 = hpre[2 * c8], x1 = hpre[2 * c8 + 1];
         v[0] = __float2bfloat16_rn(x0.x); v[1] = __float2bfloat16_rn(x0.y); v[2] = __float2bfloat16_rn(x0.z); v[3] = __float2bfloat16_rn(x0.w);
         v[4] = __float2bfloat16_rn(x1.x); v[5] = __float2bfloat16_rn(x1.y); v[6] = __float2bfloat16_rn(x1.z); v[7] = __float2bfloat16_rn(x1.w);
         *reinterpret_cast<uint4*>(sA + (size_t)(KCX + half * (HPT / 8) + c8) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
@@ -755,9 +772,36 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       }
       __syncwarp();
     }
+    float cpre[16];        // c_{t-1} of this thread's 16 hidden units (NT = 512): in flight while the gate MMA runs
+    if constexpr (NT == 512) {
+      const int64_t r = r0 + (warp & 3) * 32 + lane;
+      if (r < a.R && !a.done) {
+        const float* cp = a.c_in + ((int64_t)u * ld + r) * TC_H + (warp >> 2) * HPT;
+#pragma unroll
+        for (int e8 = 0; e8 < 2; ++e8) {      // 256-bit loads: one full sector per thread and instruction
+          uint32_t w[8];
+          asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                       : "l"(cp + 8 * e8));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cpre[8 * e8 + e] = __uint_as_float(w[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) cpre[e] = 0.f;
+      }
+    }
     mbar_wait(bar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (NT == 512 && tid == NT - 1 && it + 1 < it_hi) {
+      // the A tile is dead: fetch the NEXT tile's fc-weight block now (its unit may differ)
+      const int un = (int)((it + 1) / n_tiles);
+      const __nv_bfloat16* Wn = a.Wp + (int64_t)un * wp_stride(d.dx);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar_fc, (uint32_t)(8 * d.dx * 16));
+      bulk_g2s(aA, reinterpret_cast<const unsigned char*>(Wn + (int64_t)KC * TC_N * 8), (uint32_t)(8 * d.dx * 16), bar_fc);
+    }
     PROF_MARK(4);      // gate MMA issue + wait
     // ---- 5. epilogue (identical to v1) ----
     {
@@ -771,7 +815,7 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
       for (int j = 0; j < 8; ++j) lg[j] = 0.f;
       // partial head sums of groups 1..NG-1: group 1 in sRed, groups 2, 3 (NT = 512) in the A tile, which is dead once the
       // gate MMA has been committed; group 0 adds them in a fixed order (deterministic bits)
-      float* sRed2 = reinterpret_cast<float*>(sA);
+      float* sRed2 = reinterpret_cast<float*>(sA + 32768);      // behind the fc-weight block, before the observation chunks
       auto finish_heads = [&]() {
         if (NG == 2) {
 #pragma unroll
@@ -821,16 +865,15 @@ policy_step_tc2_kernel(const DDimsTC d, const StepTC a) {
           for (int e = 0; e < 16; ++e) { z[e] = zi[e]; z[64 + e] = zf[e]; z[128 + e] = zo[e]; z[192 + e] = zu[e]; }
         }
         float cprev[16];
-        if (valid && !a.done) {
-          const float* cp = a.c_in + srow + jb * 16;
+        if constexpr (NT == 512) {
 #pragma unroll
-          for (int e8 = 0; e8 < 2; ++e8) {      // 256-bit loads: one full sector per thread and instruction
-            uint32_t w[8];
-            asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                         : "l"(cp + 8 * e8));
+          for (int e = 0; e < 16; ++e) cprev[e] = cpre[e];
+        } else if (valid && !a.done) {
+          const float4* cp = reinterpret_cast<const float4*>(a.c_in + srow + jb * 16);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) cprev[8 * e8 + e] = __uint_as_float(w[e]);
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 x = cp[e4];
+            cprev[4 * e4] = x.x; cprev[4 * e4 + 1] = x.y; cprev[4 * e4 + 2] = x.z; cprev[4 * e4 + 3] = x.w;
           }
         } else {
 #pragma unroll

@@ -329,23 +329,26 @@ __global__ void returns_kernel(const float* __restrict__ rew, const float* __res
 // (rows staged in smem, thread = (hidden unit k, 4 logits); one atomic per output per CTA), and `dlog` may be null.
 // `Hb`: read H from one chunk of the bf16 activation store instead of the fp32 buffer.
 #define HL_GX 96
-#define HL_LD 65
+#define HL_LD 68                       // row pitch in floats: 16-byte aligned rows, conflict-free 128-bit row-owner accesses
+#define HL_DL 12                       // dlog (8) | dv | pad
+// Shared-memory traffic bounds this kernel (ncu: short scoreboard 6.3, mio throttle 3.3 per issue): rows and the head
+// weights are therefore moved with 128-bit accesses only (Wp padded to 8 logits per hidden unit = two broadcast loads).
 __global__ void __launch_bounds__(128)
 heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __restrict__ Hm,
                   const __nv_bfloat16* __restrict__ Hb, const int32_t* __restrict__ act, const float* __restrict__ Rs,
                   const float* __restrict__ Adv, int64_t M, int64_t Rc, int64_t stride_t, float v_coef, float beta,
                   float scale, float* __restrict__ dlog, float* __restrict__ dH, float* __restrict__ stats,
                   float* __restrict__ G) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int a = blockIdx.y, tid = threadIdx.x, na = d.n_a[a], mna = d.max_na;
-  float* sWp = sm;
-  float* sWv = sWp + H64 * mna;
-  float* sb = sWv + H64;
-  float* sH = sb + 16;                 // [128][HL_LD] rows of H (policy unit, then value unit)
-  float* sdl = sH + 128 * HL_LD;       // [128][9] dlog (8) + dv
+  float* sWp = sm;                     // [64][8]
+  float* sWv = sWp + H64 * 8;          // [64]
+  float* sb = sWv + H64;               // [16]
+  float* sH = sb + 16;                 // [128][HL_LD] rows of H (value unit, then policy unit)
+  float* sdl = sH + 128 * HL_LD;       // [128][HL_DL]
   const float* Wp = P + d.off_wo + (int64_t)(2 * a) * H64 * mna;
   const float* Wv = P + d.off_wo + (int64_t)(2 * a + 1) * H64 * mna;
-  for (int i = tid; i < H64 * mna; i += 128) sWp[i] = Wp[i];
+  for (int i = tid; i < H64 * 8; i += 128) { const int k = i >> 3, j = i & 7; sWp[i] = j < mna ? Wp[k * mna + j] : 0.f; }
   for (int i = tid; i < H64; i += 128) sWv[i] = Wv[i * mna];
   for (int i = tid; i < mna; i += 128) sb[i] = P[d.off_bo + (int64_t)(2 * a) * mna + i];
   if (tid == 0) sb[mna] = P[d.off_bo + (int64_t)(2 * a + 1) * mna];
@@ -354,27 +357,32 @@ heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __res
   float accp[4] = {0.f, 0.f, 0.f, 0.f}, accv = 0.f, accb = 0.f;
   const int kk = tid & 63, hh = tid >> 6;
   const int64_t n_tiles = (M + 127) / 128;
-  float* myH = sH + tid * HL_LD;
+  float4* myH4 = reinterpret_cast<float4*>(sH + tid * HL_LD);
+  const float4* sWp4 = reinterpret_cast<const float4*>(sWp);
+  const float4* sWv4 = reinterpret_cast<const float4*>(sWv);
   auto load_row = [&](int64_t off) {       // one row of H (64 values) -> this thread's smem row
     if (Hb) {
       const uint4* p4 = reinterpret_cast<const uint4*>(Hb + off);
+      uint4 x[H64 / 8];
+#pragma unroll
+      for (int k8 = 0; k8 < H64 / 8; ++k8) x[k8] = __ldg(p4 + k8);
 #pragma unroll
       for (int k8 = 0; k8 < H64 / 8; ++k8) {
-        const uint4 x = __ldg(p4 + k8);
-        const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          myH[k8 * 8 + 2 * e] = __uint_as_float(xw[e] << 16); myH[k8 * 8 + 2 * e + 1] = __uint_as_float(xw[e] & 0xffff0000u);
-        }
+        myH4[2 * k8] = make_float4(__uint_as_float(x[k8].x << 16), __uint_as_float(x[k8].x & 0xffff0000u),
+                                   __uint_as_float(x[k8].y << 16), __uint_as_float(x[k8].y & 0xffff0000u));
+        myH4[2 * k8 + 1] = make_float4(__uint_as_float(x[k8].z << 16), __uint_as_float(x[k8].z & 0xffff0000u),
+                                       __uint_as_float(x[k8].w << 16), __uint_as_float(x[k8].w & 0xffff0000u));
       }
     } else {
       const float4* p4 = reinterpret_cast<const float4*>(Hm + off);
 #pragma unroll
-      for (int k4 = 0; k4 < H64 / 4; ++k4) {
-        const float4 x = __ldg(p4 + k4);
-        myH[4 * k4] = x.x; myH[4 * k4 + 1] = x.y; myH[4 * k4 + 2] = x.z; myH[4 * k4 + 3] = x.w;
-      }
+      for (int k4 = 0; k4 < H64 / 4; ++k4) myH4[k4] = __ldg(p4 + k4);
     }
+  };
+  auto st8 = [](float* p, const float* v) {      // 256-bit store: one full sector per thread and instruction
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
   };
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t m = tile * 128 + tid;
@@ -387,20 +395,26 @@ heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __res
     if (valid) {
       load_row(ov);
       v = sb[mna]; ret = Rs[io];
-#pragma unroll 16
-      for (int k = 0; k < H64; ++k) v = fmaf(myH[k], sWv[k], v);
-      dv = scale * v_coef * (v - ret);
-      float4* dhv = reinterpret_cast<float4*>(dH + ov);
 #pragma unroll
-      for (int k4 = 0; k4 < H64 / 4; ++k4)
-        dhv[k4] = make_float4(dv * sWv[4 * k4], dv * sWv[4 * k4 + 1], dv * sWv[4 * k4 + 2], dv * sWv[4 * k4 + 3]);
+      for (int k4 = 0; k4 < H64 / 4; ++k4) {
+        const float4 x = myH4[k4], w = sWv4[k4];
+        v = fmaf(x.x, w.x, v); v = fmaf(x.y, w.y, v); v = fmaf(x.z, w.z, v); v = fmaf(x.w, w.w, v);
+      }
+      dv = scale * v_coef * (v - ret);
+#pragma unroll
+      for (int k8 = 0; k8 < H64 / 8; ++k8) {
+        const float4 w0 = sWv4[2 * k8], w1 = sWv4[2 * k8 + 1];
+        const float o[8] = {dv * w0.x, dv * w0.y, dv * w0.z, dv * w0.w, dv * w1.x, dv * w1.y, dv * w1.z, dv * w1.w};
+        st8(dH + ov + 8 * k8, o);
+      }
     } else {
-      for (int k = 0; k < H64; ++k) myH[k] = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < H64 / 4; ++k4) myH4[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    sdl[tid * 9 + 8] = dv;
+    sdl[tid * HL_DL + 8] = dv;
     if (G) {
       __syncthreads();
-      if (hh == 0) for (int row = 0; row < 128; ++row) accv = fmaf(sH[row * HL_LD + kk], sdl[row * 9 + 8], accv);
+      if (hh == 0) for (int row = 0; row < 128; ++row) accv = fmaf(sH[row * HL_LD + kk], sdl[row * HL_DL + 8], accv);
       __syncthreads();
     }
     // ---- policy unit ----
@@ -412,12 +426,17 @@ heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __res
       float lg[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) lg[j] = j < mna ? sb[j] : 0.f;
-#pragma unroll 8
-      for (int k = 0; k < H64; ++k) {
-        const float x = myH[k];
+#pragma unroll 4
+      for (int k4 = 0; k4 < H64 / 4; ++k4) {
+        const float4 x4 = myH4[k4];
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < mna) lg[j] = fmaf(x, sWp[k * mna + j], lg[j]);
+        for (int e = 0; e < 4; ++e) {
+          const float4 w0 = sWp4[2 * (4 * k4 + e)], w1 = sWp4[2 * (4 * k4 + e) + 1];
+          lg[0] = fmaf(xs[e], w0.x, lg[0]); lg[1] = fmaf(xs[e], w0.y, lg[1]); lg[2] = fmaf(xs[e], w0.z, lg[2]);
+          lg[3] = fmaf(xs[e], w0.w, lg[3]); lg[4] = fmaf(xs[e], w1.x, lg[4]); lg[5] = fmaf(xs[e], w1.y, lg[5]);
+          lg[6] = fmaf(xs[e], w1.z, lg[6]); lg[7] = fmaf(xs[e], w1.w, lg[7]);
+        }
       }
       float mx = -1e30f;
 #pragma unroll
@@ -447,19 +466,18 @@ heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __res
 #pragma unroll
         for (int j = 0; j < 8; ++j) if (j < mna) { dlp[j] = dl[j]; dlv[j] = j == 0 ? dv : 0.f; }
       }
-      float4* dhp = reinterpret_cast<float4*>(dH + op);
-#pragma unroll 4
-      for (int k4 = 0; k4 < H64 / 4; ++k4) {
-        float o[4];
+#pragma unroll 2
+      for (int k8 = 0; k8 < H64 / 8; ++k8) {
+        float o[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = k4 * 4 + e;
+        for (int e = 0; e < 8; ++e) {
+          const float4 w0 = sWp4[2 * (8 * k8 + e)], w1 = sWp4[2 * (8 * k8 + e) + 1];
           float t = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) if (j < mna) t = fmaf(dl[j], sWp[k * mna + j], t);
+          t = fmaf(dl[0], w0.x, t); t = fmaf(dl[1], w0.y, t); t = fmaf(dl[2], w0.z, t); t = fmaf(dl[3], w0.w, t);
+          t = fmaf(dl[4], w1.x, t); t = fmaf(dl[5], w1.y, t); t = fmaf(dl[6], w1.z, t); t = fmaf(dl[7], w1.w, t);
           o[e] = t;
         }
-        dhp[k4] = make_float4(o[0], o[1], o[2], o[3]);
+        st8(dH + op + 8 * k8, o);
       }
       if (a == 0) {
 #pragma unroll
@@ -468,19 +486,21 @@ heads_loss_kernel(const DDims d, const float* __restrict__ P, const float* __res
         el += -beta * ent;
       }
     } else {
-      for (int k = 0; k < H64; ++k) myH[k] = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < H64 / 4; ++k4) myH4[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (G) {      // head weight gradients of this tile: thread = (hidden unit kk, 4 logits)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sdl[tid * 9 + j] = dl[j];
+      *reinterpret_cast<float4*>(sdl + tid * HL_DL) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+      *reinterpret_cast<float4*>(sdl + tid * HL_DL + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
       __syncthreads();
+#pragma unroll 8
       for (int row = 0; row < 128; ++row) {
         const float x = sH[row * HL_LD + kk];
-        const float* q = sdl + row * 9 + hh * 4;
-        accp[0] = fmaf(x, q[0], accp[0]); accp[1] = fmaf(x, q[1], accp[1]);
-        accp[2] = fmaf(x, q[2], accp[2]); accp[3] = fmaf(x, q[3], accp[3]);
+        const float4 q = *reinterpret_cast<const float4*>(sdl + row * HL_DL + hh * 4);
+        accp[0] = fmaf(x, q.x, accp[0]); accp[1] = fmaf(x, q.y, accp[1]);
+        accp[2] = fmaf(x, q.z, accp[2]); accp[3] = fmaf(x, q.w, accp[3]);
       }
-      if (tid < 9) for (int row = 0; row < 128; ++row) accb += sdl[row * 9 + tid];
+      if (tid < 9) for (int row = 0; row < 128; ++row) accb += sdl[row * HL_DL + tid];
     }
   }
   if (G) {
@@ -1087,7 +1107,7 @@ extern "C" int tscl_heads_loss(tscl_handle* h, const float* params, const float*
   LCK(cudaSetDevice(h->device));
   const int64_t n_tiles = (M + 127) / 128;
   dim3 grid((unsigned)(grads ? (n_tiles < HL_GX ? n_tiles : HL_GX) : n_tiles), h->d.A);
-  const int smem = (H64 * h->d.max_na + H64 + 16 + 128 * HL_LD + 128 * 9) * 4;
+  const int smem = (H64 * 8 + H64 + 16 + 128 * HL_LD + 128 * HL_DL) * 4;
   heads_loss_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(h->d, params, H, (const __nv_bfloat16*)h_bf16, act, Rs, Adv,
                                                                M, Rc, stride_t, v_coef, beta, scale, dlog, dH, stats, grads);
   LCK(cudaGetLastError());

@@ -1731,6 +1731,7 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
       __syncthreads();                              // step t's tile is in shared memory
       const unsigned char* cT = sC0 + (t & 1) * 16384;
       const unsigned char* cP = sC0 + ((t - 1) & 1) * 16384;
+      uint4 zpk[4][NSUB];
 #pragma unroll
       for (int jb = 0; jb < NSUB; ++jb) {
         const int jo = jq + jb * 8;
@@ -1786,7 +1787,15 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(srcs[g][e]);
           *reinterpret_cast<uint4*>(sA + (size_t)((g * 64 + jo) >> 3) * 2048 + row * 16) = *reinterpret_cast<const uint4*>(v);
-          if (valid) *reinterpret_cast<uint4*>(a.dZb + m * TC_N + g * 64 + jo) = *reinterpret_cast<const uint4*>(v);
+          zpk[g][jb] = *reinterpret_cast<const uint4*>(v);
+        }
+      }
+      if (valid) {      // dZ of this thread's 16 hidden units: one 256-bit store (a full sector) per gate
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 x = zpk[g][0], y = zpk[g][1];
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(a.dZb + m * TC_N + g * 64 + jq), "r"(x.x),
+                       "r"(x.y), "r"(x.z), "r"(x.w), "r"(y.x), "r"(y.y), "r"(y.z), "r"(y.w) : "memory");
         }
       }
       if (keep != 0.f && t > 0) {

@@ -394,20 +394,24 @@ def main():
                 def timed(self, _o=cls.synchronize):
                     t_ = time.perf_counter(); _o(self); wait_s[0] += time.perf_counter() - t_
                 cls.synchronize = timed
-        # three back-to-back windows of one rollout + one update each; the MEDIAN window is reported (the host side of
-        # this loop is sensitive to whatever else the lease's cores are doing; all three are listed in the JSON line)
+        # seven back-to-back windows of one rollout + one update each; the MEDIAN window is reported (the host side of this
+        # loop is sensitive to whatever else the lease's cores are doing: single windows were seen to take 2-5x as long on a
+        # shared host; all seven are listed in the JSON line)
         e2e_windows = []
-        for w in range(3):
+        import gc
+        gc.collect(); gc.disable()             # no collector pauses inside the host-timed windows
+        for w in range(7):
             barrier()
             t0 = time.perf_counter()
             for i in range(e2e_steps):
                 host_step()
             barrier()
             e2e_windows.append((time.perf_counter() - t0) * 1e3)
-        e2e_ms = sorted(e2e_windows)[1]
+        gc.enable()
+        e2e_ms = sorted(e2e_windows)[3]
         if os.environ.get("TSC_E2E_PROFILE"):
             print("e2e host loop: %.3f ms/step, %.3f ms/step blocked in Event/Stream.synchronize" %
-                  (e2e_ms / e2e_steps, wait_s[0] * 1e3 / (3 * e2e_steps)), file=sys.stderr)
+                  (e2e_ms / e2e_steps, wait_s[0] * 1e3 / (7 * e2e_steps)), file=sys.stderr)
         h2d = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4
         d2h = R * net.n_nodes * 4 + R * net.n_nodes * net.max_na * 4 + R * net.n_obs * 4 + R * net.n_nodes * 4 + R * 4 + R
         e2e_api = ("BatchedTrainer.control_step_host: policy forward on device, actions+fingerprints D2H, "
@@ -416,7 +420,7 @@ def main():
             e2e_api = ("BatchedTrainer.control_step_host_pipelined: %d replica ranges, one stream each; per range: policy "
                        "forward (tscl_policy_step_v2r), actions+fingerprints D2H to pinned host buffers, "
                        "tsc_step_host_range (H2D, kernel, D2H, host sync), obs+reward H2D into the learner (tscl_host_transition); "
-                       "median of three windows; update "
+                       "median of seven windows; update "
                        "every %d steps" % (args.e2e_parts, n_step))
     else:
         e2e_steps = max(3, min(args.steps, 20))

@@ -158,16 +158,20 @@ class BatchedA2C:
         for t in (self.c_fw, self.h_fw, self.c_bw, self.h_bw):
             t.zero_()
 
-    def forward(self, obs: torch.Tensor, done: bool, out_type: str = "pv", sample: bool = True):
+    def forward(self, obs: torch.Tensor, done: bool, out_type: str = "pv", sample: bool = True, to_hist: bool = False):
         """One decision for all replicas/agents.  obs [R, n_obs] device tensor.  Returns
-        (pi [R, A, max_na], val [R, A], act [R, A] or None); 'v' does not advance the state."""
+        (pi [R, A, max_na], val [R, A], act [R, A] or None); 'v' does not advance the state.
+        `to_hist` (fused tensor-core forward only): values / actions are written straight into the rollout slots
+        val_hist[t] / act_hist[t] (what add_transition would copy there); those views are returned."""
         L, R, lib = self.lay, self.R, _lib.lib()
         commit = "p" in out_type
         want_act = sample and commit
+        to_hist = to_hist and self.use_tc and self.tc_v2 and want_act and self.t < self.T
+        val_o, act_o = (self.val_hist[self.t], self.act_hist[self.t]) if to_hist else (self.val, self.act)
         if self.use_tc:
             c1, h1 = (self.c_fw, self.h_fw) if commit else (self.c_tmp, self.h_tmp)
             args = (self._h, _p(self.P), _p(self.Wp), _p(obs), C.c_int64(R), _p(self.c_fw), _p(self.h_fw), _p(c1),
-                    _p(h1), _p(self.pi), _p(self.val), _p(self.act) if want_act else None,
+                    _p(h1), _p(self.pi), _p(val_o), _p(act_o) if want_act else None,
                     C.c_int32(1 if done else 0), C.c_uint64(self.seed), C.c_int64(self.n_forward),
                     C.c_int64(self.replica0), None)
             if self.tc_v2:
@@ -182,7 +186,8 @@ class BatchedA2C:
             self.kernel_launches += 1
             if commit:
                 self.n_forward += 1
-            return self.pi, self.val, (self.act if want_act else None)
+            self._hist_direct = to_hist
+            return self.pi, val_o, (act_o if want_act else None)
         self._mm()
         dflag = self._one.fill_(1.0 if done else 0.0)
         _lib.check(lib.tscl_fc_embed(self._h, _p(self.P), _p(obs), C.c_int64(R), C.c_int64(R), C.c_int64(0),
@@ -267,6 +272,22 @@ class BatchedA2C:
         self.rew_hist[t].copy_(r)
         self.act_hist[t].copy_(self.act if act is None else act)
         self.val_hist[t].copy_(self.val if val is None else val)
+        self.done_pre[t] = 1.0 if done_pre else 0.0
+        self.done_post[t] = 1.0 if done_post else 0.0
+        self.t += 1
+
+    def add_transition_device(self, reward: torch.Tensor, greward: torch.Tensor, rew_acc: torch.Tensor, done_pre: bool,
+                              done_post: bool):
+        """add_transition() of the device-resident loop in ONE launch: normalised / clipped reward into the rollout slot
+        and the episode sum of the global reward; actions / values are already in their slots when the last forward ran
+        with to_hist=True (copied otherwise).  Same arithmetic as add_transition (r * (1 / norm), clamp)."""
+        t = self.t
+        _lib.check(_lib.lib().tscl_device_transition(
+            self._h, _p(reward), _p(self.rew_hist[t]), C.c_int64(reward.numel()), C.c_float(self.reward_norm or 0.0),
+            C.c_float(self.reward_clip or 0.0), _p(greward), _p(rew_acc), C.c_int64(greward.numel()), self._st()))
+        if not getattr(self, "_hist_direct", False):
+            self.act_hist[t].copy_(self.act)
+            self.val_hist[t].copy_(self.val)
         self.done_pre[t] = 1.0 if done_pre else 0.0
         self.done_post[t] = 1.0 if done_post else 0.0
         self.t += 1

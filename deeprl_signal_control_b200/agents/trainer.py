@@ -71,7 +71,8 @@ class BatchedTrainer:
         """One control step of all replicas (utils.py:146-165)."""
         sim, m = self.sim, self.model
         t = m.t
-        pi, val, act = m.forward(m.obs_slot(t), self.done)
+        fused = bool(getattr(m, 'tc_v2', False))      # fused tensor-core forward: one-launch transition hand-over
+        pi, val, act = m.forward(m.obs_slot(t), self.done, to_hist=True) if fused else m.forward(m.obs_slot(t), self.done)
         fp = pi if self.agent == 'ma2c' else None                 # env.update_fingerprint(policy)
         if self.sim_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -82,8 +83,11 @@ class BatchedTrainer:
             self.sim_events.append((e0, e1))
         self.step_in_episode += 1
         new_done = self.step_in_episode >= self.T_episode         # lock-step: envs/env.py:577-579
-        m.add_transition(reward, self.done, new_done)
-        self._rew_acc.add_(greward)
+        if fused:
+            m.add_transition_device(reward, greward, self._rew_acc, self.done, new_done)
+        else:
+            m.add_transition(reward, self.done, new_done)
+            self._rew_acc.add_(greward)
         self.done = new_done
         self.n_env_steps += 1
         if m.t == m.T:

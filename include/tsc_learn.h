@@ -154,6 +154,10 @@ int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, float* ZG, cons
 int tscl_host_transition(tscl_handle* h, const float* obs_host, float* obs_dev, int64_t obs_floats, const float* rew_host,
                          float* rew_stage_dev, float* rew_hist_dev, int64_t rew_floats, float reward_norm, float reward_clip,
                          const float* grew_host, float* grew_stage_dev, float* rew_acc_dev, int64_t n, void* stream);
+/* Same hand-over with the rewards already on the device (the device-resident loop): rew_hist_dev = clip(rew_dev /
+ * reward_norm), rew_acc_dev += grew_dev, one launch. */
+int tscl_device_transition(tscl_handle* h, const float* rew_dev, float* rew_hist_dev, int64_t rew_floats, float reward_norm,
+                           float reward_clip, const float* grew_dev, float* rew_acc_dev, int64_t n, void* stream);
 /* cudaMemcpyAsync on a caller-supplied stream; kind 1 = host->device, 2 = device->host, 3 = device->device */
 int tscl_memcpy_async(tscl_handle* h, void* dst, const void* src, int64_t bytes, int32_t kind, void* stream);
 /* dX = dZ . Wx^T as a stand-alone streaming product (the shipping path; reference: tf.gradients through

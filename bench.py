@@ -77,7 +77,8 @@ def parse():
     p.add_argument("--replicas", type=int, default=None, help="env replicas per GPU (default 8192 grid / 2048 Monaco)")
     p.add_argument("--burnin", type=int, default=240)
     p.add_argument("--mode", default=None, choices=[None, "sim", "train"])
-    p.add_argument("--chunk", type=int, default=1024, help="replicas per BPTT chunk in the update")
+    p.add_argument("--chunk", type=int, default=4096,
+                   help="replicas per update chunk (4096: 1600 BPTT work items = 10.8 waves of 148 CTAs; 1024: 2.7 waves)")
     p.add_argument("--fp32-gemm", action="store_true", help="plain fp32 (no TF32 tensor cores) in the learner GEMMs")
     p.add_argument("--seed", type=int, default=12)
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -496,9 +497,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl, "scenario": args.scenario, "replicas_per_gpu": R, "agents": net.n_nodes,
                        "burnin_control_steps": args.burnin, "mode": mode, "n_step": n_step,
-                       "updates_in_timed_region": n_updates_timed, "untimed_alignment_steps": align_steps,
-                       "learner_gemm_library": "own tcgen05 kernels for the forward, BPTT and all weight gradients; cuBLAS "
-                                               "bf16 only for dX = dZ.Wx^T (1 plain batched GEMM per update chunk)"
+                       "updates_in_timed_region": n_updates_timed, "update_chunk_replicas": args.chunk, "untimed_alignment_steps": align_steps,
+                       "learner_gemm_library": "none: own tcgen05 kernels for the forward, BPTT, dX and all weight gradients; "
+                                               "own SIMT kernels for loss / heads / optimizer"
                        if mode == "train" else None,
                        "l2": "inputs larger than L2: %.0f MB of replica state per GPU is streamed every step"
                              % (R * sim.info()["state_bytes_per_replica"] / 1e6),

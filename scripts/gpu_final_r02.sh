@@ -16,11 +16,17 @@ LLR=8192 bash scripts/gpu_ll.sh > gpurun_out/r02f_launches_train_summary.txt 2>&
 ncu --set full --clock-control none --import-source on -k regex:policy_step_tc2 -s 300 -c 1 -o gpurun_out/r02f_prof_policy -f \
     python bench.py --steps 4 --warmup 3 --burnin 240 --no-cpu-baseline > gpurun_out/r02f_ncu_policy.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:lstm_bwd_tc_staged -c 1 -o gpurun_out/r02f_prof_bptt -f \
-    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 > gpurun_out/r02f_ncu_bptt.log 2>&1
+    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 --chunk 1024 > gpurun_out/r02f_ncu_bptt.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:dx_tc_kernel -c 1 -o gpurun_out/r02f_prof_dx -f \
-    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 > gpurun_out/r02f_ncu_dx.log 2>&1
+    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 --chunk 1024 > gpurun_out/r02f_ncu_dx.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc -c 1 -o gpurun_out/r02f_prof_wgrad -f \
-    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 > gpurun_out/r02f_ncu_wgrad.log 2>&1
+    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 --chunk 1024 > gpurun_out/r02f_ncu_wgrad.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:heads_loss -c 1 -o gpurun_out/r02f_prof_heads -f \
+    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 --chunk 1024 > gpurun_out/r02f_ncu_heads.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fc_bwd_tc -c 1 -o gpurun_out/r02f_prof_fcbwd -f \
+    python bench.py --steps 121 --warmup 3 --burnin 0 --no-cpu-baseline --replicas 2048 --chunk 1024 > gpurun_out/r02f_ncu_fcbwd.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tsc_step -s 245 -c 1 -o gpurun_out/r02f_prof_sim -f \
+    python bench.py --mode sim --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r02f_ncu_sim.log 2>&1
 python - <<'PY'
 import json
 for f in ["n1_train","default","driver_window","real_net","reference_arm","sim","ia2c_fc_1024","ia2c_lstm_1024"]:

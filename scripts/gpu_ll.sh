@@ -1,5 +1,5 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1200 -c 900 --csv --log-file gpurun_out/ll.csv \
-    python bench.py --replicas ${LLR:-2048} --burnin 120 --steps 121 --warmup 3 --no-cpu-baseline > gpurun_out/ll.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s ${LLS:-130} -c ${LLC:-745} --csv --log-file gpurun_out/ll.csv \
+    python bench.py --replicas ${LLR:-2048} --burnin 120 --steps 121 --warmup 3 --no-cpu-baseline --profile-run > gpurun_out/ll.log 2>&1
 python - <<'PY'
 import csv, collections
 rows=list(csv.reader(open('gpurun_out/ll.csv')))

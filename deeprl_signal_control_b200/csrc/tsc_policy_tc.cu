@@ -1305,6 +1305,8 @@ static size_t tc2_smem_bytes(int K) {
 static unsigned long long* g_policy_prof = nullptr;
 // tools only: device pointer to 8 uint64 counters that receive per-phase clock64 sums of the v2 kernel (NULL = off)
 extern "C" int tscl_debug_policy_prof(void* counters_dev) { g_policy_prof = (unsigned long long*)counters_dev; return 0; }
+static unsigned long long* g_bptt_prof = nullptr;
+extern "C" int tscl_debug_bptt_prof(void* counters_dev) { g_bptt_prof = (unsigned long long*)counters_dev; return 0; }
 
 extern "C" int tscl_policy_step_v2r(tscl_handle* h, const float* params, const void* wpack_bf16, const float* obs,
                                    int64_t R, const float* c_in, const float* h_in, float* c_out, float* h_out,
@@ -1418,6 +1420,7 @@ struct BwdTC {
   const __nv_bfloat16* Cb;   //           ([2A][T*Rc][256] / [..][64]); when set, ZG is write-only and C is unused
   __nv_bfloat16* dZb;        // optional: dZ as bf16 [2A][T*Rc][256] (operand of the tensor-core weight-gradient kernels);
                              //           ZG may then be null (needs Gb / Cb)
+  unsigned long long* prof;  // optional: 8 phase counters of the staged kernel (tscl_debug_bptt_prof)
 };
 
 // NT = 512: thread = (replica row, 16 hidden units), one CTA per SM.
@@ -1639,10 +1642,13 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+template <bool PROF>
 __global__ void __launch_bounds__(512, 1)
 lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
   constexpr int NT = 512, HPT = 16, NSUB = 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long bp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
+#define BP_MARK(i) do { if (PROF && tid == 0) { const long long c_ = clock64(); bp[i] += c_ - pc; pc = c_; } } while (0)
   unsigned char* sB = tc_smem;                       // 32 KB : Wh^T image
   unsigned char* sA = sB + BW_KC * 1024;             // 64 KB : dz tile (A operand)
   uint64_t* sBar = reinterpret_cast<uint64_t*>(sA + BW_KC * 2048);
@@ -1718,6 +1724,7 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
     float dc[HPT], dhc[HPT];
 #pragma unroll
     for (int e = 0; e < HPT; ++e) { dc[e] = 0.f; dhc[e] = 0.f; }
+    if (PROF && tid == 0) pc = clock64();
     for (int t = a.T - 1; t >= 0; --t) {
       const float keep = 1.0f - a.done[t];
       const int64_t m = ((int64_t)u * a.T + t) * a.Rc + (valid ? r : 0);
@@ -1729,6 +1736,7 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();                              // step t's tile is in shared memory
+      BP_MARK(0);                                   // waiting for step t's operands
       const unsigned char* cT = sC0 + (t & 1) * 16384;
       const unsigned char* cP = sC0 + ((t - 1) & 1) * 16384;
       uint4 zpk[4][NSUB];
@@ -1764,8 +1772,11 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
           }
         }
         if (jb == NSUB - 1) {      // every thread holds its last operands: the staging buffers can take step t-1
+          BP_MARK(5);              // shared memory -> registers (both sub-batches) + first sub-batch's math and stores
           __syncthreads();
+          BP_MARK(6);              // barrier: staging buffers free
           if (t > 0) fetch(t - 1, false);
+          BP_MARK(7);              // cp.async issue of step t-1
         }
         float dzi[8], dzf[8], dzo[8], dzu[8];
 #pragma unroll
@@ -1798,10 +1809,12 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
                        "r"(x.y), "r"(x.z), "r"(x.w), "r"(y.x), "r"(y.y), "r"(y.z), "r"(y.w) : "memory");
         }
       }
+      BP_MARK(1);                                   // second sub-batch: cell backward, dZ stores
       if (keep != 0.f && t > 0) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        BP_MARK(2);                                 // barrier before the MMA
         if (warp == 0) {
           if (lane == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1815,17 +1828,22 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
         mbar_wait(bar, parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        BP_MARK(3);                                 // MMA issue + commit + wait
         float dhp[HPT];
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)jq, dhp);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int e = 0; e < HPT; ++e) dhc[e] = dhp[e] * keep;
+        BP_MARK(4);                                 // TMEM read-back
       } else {
 #pragma unroll
         for (int e = 0; e < HPT; ++e) dhc[e] = 0.f;
       }
     }
   }
+  if (PROF && tid == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(a.prof + i, (unsigned long long)bp[i]);
+#undef BP_MARK
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -1896,11 +1914,14 @@ extern "C" int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, floa
     const size_t smem_s = BW_KC * 1024 + BW_KC * 2048 + 16 + 128 * 512 + 2 * 128 * 128 + 128 * 256;
     static int attr_s = -1;
     if (attr_s != tscl_device_of(h)) {
-      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
       attr_s = tscl_device_of(h);
     }
     const int grid_s = (int)(n_items < n_sm ? n_items : n_sm);
-    lstm_bwd_tc_staged_kernel<<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a);
+    a.prof = g_bptt_prof;
+    if (a.prof) lstm_bwd_tc_staged_kernel<true><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a);
+    else lstm_bwd_tc_staged_kernel<false><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a);
   } else if (bw_threads == 512) lstm_bwd_tc_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
   else lstm_bwd_tc_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());

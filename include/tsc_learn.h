@@ -179,6 +179,9 @@ int tscl_unpack_store(tscl_handle* h, const void* st_x, const void* st_g, const 
 /* Tools only (scripts/profile_policy_phases.py): per-phase clock64 sums of tscl_policy_step_v2 are added to 8 uint64
  * device counters while the pointer is set (NULL = off; a separate instantiation of the kernel, the hot one is unchanged). */
 int tscl_debug_policy_prof(void* counters_dev);
+/* same for the staged BPTT kernel: 8 counters (operand wait | smem->regs + cell backward + dZ stores | barrier | MMA + wait |
+ * TMEM read-back), summed over CTAs; NULL switches profiling off */
+int tscl_debug_bptt_prof(void* counters_dev);
 
 /* Per-agent clip_by_global_norm(max_norm) + RMSProp step (TF1 semantics).  agent_of [n_params] u8.
  * norms [A] receives the pre-clip global norms. */

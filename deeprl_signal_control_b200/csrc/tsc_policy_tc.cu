@@ -16,6 +16,7 @@
 // Operand layouts (bytes, 16-byte "core rows", no swizzle; cute canonical ((8,n),2):((1,SBO),LBO)):
 //   A tile  [KC][128 rows][16 B]   : LBO = 2048 (next K chunk of 8 bf16), SBO = 128 (next 8 rows)
 //   B tile  [KC][256 cols][16 B]   : LBO = 4096,                          SBO = 128
+#include <cuda.h>
 #include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -1642,27 +1643,33 @@ lstm_bwd_tc_kernel(const DDimsTC d, const BwdTC a) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-template <bool PROF>
+// TMA = true: the per-step operand tile (gates 64 KB, dH 32 KB, c 16 KB) arrives by SEVEN cp.async.bulk.tensor copies issued
+// by one thread (hardware 128-byte swizzle = the pattern the readers use) instead of 14 cp.async per thread: the phase
+// profile showed the issue of those 7168 16-byte copies blocking every warp for 7.9 k of the 17 k cycles of a step.
+template <bool PROF, bool TMA>
 __global__ void __launch_bounds__(512, 1)
-lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
+lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a, const __grid_constant__ CUtensorMap mapG,
+                          const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD) {
   constexpr int NT = 512, HPT = 16, NSUB = 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long bp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
 #define BP_MARK(i) do { if (PROF && tid == 0) { const long long c_ = clock64(); bp[i] += c_ - pc; pc = c_; } } while (0)
   unsigned char* sB = tc_smem;                       // 32 KB : Wh^T image
   unsigned char* sA = sB + BW_KC * 1024;             // 64 KB : dz tile (A operand)
-  uint64_t* sBar = reinterpret_cast<uint64_t*>(sA + BW_KC * 2048);
-  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 1);
-  unsigned char* sG = sA + BW_KC * 2048 + 16;        // 64 KB : gates [128][32 chunks ^ (row & 31)]
+  unsigned char* sG = sA + BW_KC * 2048;             // 64 KB : gates [128][32 chunks ^ (row & 31)]   (1024-byte aligned)
+                                                     //         TMA: 4 boxes [128 rows][8 chunks ^ (row & 7)], one per gate
   unsigned char* sC0 = sG + 128 * 512;               // 16 KB x 2 : c ring, [128][8 chunks ^ (row & 7)]
-  unsigned char* sD = sC0 + 2 * 128 * 128;           // 32 KB : dH fp32 [128][16 chunks ^ (row & 15)]
-  const uint32_t bar = smem_u32(sBar);
+  unsigned char* sD = sC0 + 2 * 128 * 128;           // 32 KB : dH fp32 [128][16 chunks ^ (row & 15)]; TMA: 2 boxes of 32 floats
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(sD + 128 * 256);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(sBar + 2);
+  const uint32_t bar = smem_u32(sBar), ldbar = bar + 8;
+  uint32_t ldpar = 0;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(64));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar, 1); mbar_init(ldbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1698,6 +1705,22 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
     // coalesced fetch of one step's tile: rows beyond Rc are clamped to a valid row (their results are never stored)
     auto fetch = [&](int t, bool with_c_t) {
       const int64_t mb = ((int64_t)u * a.T + t) * a.Rc;            // row index of replica 0 at step t
+      if constexpr (TMA) {
+        if (tid == 0) {       // rows past the end of the tensors are zero-filled; rows past Rc belong to other tiles and are never stored
+          auto tma2d = [&](uint32_t dst, const CUtensorMap* mp, int x, int64_t y) {
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(mp)), "r"(x), "r"((int)y), "r"(ldbar) : "memory");
+          };
+          const int64_t y = mb + rt0;
+          mbar_expect_tx(ldbar, (uint32_t)(65536 + 32768 + (with_c_t ? 16384 : 0) + (t > 0 ? 16384 : 0)));
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tma2d(aG + g * 16384, &mapG, g * 64, y);
+          tma2d(aD, &mapD, 0, y); tma2d(aD + 16384, &mapD, 32, y);
+          if (with_c_t) tma2d(aC + (t & 1) * 16384, &mapC, 0, y);
+          if (t > 0) tma2d(aC + ((t - 1) & 1) * 16384, &mapC, 0, y - a.Rc);
+        }
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {                                // gates: 128 rows x 32 chunks
         const int id = i * NT + tid, rw = id >> 5, c = id & 31;
@@ -1728,14 +1751,18 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
     for (int t = a.T - 1; t >= 0; --t) {
       const float keep = 1.0f - a.done[t];
       const int64_t m = ((int64_t)u * a.T + t) * a.Rc + (valid ? r : 0);
-      if (t > 1) {      // pull step t-2's operands towards L2: they are fetched into shared memory during step t-1
+      if (!TMA && t > 1) {      // pull step t-2's operands towards L2: they are fetched into shared memory during step t-1
         const int64_t mp = ((int64_t)u * a.T + t - 2) * a.Rc + (valid ? r : 0);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Gb + mp * TC_N + qt * 64));
         if (qt == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Cb + mp * TC_H));
         if (qt >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dH + mp * TC_H + (qt - 2) * 32));
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();                              // step t's tile is in shared memory
+      if constexpr (TMA) {
+        mbar_wait(ldbar, ldpar); ldpar ^= 1;          // step t's tile has landed (complete_tx of all its copies)
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                            // step t's tile is in shared memory
+      }
       BP_MARK(0);                                   // waiting for step t's operands
       const unsigned char* cT = sC0 + (t & 1) * 16384;
       const unsigned char* cP = sC0 + ((t - 1) & 1) * 16384;
@@ -1746,10 +1773,18 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
         float gi[8], gf[8], go[8], gu[8], ct[8], cp[8], dh[8];
         {
           const int cg = jo >> 3, sw = row & 31;     // chunk of 8 hidden units inside each 64-wide gate block
+          if constexpr (TMA) {
+            const unsigned char* gp = sG + row * 128 + ((cg ^ (row & 7)) << 4);
+            bf8(*reinterpret_cast<const uint4*>(gp), gi);
+            bf8(*reinterpret_cast<const uint4*>(gp + 16384), gf);
+            bf8(*reinterpret_cast<const uint4*>(gp + 32768), go);
+            bf8(*reinterpret_cast<const uint4*>(gp + 49152), gu);
+          } else {
           bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((cg) ^ sw) << 4)), gi);
           bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((8 + cg) ^ sw) << 4)), gf);
           bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((16 + cg) ^ sw) << 4)), go);
           bf8(*reinterpret_cast<const uint4*>(sG + row * 512 + (((24 + cg) ^ sw) << 4)), gu);
+          }
           bf8(*reinterpret_cast<const uint4*>(cT + row * 128 + ((cg ^ (row & 7)) << 4)), ct);
           if (t > 0) bf8(*reinterpret_cast<const uint4*>(cP + row * 128 + ((cg ^ (row & 7)) << 4)), cp);
           else if (valid) {
@@ -1761,8 +1796,10 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
             for (int e = 0; e < 8; ++e) cp[e] = 0.f;
           }
           const int cd = jo >> 2;                    // dH: 4 floats per chunk
-          const float4 d0 = *reinterpret_cast<const float4*>(sD + row * 256 + ((cd ^ (row & 15)) << 4));
-          const float4 d1 = *reinterpret_cast<const float4*>(sD + row * 256 + (((cd + 1) ^ (row & 15)) << 4));
+          const float4 d0 = TMA ? *reinterpret_cast<const float4*>(sD + (cd >> 3) * 16384 + row * 128 + (((cd & 7) ^ (row & 7)) << 4))
+                                : *reinterpret_cast<const float4*>(sD + row * 256 + ((cd ^ (row & 15)) << 4));
+          const float4 d1 = TMA ? *reinterpret_cast<const float4*>(sD + (cd >> 3) * 16384 + row * 128 + ((((cd + 1) & 7) ^ (row & 7)) << 4))
+                                : *reinterpret_cast<const float4*>(sD + row * 256 + (((cd + 1) ^ (row & 15)) << 4));
           dh[0] = d0.x; dh[1] = d0.y; dh[2] = d0.z; dh[3] = d0.w; dh[4] = d1.x; dh[5] = d1.y; dh[6] = d1.z; dh[7] = d1.w;
 #pragma unroll
           for (int e = 0; e < 8; ++e) cp[e] *= keep;
@@ -1850,6 +1887,29 @@ lstm_bwd_tc_staged_kernel(const DDimsTC d, const BwdTC a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
 }
 
+// 2-D tiled tensor map (row-major [rows][cols], box = box_cols x box_rows, inner box = 128 bytes, 128-byte swizzle) through the
+// driver entry point (no link-time dependency on libcuda)
+static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
+                         uint32_t box_cols, uint32_t box_rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = []() -> encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (encode_fn)p;
+  }();
+  if (!fn || !base) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  return fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int tscl_pack_wxt(tscl_handle* h, const float* params, void* wxt_bf16, void* stream) {
   if (!h || !params || !wxt_bf16) return tsc_set_error("tscl_pack_wxt: bad argument");
   PCK(cudaSetDevice(tscl_device_of(h)));
@@ -1911,17 +1971,33 @@ extern "C" int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, floa
   // staged variant (coalesced cp.async into swizzled shared memory one step ahead): store path without fused dX
   static const int bw_staged = []() { const char* e = getenv("TSC_BPTT_STAGED"); return e ? atoi(e) : 1; }();
   if (bw_staged && bw_threads == 512 && a.Gb && a.Cb && a.dZb && !a.ZG && !a.dXb) {
-    const size_t smem_s = BW_KC * 1024 + BW_KC * 2048 + 16 + 128 * 512 + 2 * 128 * 128 + 128 * 256;
+    const size_t smem_s = BW_KC * 1024 + BW_KC * 2048 + 128 * 512 + 2 * 128 * 128 + 128 * 256 + 32;
     static int attr_s = -1;
     if (attr_s != tscl_device_of(h)) {
-      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      PCK(cudaFuncSetAttribute(lstm_bwd_tc_staged_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
       attr_s = tscl_device_of(h);
     }
     const int grid_s = (int)(n_items < n_sm ? n_items : n_sm);
     a.prof = g_bptt_prof;
-    if (a.prof) lstm_bwd_tc_staged_kernel<true><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a);
-    else lstm_bwd_tc_staged_kernel<false><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a);
+    // operand tiles by TMA (tensor maps over this chunk's gate / c / dH arrays, 128-byte swizzle); TSC_BPTT_TMA=0: cp.async
+    static const int bw_tma = []() { const char* e = getenv("TSC_BPTT_TMA"); return e ? atoi(e) : 1; }();
+    CUtensorMap mG, mC, mD;
+    memset(&mG, 0, sizeof(mG)); memset(&mC, 0, sizeof(mC)); memset(&mD, 0, sizeof(mD));
+    const uint64_t rows = (uint64_t)2 * d.A * T * Rc;
+    const bool tma = bw_tma && rows < (1ull << 31) &&
+                     make_tmap_2d(&mG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gates_bf16, rows, TC_N, 64, 128) &&
+                     make_tmap_2d(&mC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c_bf16, rows, TC_H, 64, 128) &&
+                     make_tmap_2d(&mD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dH, rows, TC_H, 32, 128);
+    if (tma) {
+      if (a.prof) lstm_bwd_tc_staged_kernel<true, true><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a, mG, mC, mD);
+      else lstm_bwd_tc_staged_kernel<false, true><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a, mG, mC, mD);
+    } else {
+      if (a.prof) lstm_bwd_tc_staged_kernel<true, false><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a, mG, mC, mD);
+      else lstm_bwd_tc_staged_kernel<false, false><<<grid_s, 512, smem_s, (cudaStream_t)stream>>>(d, a, mG, mC, mD);
+    }
   } else if (bw_threads == 512) lstm_bwd_tc_kernel<512><<<grid, 512, smem, (cudaStream_t)stream>>>(d, a);
   else lstm_bwd_tc_kernel<256><<<grid, 256, smem, (cudaStream_t)stream>>>(d, a);
   PCK(cudaGetLastError());

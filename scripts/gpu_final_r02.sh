@@ -12,6 +12,8 @@ python bench.py --agent ia2c --policy fc --replicas 1024 --steps 120 --warmup 5 
 python bench.py --agent ia2c --replicas 1024 --steps 120 --warmup 5 --no-cpu-baseline > gpurun_out/r02f_bench_ia2c_lstm_1024.json 2>> gpurun_out/r02f_bench.err
 python scripts/profile_policy_phases.py > gpurun_out/r02f_policy_phases.log 2>&1
 python scripts/time_dx_kernel.py > gpurun_out/r02f_dx_kernel.log 2>&1
+python scripts/profile_bptt_phases.py > gpurun_out/r02f_bptt_phases.log 2>&1
+TSC_BPTT_TMA=0 python scripts/profile_bptt_phases.py > gpurun_out/r02f_bptt_phases_cpasync.log 2>&1
 LLR=8192 bash scripts/gpu_ll.sh > gpurun_out/r02f_launches_train_summary.txt 2>&1; cp gpurun_out/ll.csv gpurun_out/r02f_launches_train.csv
 ncu --set full --clock-control none --import-source on -k regex:policy_step_tc2 -s 300 -c 1 -o gpurun_out/r02f_prof_policy -f \
     python bench.py --steps 4 --warmup 3 --burnin 240 --no-cpu-baseline > gpurun_out/r02f_ncu_policy.log 2>&1

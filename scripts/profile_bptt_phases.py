@@ -34,7 +34,7 @@ n_items = 2 * lay.A * ((chunk + 127) // 128) * ((R + chunk - 1) // chunk)
 steps = n_items * 120 / 148
 print("BPTT: %.0f cycles per CTA per update (%.2f ms at 1.965 GHz), %.0f (tile, step) pairs per CTA = %.0f cycles each"
       % (tot, tot / 1.965e6, steps, tot / steps))
-for nm, v in zip(["wait for step t's operands (cp.async + barrier)", "smem -> regs, prefetch issue, cell backward, dZ stores",
+for nm, v in zip(["wait for step t's operands", "smem -> regs, prefetch issue, cell backward, dZ stores",
                   "fence + barrier before the MMA", "MMA issue + commit + wait", "TMEM read-back",
-                  "  (of phase 2) smem -> regs + first sub-batch", "  (of phase 2) barrier", "  (of phase 2) cp.async issue"], p):
+                  "  (of phase 2) smem -> regs + first sub-batch", "  (of phase 2) barrier", "  (of phase 2) operand issue (TMA / cp.async)"], p):
     print("   %-56s %9.0f cycles  %5.1f %%   %.0f per step" % (nm, v, 100 * v / tot, v / steps))

@@ -11,9 +11,13 @@ Device-side counterpart of reference agents/models.py (IA2C/MA2C) + agents/polic
 Replicas share the weights: the gradient is the mean over replicas (and over ranks: one
 `all_reduce(SUM)` of the flat gradient per update, then identical updates everywhere).
 
-Hand-written kernels (csrc/tsc_learn.cu) do the fc front end, the LSTM sequence forward/backward
-with the cell fused, heads + sampling, loss gradients, returns and clip+RMSProp.  The three plain
-batched GEMMs (X.Wx, dZ.Wx^T, [X|H]^T.dZ) go through cuBLAS (`torch.baddbmm/bmm`) this round.
+Shipping path (`use_tc`, the default): every kernel is hand-written — the fused tcgen05 forward
+(csrc/tsc_policy_tc.cu: fc front end, gate GEMM, LSTM cell, heads, sampling, bf16 activation store), the tcgen05
+update (BPTT with TMA operand copies, dX = dZ.Wx^T, LSTM and fc weight gradients) and the SIMT kernels of
+csrc/tsc_learn.cu (loss / head gradients, returns, clip + RMSProp).  No library GEMM runs on it.
+`use_tc=False` selects the plain fp32 twin kernels (fc_embed, lstm_seq_fwd / bwd, heads, fc_bwd) that the reference
+goldens pin at 2e-4; only on that path do the three plain batched products (X.Wx, dZ.Wx^T, [X|H]^T.dZ) go through
+`torch.baddbmm / bmm` (fp32, TF32 only when `allow_tf32`).
 """
 from __future__ import annotations
 
@@ -405,8 +409,8 @@ class BatchedA2C:
                 self.gv["wx"].baddbmm_(X.transpose(1, 2), dZ)
                 self.gv["wh"].baddbmm_(Hp.transpose(1, 2), dZ)
                 self.gv["bl"].add_(dZ.sum(dim=1))
-            # dX = dZ . Wx^T: fused into the BPTT kernel on the shipping path; a library GEMM only on the fp32 twin path
-            # (and for layouts whose dx is not a multiple of 32)
+            # dX = dZ . Wx^T: own warp-specialised tcgen05 kernel on the shipping path (tscl_dx_tc); a library GEMM only on
+            # the fp32 twin path, for dx > 224 and under TSC_DX_LIBRARY=1 (A/B measurements)
             if all_tc and not fuse_dx and self.dx_own:
                 _lib.check(lib.tscl_dx_tc(self._h, _p(dZb), _p(self.Wxt), _p(dXb), C.c_int64(M), st()))
             elif all_tc and not fuse_dx:

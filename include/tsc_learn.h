@@ -132,14 +132,18 @@ int tscl_wgrad_tc(tscl_handle* h, const float* dZ, const void* dz_bf16, const fl
 
 /* BPTT on the tensor cores (tcgen05): same contract as tscl_lstm_seq_bwd, with the recurrent product dz.Wh^T as
  * a bf16 MMA (M=128, N=64, K=256) per step; wt_bf16 [2A][32][64][8] comes from tscl_pack_wht (refresh after
- * every optimizer step). */
+ * every optimizer step).  With gates_bf16 / c_bf16 / dz_bf16 and ZG == NULL (the shipping call) the per-step operand tile
+ * of 128 replicas (gates, c, dH: 112 KB) is fetched one step ahead by cp.async.bulk.tensor copies through tensor maps
+ * built over the caller's arrays (cuTensorMapEncodeTiled via the driver entry point; TSC_BPTT_TMA=0 selects the
+ * cp.async variant); the arrays must be 16-byte aligned and hold 2A * T * Rc rows. */
 int tscl_pack_wht(tscl_handle* h, const float* params, void* wt_bf16, void* stream);
 int tscl_lstm_seq_bwd_tc(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH, const float* c0,
                          const float* done, int32_t T, int64_t Rc, int64_t ld_state, int64_t r0,
                          const void* gates_bf16, const void* c_bf16, void* dz_bf16, void* stream);
 /* The same kernel with dX = dZ . Wx^T fused into every step (second tcgen05 product of the same dz tile, M=128, N=dx,
  * K=256, accumulator in TMEM columns 64..64+dx): wxt_bf16 [2A][32][dx][8] from tscl_pack_wxt (refresh after every
- * optimizer step), dx_bf16 [2A][T*Rc][dx] receives dX as bf16 — this replaces the last library GEMM of the update
+ * optimizer step), dx_bf16 [2A][T*Rc][dx] receives dX as bf16 — one way of replacing the last library GEMM of the update
+ * (the shipping one is tscl_dx_tc below)
  * (reference: the tf.gradients chain through agents/utils.py:106, `tf.matmul(x, wx)`).  Both NULL = plain BPTT. */
 int tscl_pack_wxt(tscl_handle* h, const float* params, void* wxt_bf16, void* stream);
 int tscl_lstm_seq_bwd_tc_dx(tscl_handle* h, const void* wt_bf16, float* ZG, const float* C, const float* dH, const float* c0,

@@ -81,3 +81,42 @@ def test_nstep_returns_are_linear_and_match_closed_form():
     np.testing.assert_allclose(R1[8], r1[8] + gamma * b1, atol=1e-12)
     # a `done` cuts the bootstrap: R_7 = r_7 exactly
     np.testing.assert_allclose(R1[7], r1[7], atol=1e-12)
+
+
+def test_queue_discharge_headway_at_a_signal(tmp_path):
+    """Model-level check that needs no reference numbers: a standing queue released by a green signal discharges with
+    the Krauss car-following headway tau + (length + minGap) / v, i.e. one vehicle per ~2 s (about 1800 veh/h per lane)
+    for the reference's vType (accel 5, decel 10, sigma 0.5, tau 1, length 5, minGap 2.5) — the saturation flow SUMO users
+    quote for tau = 1.  (The gap to the reference's recorded congestion, DESIGN.md 2.2, is therefore not a stop-line
+    capacity error of a factor.)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures"))
+    import make_mini_sumo
+    from deeprl_signal_control_b200.net import sumo_ingest as ing
+    from deeprl_signal_control_b200.net.tables import EnvParams
+    from oracle.sim_ref import RefSim
+    old = make_mini_sumo.L_EDGE
+    make_mini_sumo.L_EDGE = 900.0                      # room for a 120-vehicle queue
+    try:
+        net_file, rou_file = make_mini_sumo.write(str(tmp_path))
+    finally:
+        make_mini_sumo.L_EDGE = old
+    with open(rou_file, "w") as f:
+        f.write('<routes>\n <vType id="car" length="5" accel="5" decel="10"/>\n <flow id="f0" from="W_A" to="B_E" via="A_B" '
+                'begin="0" end="3600" vehsPerHour="3600" type="car"/>\n</routes>\n')
+    net = ing.load_sumo_scenario(net_file, rou_file, agent="greedy", use_wait=True)
+    par = EnvParams(agent="greedy", episode_length_sec=3600, control_interval_sec=1, yellow_interval_sec=0)
+    sim = RefSim(net, par, 1)
+    sim.reset(np.array([3], np.uint64)); sim.set_train_mode(False)
+    l_ab = [i for i, nm in enumerate(net.lane_names) if nm.startswith("A_B")][0]
+    crossed = []
+    for sec in range(700):
+        sim.step(np.array([[0 if sec < 600 else 1, 1]], np.int32))       # west approach red for 600 s, then green
+        if sec >= 600:
+            cnt, _ = sim.dump_state(0)
+            crossed.append(int(cnt[l_ab]))              # nobody leaves A_B (909 m) within these 100 s
+    assert sim.misc(0)["live"] > 100                    # the queue was there
+    n20, n90 = crossed[20], crossed[90]
+    headway = 70.0 / (n90 - n20)
+    assert 1.6 <= headway <= 2.4, headway               # ~1800 veh/h per lane
